@@ -1,0 +1,144 @@
+/* libmultiverse_b200 - C ABI of the B200-native Multiverse ConvRNN hot path.
+ *
+ * The reference (JunweiLiang/Multiverse, code/pred_models.py) has no FFI: its device work is
+ * TensorFlow-1.15 op dispatch behind `sess.run` (pred_models.py:1732 train, :1779 test,
+ * multifuture_inference.py:471 K-way decode).  Each entry point below replaces the TF ops of one
+ * group of call sites; the citation on every function is the reference code it stands in for.
+ * INTEGRATION.md shows the ctypes binding (the reference is pure Python) a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current device
+ *     unless noted; the caller (PyTorch in this repo) owns all memory, nothing is allocated
+ *     or retained by the library; work is enqueued asynchronously on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - return 0 on success, non-zero on error; mvb_last_error() returns a thread-local message.
+ *   - activations use the library's "halo" layout: a grid of H x W cells is stored as
+ *     S = (H+1)*(W+1) rows per sample, row = y*(W+1)+x, the extra column/row are zeros that
+ *     the library never writes.  "planes" are the P bf16 summands of an fp32 value
+ *     (v = p0 + p1 (+ p2)); a plane tensor is [P][rows][cpad] bf16.
+ *   - NS is the number of sample rows (batch, or batch*beam); fp32 state tensors are
+ *     [NS*S, 256]; the hidden size is fixed at 256 (enc/dec_hidden_size of every published config).
+ */
+#ifndef MULTIVERSE_B200_H_
+#define MULTIVERSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* mvb_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int mvb_abi_version(void);
+/* Number of kernels this library has launched on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+long long mvb_launch_count(void);
+void mvb_reset_launch_count(void);
+
+/* ---- a1: ConvLSTM cell (tf.contrib.rnn.ConvLSTMCell built at pred_models.py:189-202,
+ *      :236-249; called through dynamic_rnn :212,:232 and raw_rnn :455,:678) -------------- */
+
+/* Channels per tap of the packed K dimension for an input of cx channels: roundup(cx,32)+256. */
+int mvb_cell_cpad(int cx);
+
+/* Pack a TF ConvLSTM `kernel` [3,3,cx+256,1024] (HWIO; gate order i,j,f,o) and `biases` [1024]
+ * (host layout of the TF variables, but resident on the device) into
+ *   w_planes   bf16 [P][1024][9*cpad]   (row = tile*256 + gate*64 + ch%64, K-major)
+ *   bias_packed fp32 [1024]             (same row order). */
+int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_planes,
+                          float* bias_packed, int cx, int planes, void* stream);
+
+/* One cell step over NS sample rows:  (c_in, xh) -> (c_out, h).
+ *   xh_planes  bf16 [P][NS*S][cpad]: concat([x (cx, zero-padded to roundup(cx,32)), h (256)])
+ *   c_in       fp32 [*,256] or NULL (zero state); row_map int32 [NS] (source sample row of c_in
+ *              for each sample row - the beam search's parent gather, pred_models.py:611-623) or NULL
+ *   c_out      fp32 [NS*S,256];  h32_out fp32 [NS*S,256] or NULL
+ *   hp_out     bf16 planes of h written at channel offset ch_off_out of rows with pitch cpad_out
+ *              (the h block of the NEXT step's xh), plane stride hp_plane_stride elements; or NULL
+ * Semantics: g = conv3x3_SAME(concat[x,h]) + biases; i,j,f,o = split(g);
+ *   c' = sigmoid(f+forget_bias)*c + sigmoid(i)*tanh(j);  h' = tanh(c')*sigmoid(o). */
+int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const float* bias_packed,
+                          const float* c_in, const int32_t* row_map, float* c_out, float* h32_out,
+                          void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
+                          int64_t NS, int H, int W, int cpad, int planes, float forget_bias,
+                          void* stream);
+
+/* ---- layout conversion at the API boundary (placeholders are NHWC, pred_models.py:62-115) */
+
+/* fp32 NHWC [NS,H,W,C] -> bf16 planes written at channel offset ch_off of halo rows (pitch cpad). */
+int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,
+                       int ch_off, int64_t NS, int H, int W, int C, int planes, void* stream);
+/* fp32 NHWC [NS,H,W,C] <-> fp32 halo [NS*S, C] (halo cells are left untouched / skipped). */
+int mvb_nhwc_to_halo(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream);
+int mvb_halo_to_nhwc(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream);
+
+/* ---- a3/k11: class-encoder input, scene_conv (.) one_hot(obs cell) (pred_models.py:210) ---
+ * Writes the single non-zero pixel of step t into the x block (channels [0,64)) of xh and
+ * clears the pixel written two steps earlier into the same buffer.
+ *   scene_conv fp32 [F,H,W,64] (per unique frame), frame_idx int32 [NS] (obs_scene[:,t]),
+ *   label int32 [NS] (grid_obs_labels[:,t]), prev_label int32 [NS] or NULL. */
+int mvb_enc_class_input(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                        const int32_t* prev_label, void* xh_planes, int64_t plane_stride, int cpad,
+                        int64_t NS, int H, int W, int planes, void* stream);
+
+/* ---- a4: scene CNN (pred_models.py:146-165; conv2d helper :1333-1373) ------------------
+ * out = tanh(conv3x3 stride 2 SAME(in, W) + b), fp32 NHWC; TF SAME padding. */
+int mvb_scene_conv_fwd(const float* in, const float* W, const float* b, float* out, int64_t F,
+                       int IH, int IW, int Cin, int Cout, void* stream);
+/* scene_mean[n] = mean_t scene_conv[frame_idx[n,t]]  (gnn_edge, pred_models.py:826-828). */
+int mvb_scene_time_mean(const float* scene_conv, const int32_t* frame_idx, float* out, int64_t N,
+                        int T, int64_t HWC, void* stream);
+
+/* ---- a7-a9: graph attention (gnn_edge :808-858, gnn_mask_edge :885-909, gnn_node :860-882,
+ *      residual :378/:651):  h' = h + softmax_{q in N3x3(p)}(cos(F_p,F_q)) . h_q,
+ *      F = [h ; scene_mean].  Reads fp32 h (halo; sample row row_map[s] if given - the beam
+ *      parent gather), writes the bf16 planes of h' into the h block of the next xh. */
+int mvb_gnn_attend_fwd(const float* h32, const int32_t* row_map, const float* scene_mean,
+                       int beam, void* hp_out, int64_t hp_plane_stride, int cpad_out,
+                       int ch_off_out, int64_t NS, int H, int W, int planes, void* stream);
+
+/* ---- a10/a11 + argmax: heads (hidden2grid :925-959, grid_emb :912-919, argmax/one_hot
+ *      :411-415) ---------------------------------------------------------------------------
+ * Class head: logits[s, HW] = conv3x3(h, Wo[3,3,256,1]); ids[s] = argmax (first index on ties);
+ * if xh_next: x block <- planes of tanh(conv3x3(one_hot(ids), We[3,3,1,E]) + be).
+ *   logits_out fp32 [NS,HW] (standard row-major cells); ids_out int32 [NS] or NULL. */
+int mvb_head_class_fwd(const float* h32, const float* Wo, float* logits_out, int32_t* ids_out,
+                       const float* We, const float* be, int E, void* xh_next,
+                       int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                       void* stream);
+/* Regression head: off[s,HW,2] = conv3x3(h, Wo[3,3,256,2]);
+ * if xh_next: x block <- planes of tanh(conv3x3(off, We[3,3,2,E]) + be). */
+int mvb_head_reg_fwd(const float* h32, const float* Wo, float* off_out, const float* We,
+                     const float* be, int E, void* xh_next, int64_t plane_stride, int cpad,
+                     int64_t NS, int H, int W, int planes, void* stream);
+/* x block <- planes of tanh(conv3x3(one_hot(ids), We) + be) for given ids (decoder step 0 and
+ * the beam search's chosen cells, pred_models.py:602-606, :662-666). */
+int mvb_emb_onehot_fwd(const int32_t* ids, const float* We, const float* be, int E, void* xh_next,
+                       int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                       void* stream);
+/* x block <- planes of tanh(conv3x3(x, We[3,3,2,E]) + be) for a dense NHWC fp32 input [NS,H,W,2]
+ * (regression decoder step 0, pred_models.py:386-387, :442-446). */
+int mvb_emb_dense_fwd(const float* x, const float* We, const float* be, int E, void* xh_next,
+                      int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                      void* stream);
+
+/* ---- a6: beam step (pred_models.py:547-606; add_div_penalty :1197-1223) ------------------
+ * Per sample n over its B beams: lp = log_softmax(logits) + score; optional
+ * lp += log(gamma) * rank_within_row(lp); candidates = all B*V (first_step: beam 0 only);
+ * top-B (descending, ties -> lower flat index); score' (zeroed if zero_scores);
+ * ids = idx % V; parents = idx / V; row_map_out[n*B+b] = n*B + parents (for the state gather). */
+int mvb_beam_step(const float* logits, const float* score_in, float* score_out, int32_t* ids_out,
+                  int32_t* parents_out, int32_t* row_map_out, int64_t N, int B, int V,
+                  int first_step, int zero_scores, int diverse, float log_gamma, void* stream);
+/* Back-trace (pred_models.py:689-764): step_ids/step_parents int32 [Tp,N,B], step_logits fp32
+ * [Tp,N,B,V] -> out_ids int32 [N,B,Tp], out_logits fp32 [N,B,Tp,V]. */
+int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
+                       const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,
+                       int B, int Tp, int V, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIVERSE_B200_H_ */

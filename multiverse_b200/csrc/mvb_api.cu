@@ -1,0 +1,169 @@
+// extern "C" surface of libmultiverse_b200 (declared in include/multiverse_b200.h) plus the
+// host-side plumbing shared by the kernels: error string, launch counter, TMA descriptor encode.
+#include "mvb_common.cuh"
+#include "mvb_kernels.h"
+#include "../../include/multiverse_b200.h"
+
+#include <string.h>
+
+namespace mvb {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+void count_launch(int n) { g_launches += n; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s",
+              cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                        uint32_t b2, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MVB_ERR_DRIVER;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu box %u,%u,%u)",
+              (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0,
+              b1, b2);
+    return MVB_ERR_DRIVER;
+  }
+  return MVB_OK;
+}
+
+}  // namespace mvb
+
+using namespace mvb;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* mvb_last_error(void) { return get_error(); }
+int mvb_abi_version(void) { return 1; }
+long long mvb_launch_count(void) { return g_launches; }
+void mvb_reset_launch_count(void) { g_launches = 0; }
+
+int mvb_cell_cpad(int cx) { return (cx + 31) / 32 * 32 + kHidden; }
+
+int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_planes,
+                          float* bias_packed, int cx, int planes, void* stream) {
+  return pack_cell_weights(kernel, biases, w_planes, bias_packed, cx, planes, S(stream));
+}
+
+int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const float* bias_packed,
+                          const float* c_in, const int32_t* row_map, float* c_out, float* h32_out,
+                          void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
+                          int64_t NS, int H, int W, int cpad, int planes, float forget_bias,
+                          void* stream) {
+  return cell_fwd(xh_planes, w_planes, bias_packed, c_in, row_map, c_out, h32_out, hp_out,
+                  hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
+                  S(stream));
+}
+
+int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,
+                       int ch_off, int64_t NS, int H, int W, int C, int planes, void* stream) {
+  return nhwc_to_planes(src, dst_planes, plane_stride, cpad, ch_off, NS, H, W, C, planes, S(stream));
+}
+int mvb_nhwc_to_halo(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream) {
+  return nhwc_halo_copy(src, dst, NS, H, W, C, 0, S(stream));
+}
+int mvb_halo_to_nhwc(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream) {
+  return nhwc_halo_copy(src, dst, NS, H, W, C, 1, S(stream));
+}
+
+int mvb_enc_class_input(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                        const int32_t* prev_label, void* xh_planes, int64_t plane_stride, int cpad,
+                        int64_t NS, int H, int W, int planes, void* stream) {
+  return enc_class_input(scene_conv, frame_idx, label, prev_label, xh_planes, plane_stride, cpad,
+                         NS, H, W, planes, S(stream));
+}
+
+int mvb_scene_conv_fwd(const float* in, const float* W, const float* b, float* out, int64_t F,
+                       int IH, int IW, int Cin, int Cout, void* stream) {
+  return scene_conv_fwd(in, W, b, out, F, IH, IW, Cin, Cout, S(stream));
+}
+int mvb_scene_time_mean(const float* scene_conv, const int32_t* frame_idx, float* out, int64_t N,
+                        int T, int64_t HWC, void* stream) {
+  return scene_time_mean(scene_conv, frame_idx, out, N, T, HWC, S(stream));
+}
+
+int mvb_gnn_attend_fwd(const float* h32, const int32_t* row_map, const float* scene_mean,
+                       int beam, void* hp_out, int64_t hp_plane_stride, int cpad_out,
+                       int ch_off_out, int64_t NS, int H, int W, int planes, void* stream) {
+  return gnn_attend_fwd(h32, row_map, scene_mean, beam, hp_out, hp_plane_stride, cpad_out,
+                        ch_off_out, NS, H, W, planes, S(stream));
+}
+
+int mvb_head_class_fwd(const float* h32, const float* Wo, float* logits_out, int32_t* ids_out,
+                       const float* We, const float* be, int E, void* xh_next,
+                       int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                       void* stream) {
+  return head_fwd(h32, Wo, 1, logits_out, ids_out, We, be, E, xh_next, plane_stride, cpad, NS, H,
+                  W, planes, S(stream));
+}
+int mvb_head_reg_fwd(const float* h32, const float* Wo, float* off_out, const float* We,
+                     const float* be, int E, void* xh_next, int64_t plane_stride, int cpad,
+                     int64_t NS, int H, int W, int planes, void* stream) {
+  return head_fwd(h32, Wo, 2, off_out, nullptr, We, be, E, xh_next, plane_stride, cpad, NS, H, W,
+                  planes, S(stream));
+}
+int mvb_emb_onehot_fwd(const int32_t* ids, const float* We, const float* be, int E, void* xh_next,
+                       int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                       void* stream) {
+  return emb_onehot_fwd(ids, We, be, E, xh_next, plane_stride, cpad, NS, H, W, planes, S(stream));
+}
+int mvb_emb_dense_fwd(const float* x, const float* We, const float* be, int E, void* xh_next,
+                      int64_t plane_stride, int cpad, int64_t NS, int H, int W, int planes,
+                      void* stream) {
+  return emb_dense_fwd(x, We, be, E, xh_next, plane_stride, cpad, NS, H, W, planes, S(stream));
+}
+
+int mvb_beam_step(const float* logits, const float* score_in, float* score_out, int32_t* ids_out,
+                  int32_t* parents_out, int32_t* row_map_out, int64_t N, int B, int V,
+                  int first_step, int zero_scores, int diverse, float log_gamma, void* stream) {
+  return beam_step(logits, score_in, score_out, ids_out, parents_out, row_map_out, N, B, V,
+                   first_step, zero_scores, diverse, log_gamma, S(stream));
+}
+int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
+                       const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,
+                       int B, int Tp, int V, void* stream) {
+  return beam_backtrace(step_ids, step_parents, step_logits, out_ids, out_logits, N, B, Tp, V,
+                        S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// K-cell: the fused ConvLSTM cell of the Multiverse encoder/decoder.
+//
+// Replaces, per call, what the reference runs as tf.contrib.rnn.ConvLSTMCell.call
+// (built at code/pred_models.py:189-202 and :236-249, driven by dynamic_rnn :212/:232
+// and raw_rnn :455/:678):  concat([x,h]) -> conv3x3 SAME -> +biases -> split i,j,f,o ->
+// c' = sigmoid(f+forget_bias)*c + sigmoid(i)*tanh(j);  h' = tanh(c')*sigmoid(o).
+//
+// Formulation: one persistent warp-specialised tcgen05 GEMM
+//     G[R, 1024] = A[R, 9*Cpad] * Bt[1024, 9*Cpad]^T
+// over the halo layout (mvb_common.cuh): the A k-block for tap t / channel chunk q is
+// the TMA box  rows [m0+shift(t), +128) x channels [32q, +32)  of the activation matrix,
+// so the 3x3 im2col never exists in memory.  fp32 parity on bf16 tensor cores comes
+// from operand planes: x = x0+x1(+x2) with every plane bf16 (mvb::split_planes), and
+// the products a_i*b_j with i+j < P are all accumulated into the same fp32 TMEM tile
+// (P=2 -> 3 MMAs, error ~2^-17; P=3 -> 6 MMAs, ~2^-24; P=1 -> plain bf16).
+// Output columns are gate-interleaved (tile of 256 = 4 gates x 64 channels) so the
+// epilogue warps own i,j,f,o of a channel and emit (c', h') directly - the gate
+// pre-activations never reach HBM.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   TMA producer      warp 1   MMA issuer (one thread)
+//   warp 2   TMEM allocator    warp 3   idle
+//   warps 4-11  epilogue: two warpgroups split the 64 channels of a tile; TMEM holds
+//               two 256-column accumulators so tile i+1's MMAs overlap tile i's epilogue.
+#include "mvb_common.cuh"
+#include "mvb_kernels.h"
+
+namespace mvb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 32;   // bf16 elements = 64 B = one SWIZZLE_64B row
+constexpr int UMMA_K = 16;
+constexpr int TILE_CH = 64;   // hidden channels per N tile
+constexpr int N_TILES = kGates / BLOCK_N;  // 4
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
+constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;  // 8 KB
+constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t SW64_LAYOUT = 4;
+constexpr uint32_t SW64_SBO = 8 * BLOCK_K * 2;  // 512 B between 8-row groups
+
+template <int P> struct CellCfg {
+  static constexpr int STAGE_BYTES = P * (A_PLANE_BYTES + B_PLANE_BYTES);
+  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 4 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct CellParams {
+  const float* bias;        // [1024] packed (tile, gate, channel) order
+  const float* c_in;        // [R_src, 256] or nullptr (zero state)
+  const int* row_map;       // [NS] source sample-row of c_in, or nullptr (identity)
+  float* c_out;             // [R, 256]
+  float* h32_out;           // [R, 256] or nullptr
+  __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
+  long long hp_plane_stride;  // elements between planes of hp_out
+  int cpad_out;             // row pitch of hp_out (elements)
+  int ch_off_out;           // channel offset of the h block inside hp_out rows
+  long long R;              // total halo rows
+  int H, W;
+  int cpad;                 // K channels per tap (multiple of 32)
+  float forget_bias;
+};
+
+// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) |
+                            ((BLOCK_M >> 4) << 24);
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmB, const CellParams prm) {
+  using Cfg = CellCfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const Grid g = make_grid(prm.H, prm.W);
+  const int kc = prm.cpad / BLOCK_K;     // channel chunks per tap
+  const int num_kb = 9 * kc;
+  const long long num_m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
+  const long long num_tiles = num_m_tiles * N_TILES;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const long long m0 = (t / N_TILES) * BLOCK_M;
+      const int n0 = (int)(t % N_TILES) * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kc, q = kb - tap * kc;
+        const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + P * A_PLANE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_3d(sa, &tmA, &full_bar[stage], q * BLOCK_K, (int)(m0 + shift), 0);
+        tma_load_3d(sb, &tmB, &full_bar[stage], tap * prm.cpad + q * BLOCK_K, n0, 0);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + P * A_PLANE_BYTES;
+        uint32_t first = (kb == 0) ? 0u : 1u;
+#pragma unroll
+        for (int pa = 0; pa < P; ++pa) {
+#pragma unroll
+          for (int pb = 0; pb < P - pa; ++pb) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t ad = make_smem_desc(sa + pa * A_PLANE_BYTES + k * UMMA_K * 2, SW64_SBO, SW64_LAYOUT);
+              const uint64_t bd = make_smem_desc(sb + pb * B_PLANE_BYTES + k * UMMA_K * 2, SW64_SBO, SW64_LAYOUT);
+              umma_bf16(d_tmem, ad, bd, kIdesc, first);
+              first = 1u;
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[as]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int cgp = (warp - 4) >> 2;         // column group (0/1): channels [32*cgp, +32)
+    long long it = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const long long m0 = (t / N_TILES) * BLOCK_M;
+      const int nt = (int)(t % N_TILES);
+      const long long row = m0 + wq * 32 + lane;
+      bool valid = row < prm.R;
+      long long src_row = row;
+      if (valid) {
+        const long long smp = row / g.S;
+        const int rem = (int)(row - smp * g.S);
+        const int y = rem / g.Wp, x = rem - y * g.Wp;
+        valid = (x < g.W) && (y < g.H);
+        if (valid && prm.row_map) src_row = (long long)prm.row_map[smp] * g.S + rem;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int j0 = cgp * 32 + cc * 16;            // channel offset inside the tile
+        const int ch0 = nt * TILE_CH + j0;            // hidden channel
+        uint32_t gi[16], gj[16], gf[16], go[16];
+        tmem_ld16(t_row + 0 * TILE_CH + j0, gi);
+        tmem_ld16(t_row + 1 * TILE_CH + j0, gj);
+        tmem_ld16(t_row + 2 * TILE_CH + j0, gf);
+        tmem_ld16(t_row + 3 * TILE_CH + j0, go);
+        float cprev[16];
+        if (valid && prm.c_in) {
+          const float4* cp = reinterpret_cast<const float4*>(prm.c_in + src_row * kHidden + ch0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 q4 = __ldg(cp + v);
+            cprev[4 * v] = q4.x; cprev[4 * v + 1] = q4.y; cprev[4 * v + 2] = q4.z; cprev[4 * v + 3] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) cprev[v] = 0.f;
+        }
+        tmem_ld_wait();
+        if (valid) {
+          const float* bptr = prm.bias + nt * BLOCK_N + j0;
+          float cn[16], hn[16];
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            const float xi = __uint_as_float(gi[v]) + __ldg(bptr + 0 * TILE_CH + v);
+            const float xj = __uint_as_float(gj[v]) + __ldg(bptr + 1 * TILE_CH + v);
+            const float xf = __uint_as_float(gf[v]) + __ldg(bptr + 2 * TILE_CH + v);
+            const float xo = __uint_as_float(go[v]) + __ldg(bptr + 3 * TILE_CH + v);
+            const float c1 = sigmoid_acc(xf + prm.forget_bias) * cprev[v] + sigmoid_acc(xi) * tanh_acc(xj);
+            cn[v] = c1;
+            hn[v] = tanh_acc(c1) * sigmoid_acc(xo);
+          }
+          float4* co = reinterpret_cast<float4*>(prm.c_out + row * kHidden + ch0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) co[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
+          if (prm.h32_out) {
+            float4* ho = reinterpret_cast<float4*>(prm.h32_out + row * kHidden + ch0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) ho[v] = make_float4(hn[4 * v], hn[4 * v + 1], hn[4 * v + 2], hn[4 * v + 3]);
+          }
+          if (prm.hp_out) {
+            uint32_t pk[P][8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              __nv_bfloat16 a[P], b[P];
+              split_planes<P>(hn[2 * v], a);
+              split_planes<P>(hn[2 * v + 1], b);
+#pragma unroll
+              for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              uint4* po = reinterpret_cast<uint4*>(prm.hp_out + p * prm.hp_plane_stride +
+                                                   row * prm.cpad_out + prm.ch_off_out + ch0);
+              po[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+              po[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ----------------------------------------------------------------------------------
+// weight packing:  TF kernel [3,3,Cx+256,1024] (HWIO, gate order i,j,f,o) + biases
+//   -> planes bf16 [P][1024][9*cpad]  (row = tile*256 + gate*64 + j,  k = tap*cpad + kc)
+//   -> bias fp32 [1024] in the same row order
+// kc < cx: input channel kc;  cx <= kc < cxp: zero;  kc >= cxp: hidden channel kc-cxp.
+// ----------------------------------------------------------------------------------
+template <int P>
+__global__ void pack_weights_kernel(const float* __restrict__ kernel, const float* __restrict__ biases,
+                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_packed,
+                                    int cx, int cxp, int cpad) {
+  const long long ktot = 9LL * cpad;
+  const long long total = (long long)kGates * ktot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ktot);
+    const int k = (int)(i - (long long)n * ktot);
+    const int tap = k / cpad, kcn = k - tap * cpad;
+    const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+    const int col = gate * kHidden + tile * TILE_CH + j;
+    float v = 0.f;
+    int cin = -1;
+    if (kcn < cx) cin = kcn;
+    else if (kcn >= cxp) cin = cx + (kcn - cxp);
+    if (cin >= 0) v = kernel[((long long)tap * (cx + kHidden) + cin) * kGates + col];
+    __nv_bfloat16 pl[P];
+    split_planes<P>(v, pl);
+#pragma unroll
+    for (int p = 0; p < P; ++p) wp[(long long)p * total + i] = pl[p];
+    if (k == 0) bias_packed[n] = biases[col];
+  }
+}
+
+template <int P>
+static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CellParams& prm,
+                       int num_sms, cudaStream_t stream) {
+  using Cfg = CellCfg<P>;
+  static bool configured = false;
+  if (!configured) {
+    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const long long num_tiles = ((prm.R + BLOCK_M - 1) / BLOCK_M) * N_TILES;
+  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  cell_fwd_kernel<P><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, const float* c_in,
+             const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
+             int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
+             float forget_bias, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "cell_fwd: planes P=%d not in {1,2,3}", P);
+  MVB_REQUIRE(cpad % BLOCK_K == 0 && cpad >= kHidden + BLOCK_K, "cell_fwd: cpad=%d must be a multiple of 32 and >= 288", cpad);
+  MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
+  MVB_REQUIRE(xh_planes && w_planes && bias && c_out, "cell_fwd: null pointer");
+  if (hp_out) MVB_REQUIRE(cpad_out % 8 == 0 && ch_off_out % 8 == 0, "cell_fwd: hp_out pitch/offset must be multiples of 8");
+  const Grid g = make_grid(H, W);
+  const long long R = NS * g.S;
+  MVB_REQUIRE(R + 2LL * g.Wp + 256 < 0x7fffffffLL, "cell_fwd: too many rows (%lld) for int32 TMA coordinates", R);
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_3d_bf16(&tmA, xh_planes, (uint64_t)cpad, (uint64_t)R, (uint64_t)P,
+                               (uint64_t)cpad * 2, (uint64_t)R * cpad * 2, BLOCK_K, BLOCK_M, P, 64);
+  if (rc) return rc;
+  const uint64_t ktot = 9ull * cpad;
+  rc = encode_tmap_3d_bf16(&tmB, w_planes, ktot, (uint64_t)kGates, (uint64_t)P, ktot * 2,
+                           ktot * kGates * 2, BLOCK_K, BLOCK_N, P, 64);
+  if (rc) return rc;
+
+  CellParams prm;
+  prm.bias = bias; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
+  prm.hp_out = reinterpret_cast<__nv_bfloat16*>(hp_out);
+  prm.hp_plane_stride = hp_plane_stride; prm.cpad_out = cpad_out; prm.ch_off_out = ch_off_out;
+  prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.forget_bias = forget_bias;
+
+  int dev = 0, num_sms = 0;
+  MVB_CHECK_CUDA(cudaGetDevice(&dev));
+  MVB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  switch (P) {
+    case 1: return launch_cell<1>(tmA, tmB, prm, num_sms, stream);
+    case 2: return launch_cell<2>(tmA, tmB, prm, num_sms, stream);
+    default: return launch_cell<3>(tmA, tmB, prm, num_sms, stream);
+  }
+}
+
+int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
+                      int cx, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "pack_cell_weights: planes P=%d not in {1,2,3}", P);
+  MVB_REQUIRE(cx >= 1, "pack_cell_weights: cx=%d", cx);
+  const int cxp = (cx + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  const int cpad = cxp + kHidden;
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(w_planes);
+  const int threads = 256, blocks = 1184;
+  switch (P) {
+    case 1: pack_weights_kernel<1><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
+    case 2: pack_weights_kernel<2><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
+    default: pack_weights_kernel<3><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+}  // namespace mvb

@@ -1,0 +1,234 @@
+// Common device/host helpers for libmultiverse_b200 (sm_100a only).
+//
+// Internal "halo" layout used by every kernel of the hot path:
+//   a location grid of H x W cells is stored with ONE shared zero column and ONE
+//   shared zero row: pixel (n, y, x) lives at row  r = n*S + y*(W+1) + x  with
+//   S = (H+1)*(W+1);  x == W and y == H are zero cells that are never written.
+//   A 3x3 "SAME" tap (dy,dx) is then the constant row shift  (dy-1)*(W+1)+(dx-1)
+//   for every pixel of every image, so the im2col A-operand of the ConvLSTM GEMM is
+//   a plain 2-D TMA box of the activation matrix [rows, channels] at a shifted row
+//   coordinate (rows < 0 / >= R are zero-filled by TMA).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+namespace mvb {
+
+constexpr int kHidden = 256;          // enc/dec hidden size of every published config
+constexpr int kGates = 4 * kHidden;   // i, j, f, o
+
+// ----------------------------------------------------------------------------------
+// error plumbing (C-ABI: int return codes + thread-local message)
+// ----------------------------------------------------------------------------------
+enum : int {
+  MVB_OK = 0,
+  MVB_ERR_INVALID = 1,
+  MVB_ERR_CUDA = 2,
+  MVB_ERR_DRIVER = 3,
+};
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define MVB_CHECK_CUDA(expr)                                                      \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      mvb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                     __FILE__, __LINE__);                                         \
+      return mvb::MVB_ERR_CUDA;                                                   \
+    }                                                                             \
+  } while (0)
+
+#define MVB_REQUIRE(cond, ...)                                                    \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      mvb::set_error(__VA_ARGS__);                                                \
+      return mvb::MVB_ERR_INVALID;                                                \
+    }                                                                             \
+  } while (0)
+
+// ----------------------------------------------------------------------------------
+// halo-layout index helpers
+// ----------------------------------------------------------------------------------
+struct Grid {
+  int H, W;      // valid cells
+  int Wp;        // W + 1
+  int S;         // (H+1)*(W+1) rows per sample
+};
+__host__ __device__ inline Grid make_grid(int H, int W) {
+  Grid g; g.H = H; g.W = W; g.Wp = W + 1; g.S = (H + 1) * (W + 1); return g;
+}
+
+// ----------------------------------------------------------------------------------
+// bf16 plane splitting:  v = p0 + p1 (+ p2) + O(2^-9P |v|)
+// ----------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void split_planes(float v, __nv_bfloat16 (&out)[P]) {
+  float r = v;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    out[p] = __float2bfloat16_rn(r);
+    r -= __bfloat162float(out[p]);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// ----------------------------------------------------------------------------------
+// activations: fp32, ~1e-6 accurate (MUFU.EX2 is 2^-22; tanh.approx at 2^-11 is NOT
+// acceptable for the 1e-4 parity bar, so it is never used)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_acc(float x) {
+  return __frcp_rn(1.0f + __expf(-x));
+}
+__device__ __forceinline__ float tanh_acc(float x) {
+  // 1 - 2/(exp(2x)+1): exact limits at +-inf, abs error ~1e-7
+  return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
+}
+
+// ----------------------------------------------------------------------------------
+// warp reductions
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ----------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA, tcgen05
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+// 3-D tiled TMA load, completes on an mbarrier with complete_tx::bytes.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// Allocate `ncols` TMEM columns (power of two >= 32); whole warp executes.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, one CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// mbarrier arrive once all previously issued tcgen05.mma of this thread retire.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+
+// TMEM -> registers: this thread's lane (row), 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (SM100 "version 1"), swizzle given by
+// layout_type (2 = 128B, 4 = 64B, 6 = 32B); sbo = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ----------------------------------------------------------------------------------
+// host: TMA descriptor encode through the runtime's driver entry point (no -lcuda)
+// ----------------------------------------------------------------------------------
+int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
+                        uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                        uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+
+}  // namespace mvb

@@ -1,0 +1,57 @@
+// Internal C++ launchers (one per kernel group); the extern "C" wrappers live in mvb_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mvb {
+
+void count_launch(int n);
+
+// mvb_cell.cu
+int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, const float* c_in,
+             const int* row_map, float* c_out, float* h32_out, void* hp_out,
+             long long hp_plane_stride, int cpad_out, int ch_off_out, long long NS, int H, int W,
+             int cpad, int P, float forget_bias, cudaStream_t stream);
+int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
+                      int cx, int P, cudaStream_t stream);
+
+// mvb_layout.cu
+int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
+                   long long NS, int H, int W, int C, int P, cudaStream_t stream);
+int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int C, int to_nhwc,
+                   cudaStream_t stream);
+int enc_class_input(const float* scene_conv, const int* frame_idx, const int* label,
+                    const int* prev_label, void* xh_planes, long long plane_stride, int cpad,
+                    long long NS, int H, int W, int P, cudaStream_t stream);
+
+// mvb_scene.cu
+int scene_conv_fwd(const float* in, const float* W, const float* b, float* out, long long F, int IH,
+                   int IW, int Cin, int Cout, cudaStream_t stream);
+int scene_time_mean(const float* scene_conv, const int* frame_idx, float* out, long long N, int T,
+                    long long HWC, cudaStream_t stream);
+
+// mvb_gnn.cu
+int gnn_attend_fwd(const float* h32, const int* row_map, const float* scene_mean, int beam,
+                   void* hp_out, long long hp_plane_stride, int cpad_out, int ch_off_out,
+                   long long NS, int H, int W, int P, cudaStream_t stream);
+
+// mvb_head.cu
+int head_fwd(const float* h32, const float* Wo, int Pout, float* out, int* ids_out, const float* We,
+             const float* be, int E, void* xh_next, long long plane_stride, int cpad, long long NS,
+             int H, int W, int P, cudaStream_t stream);
+int emb_onehot_fwd(const int* ids, const float* We, const float* be, int E, void* xh_next,
+                   long long plane_stride, int cpad, long long NS, int H, int W, int P,
+                   cudaStream_t stream);
+int emb_dense_fwd(const float* x, const float* We, const float* be, int E, void* xh_next,
+                  long long plane_stride, int cpad, long long NS, int H, int W, int P,
+                  cudaStream_t stream);
+
+// mvb_beam.cu
+int beam_step(const float* logits, const float* score_in, float* score_out, int* ids_out,
+              int* parents_out, int* row_map_out, long long N, int B, int V, int first_step,
+              int zero_scores, int diverse, float log_gamma, cudaStream_t stream);
+int beam_backtrace(const int* step_ids, const int* step_parents, const float* step_logits,
+                   int* out_ids, float* out_logits, long long N, int B, int Tp, int V,
+                   cudaStream_t stream);
+
+}  // namespace mvb

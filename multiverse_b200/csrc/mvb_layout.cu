@@ -1,0 +1,131 @@
+// Layout kernels at the API boundary: NHWC fp32 (the reference's placeholder layout,
+// code/pred_models.py:62-115) <-> the library's halo layout / bf16 operand planes, and the
+// class-encoder input of code/pred_models.py:210.  All HBM-bound, one pass.
+#include "mvb_common.cuh"
+#include "mvb_kernels.h"
+
+namespace mvb {
+
+// One thread per (pixel, channel); channel fastest so reads and writes coalesce.
+template <int P>
+__global__ void nhwc_to_planes_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      long long plane_stride, int cpad, int ch_off, long long NS,
+                                      Grid g, int C) {
+  const long long total = NS * g.H * g.W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int x = (int)(pix % g.W);
+    const long long t = pix / g.W;
+    const int y = (int)(t % g.H);
+    const long long s = t / g.H;
+    const long long row = s * g.S + (long long)y * g.Wp + x;
+    __nv_bfloat16 pl[P];
+    split_planes<P>(src[i], pl);
+#pragma unroll
+    for (int p = 0; p < P; ++p) dst[p * plane_stride + row * cpad + ch_off + c] = pl[p];
+  }
+}
+
+__global__ void nhwc_halo_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                      long long NS, Grid g, int C, int to_nhwc) {
+  const int c4 = C / 4;
+  const long long total = NS * g.H * g.W * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4);
+    const long long pix = i / c4;
+    const int x = (int)(pix % g.W);
+    const long long t = pix / g.W;
+    const int y = (int)(t % g.H);
+    const long long s = t / g.H;
+    const long long row = s * g.S + (long long)y * g.Wp + x;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    if (to_nhwc) d4[pix * c4 + c] = s4[row * c4 + c];
+    else d4[row * c4 + c] = s4[pix * c4 + c];
+  }
+}
+
+// One block of 64 threads per sample row: thread c handles scene channel c.
+template <int P>
+__global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
+                                       const int* __restrict__ frame_idx,
+                                       const int* __restrict__ label,
+                                       const int* __restrict__ prev_label,
+                                       __nv_bfloat16* __restrict__ xh, long long plane_stride,
+                                       int cpad, Grid g) {
+  const long long s = blockIdx.x;
+  const int c = threadIdx.x;  // 0..63
+  const int hw = g.H * g.W;
+  if (prev_label) {
+    const int pl = prev_label[s];
+    if (pl >= 0 && pl < hw) {
+      const long long row = s * g.S + (long long)(pl / g.W) * g.Wp + (pl % g.W);
+#pragma unroll
+      for (int p = 0; p < P; ++p) xh[p * plane_stride + row * cpad + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();  // same-pixel clear/set ordering inside the block
+  const int lb = label[s];
+  if (lb >= 0 && lb < hw) {
+    const long long row = s * g.S + (long long)(lb / g.W) * g.Wp + (lb % g.W);
+    const float v = scene_conv[((long long)frame_idx[s] * hw + lb) * 64 + c];
+    __nv_bfloat16 pl[P];
+    split_planes<P>(v, pl);
+#pragma unroll
+    for (int p = 0; p < P; ++p) xh[p * plane_stride + row * cpad + c] = pl[p];
+  }
+}
+
+int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
+                   long long NS, int H, int W, int C, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "nhwc_to_planes: planes P=%d", P);
+  MVB_REQUIRE(src && dst_planes && NS > 0 && C > 0 && ch_off + C <= cpad, "nhwc_to_planes: bad args");
+  const Grid g = make_grid(H, W);
+  const long long total = NS * H * W * C;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_planes);
+  switch (P) {
+    case 1: nhwc_to_planes_kernel<1><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
+    case 2: nhwc_to_planes_kernel<2><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
+    default: nhwc_to_planes_kernel<3><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int C, int to_nhwc,
+                   cudaStream_t stream) {
+  MVB_REQUIRE(src && dst && NS > 0 && C > 0 && C % 4 == 0, "nhwc_halo_copy: bad args (C=%d must be a multiple of 4)", C);
+  const Grid g = make_grid(H, W);
+  const long long total = NS * H * W * (C / 4);
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  nhwc_halo_copy_kernel<<<blocks, threads, 0, stream>>>(src, dst, NS, g, C, to_nhwc);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int enc_class_input(const float* scene_conv, const int* frame_idx, const int* label,
+                    const int* prev_label, void* xh_planes, long long plane_stride, int cpad,
+                    long long NS, int H, int W, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "enc_class_input: planes P=%d", P);
+  MVB_REQUIRE(scene_conv && frame_idx && label && xh_planes && NS > 0, "enc_class_input: bad args");
+  const Grid g = make_grid(H, W);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(xh_planes);
+  switch (P) {
+    case 1: enc_class_input_kernel<1><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
+    case 2: enc_class_input_kernel<2><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
+    default: enc_class_input_kernel<3><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+}  // namespace mvb

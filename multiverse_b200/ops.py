@@ -1,0 +1,177 @@
+# coding=utf-8
+"""Thin torch-tensor wrappers over the C ABI (one per entry point of include/multiverse_b200.h).
+
+PyTorch only owns memory and streams here; every computation is a kernel of
+libmultiverse_b200.so.  All tensors must be contiguous CUDA tensors on the current device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+
+from . import _lib
+
+HIDDEN = 256
+DEFAULT_PLANES = int(os.environ.get("MVB_PLANES", "2"))
+
+
+def _p(t):
+  if t is None:
+    return None
+  assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+  return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def halo_rows(ns, h, w):
+  """Rows of the halo layout for ns sample rows of an h x w grid."""
+  return ns * (h + 1) * (w + 1)
+
+
+def cell_cpad(cx):
+  return (cx + 31) // 32 * 32 + HIDDEN
+
+
+def launch_count():
+  return int(_lib.load().mvb_launch_count())
+
+
+def reset_launch_count():
+  _lib.load().mvb_reset_launch_count()
+
+
+class PackedCell(object):
+  """Device-resident packed weights of one ConvLSTM cell (see mvb_pack_cell_weights)."""
+
+  def __init__(self, kernel, biases, planes=None):
+    planes = planes or DEFAULT_PLANES
+    assert kernel.dim() == 4 and kernel.shape[0] == 3 and kernel.shape[1] == 3
+    assert kernel.shape[3] == 4 * HIDDEN
+    self.cx = int(kernel.shape[2]) - HIDDEN
+    self.cxp = (self.cx + 31) // 32 * 32
+    self.cpad = self.cxp + HIDDEN
+    self.planes = planes
+    kernel = kernel.detach().to(torch.float32).contiguous()
+    biases = biases.detach().to(torch.float32).contiguous()
+    self.w = torch.empty((planes, 4 * HIDDEN, 9 * self.cpad), dtype=torch.bfloat16,
+                         device=kernel.device)
+    self.bias = torch.empty((4 * HIDDEN,), dtype=torch.float32, device=kernel.device)
+    _lib.call("mvb_pack_cell_weights", _p(kernel), _p(biases), _p(self.w), _p(self.bias),
+              self.cx, planes, _stream())
+
+
+def alloc_xh(ns, h, w, cpad, planes, device):
+  """Zeroed operand planes [P, R, cpad]; halo cells and channel padding must stay zero."""
+  return torch.zeros((planes, halo_rows(ns, h, w), cpad), dtype=torch.bfloat16, device=device)
+
+
+def alloc_state(ns, h, w, device, zero=True):
+  f = torch.zeros if zero else torch.empty
+  return f((halo_rows(ns, h, w), HIDDEN), dtype=torch.float32, device=device)
+
+
+def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
+             forget_bias=1.0):
+  """One ConvLSTM step.  xh_next: operand planes whose h block (channel offset = its cxp)
+  receives the bf16 planes of h', or None."""
+  assert xh.shape[2] == packed.cpad and xh.shape[0] == packed.planes
+  if xh_next is not None:
+    stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
+  else:
+    stride, cpad_out, off = 0, 0, 0
+  _lib.call("mvb_convlstm_cell_fwd", _p(xh), _p(packed.w), _p(packed.bias), _p(c_in),
+            _p(row_map), _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w,
+            packed.cpad, packed.planes, float(forget_bias), _stream())
+
+
+def nhwc_to_planes(src, xh, ch_off, h, w):
+  ns, c = src.shape[0], src.shape[-1]
+  _lib.call("mvb_nhwc_to_planes", _p(src), _p(xh), xh.stride(0), xh.shape[2], ch_off, ns, h, w,
+            c, xh.shape[0], _stream())
+
+
+def nhwc_to_halo(src, dst, h, w):
+  _lib.call("mvb_nhwc_to_halo", _p(src), _p(dst), src.shape[0], h, w, src.shape[-1], _stream())
+
+
+def halo_to_nhwc(src, dst, h, w):
+  _lib.call("mvb_halo_to_nhwc", _p(src), _p(dst), dst.shape[0], h, w, dst.shape[-1], _stream())
+
+
+def enc_class_input(scene_conv, frame_idx, label, prev_label, xh, h, w):
+  _lib.call("mvb_enc_class_input", _p(scene_conv), _p(frame_idx), _p(label), _p(prev_label),
+            _p(xh), xh.stride(0), xh.shape[2], label.shape[0], h, w, xh.shape[0], _stream())
+
+
+def scene_conv_fwd(x, W, b):
+  f, ih, iw, cin = x.shape
+  cout = W.shape[3]
+  out = torch.empty((f, (ih + 1) // 2, (iw + 1) // 2, cout), dtype=torch.float32, device=x.device)
+  _lib.call("mvb_scene_conv_fwd", _p(x), _p(W), _p(b), _p(out), f, ih, iw, cin, cout, _stream())
+  return out
+
+
+def scene_time_mean(scene_conv, frame_idx):
+  n, t = frame_idx.shape
+  hwc = scene_conv[0].numel()
+  out = torch.empty((n,) + tuple(scene_conv.shape[1:]), dtype=torch.float32,
+                    device=scene_conv.device)
+  _lib.call("mvb_scene_time_mean", _p(scene_conv), _p(frame_idx), _p(out), n, t, hwc, _stream())
+  return out
+
+
+def gnn_attend_fwd(h32, scene_mean, xh_next, h, w, ns, beam=1, row_map=None):
+  _lib.call("mvb_gnn_attend_fwd", _p(h32), _p(row_map), _p(scene_mean), beam, _p(xh_next),
+            xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN, ns, h, w,
+            xh_next.shape[0], _stream())
+
+
+def head_class_fwd(h32, Wo, logits_out, ids_out, We, be, xh_next, h, w, ns, planes=None):
+  e = 0 if We is None else We.shape[3]
+  if xh_next is not None:
+    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], xh_next.shape[0]
+  else:
+    stride, cpad, planes = 0, 0, planes or DEFAULT_PLANES
+  _lib.call("mvb_head_class_fwd", _p(h32), _p(Wo), _p(logits_out), _p(ids_out), _p(We), _p(be), e,
+            _p(xh_next), stride, cpad, ns, h, w, planes, _stream())
+
+
+def head_reg_fwd(h32, Wo, off_out, We, be, xh_next, h, w, ns, planes=None):
+  e = 0 if We is None else We.shape[3]
+  if xh_next is not None:
+    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], xh_next.shape[0]
+  else:
+    stride, cpad, planes = 0, 0, planes or DEFAULT_PLANES
+  _lib.call("mvb_head_reg_fwd", _p(h32), _p(Wo), _p(off_out), _p(We), _p(be), e, _p(xh_next),
+            stride, cpad, ns, h, w, planes, _stream())
+
+
+def emb_onehot_fwd(ids, We, be, xh_next, h, w):
+  _lib.call("mvb_emb_onehot_fwd", _p(ids), _p(We), _p(be), We.shape[3], _p(xh_next),
+            xh_next.stride(0), xh_next.shape[2], ids.numel(), h, w, xh_next.shape[0], _stream())
+
+
+def emb_dense_fwd(x, We, be, xh_next, h, w):
+  _lib.call("mvb_emb_dense_fwd", _p(x), _p(We), _p(be), We.shape[3], _p(xh_next),
+            xh_next.stride(0), xh_next.shape[2], x.shape[0], h, w, xh_next.shape[0], _stream())
+
+
+def beam_step(logits, score_in, score_out, ids_out, parents_out, row_map_out, n, b, v,
+              first_step, zero_scores, diverse, gamma):
+  lg = math.log(gamma) if diverse else 0.0
+  _lib.call("mvb_beam_step", _p(logits), _p(score_in), _p(score_out), _p(ids_out),
+            _p(parents_out), _p(row_map_out), n, b, v, int(first_step), int(zero_scores),
+            int(diverse), float(lg), _stream())
+
+
+def beam_backtrace(step_ids, step_parents, step_logits, out_ids, out_logits):
+  tp, n, b = step_ids.shape
+  v = step_logits.shape[-1]
+  _lib.call("mvb_beam_backtrace", _p(step_ids), _p(step_parents), _p(step_logits), _p(out_ids),
+            _p(out_logits), n, b, tp, v, _stream())
