@@ -46,9 +46,14 @@ int mvb_cell_cpad(int cx);
 /* Pack a TF ConvLSTM `kernel` [3,3,cx+256,1024] (HWIO; gate order i,j,f,o) and `biases` [1024]
  * (host layout of the TF variables, but resident on the device) into
  *   w_planes   bf16 [P][1024][9*cpad]   (row = tile*256 + gate*64 + ch%64, K-major)
- *   bias_packed fp32 [1024]             (same row order). */
+ *   bias_packed fp32 [1024]             (same row order).
+ * comp != 0 (needs planes == 2 and 4*cx <= roundup(cx,32)): "compensated x block" for inputs of
+ * large magnitude (the regression encoder's raw pixel offsets, pred_models.py:232): the zero
+ * padding of the x block instead carries [W | W | W-w0-w1 | w1] against the activation side's
+ * [x | x-x0-x1 | x | x1] (mvb_nhwc_to_planes with comp), so the terms the 3-product bf16 scheme
+ * drops are added back by the same MMAs and the x contribution is exact to fp32. */
 int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_planes,
-                          float* bias_packed, int cx, int planes, void* stream);
+                          float* bias_packed, int cx, int planes, int comp, void* stream);
 
 /* One cell step over NS sample rows:  (c_in, xh) -> (c_out, h).
  *   xh_planes  bf16 [P][NS*S][cpad]: concat([x (cx, zero-padded to roundup(cx,32)), h (256)])
@@ -67,9 +72,11 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
 
 /* ---- layout conversion at the API boundary (placeholders are NHWC, pred_models.py:62-115) */
 
-/* fp32 NHWC [NS,H,W,C] -> bf16 planes written at channel offset ch_off of halo rows (pitch cpad). */
+/* fp32 NHWC [NS,H,W,C] -> bf16 planes written at channel offset ch_off of halo rows (pitch cpad);
+ * comp != 0 also writes the compensation channels [ch_off+C, ch_off+4C) (see above). */
 int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,
-                       int ch_off, int64_t NS, int H, int W, int C, int planes, void* stream);
+                       int ch_off, int64_t NS, int H, int W, int C, int planes, int comp,
+                       void* stream);
 /* fp32 NHWC [NS,H,W,C] <-> fp32 halo [NS*S, C] (halo cells are left untouched / skipped). */
 int mvb_nhwc_to_halo(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream);
 int mvb_halo_to_nhwc(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream);

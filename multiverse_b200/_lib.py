@@ -20,10 +20,10 @@ SIGNATURES = {
     "mvb_launch_count": [],
     "mvb_reset_launch_count": [],
     "mvb_cell_cpad": [_i],
-    "mvb_pack_cell_weights": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "mvb_pack_cell_weights": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvb_convlstm_cell_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                               _i, _i, _f, _vp],
-    "mvb_nhwc_to_planes": [_vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _vp],
+    "mvb_nhwc_to_planes": [_vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _i, _vp],
     "mvb_nhwc_to_halo": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_halo_to_nhwc": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_enc_class_input": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _i, _i, _vp],

@@ -74,15 +74,15 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 1; }
+int mvb_abi_version(void) { return 2; }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 
 int mvb_cell_cpad(int cx) { return (cx + 31) / 32 * 32 + kHidden; }
 
 int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_planes,
-                          float* bias_packed, int cx, int planes, void* stream) {
-  return pack_cell_weights(kernel, biases, w_planes, bias_packed, cx, planes, S(stream));
+                          float* bias_packed, int cx, int planes, int comp, void* stream) {
+  return pack_cell_weights(kernel, biases, w_planes, bias_packed, cx, planes, comp, S(stream));
 }
 
 int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const float* bias_packed,
@@ -96,8 +96,10 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
 }
 
 int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,
-                       int ch_off, int64_t NS, int H, int W, int C, int planes, void* stream) {
-  return nhwc_to_planes(src, dst_planes, plane_stride, cpad, ch_off, NS, H, W, C, planes, S(stream));
+                       int ch_off, int64_t NS, int H, int W, int C, int planes, int comp,
+                       void* stream) {
+  return nhwc_to_planes(src, dst_planes, plane_stride, cpad, ch_off, NS, H, W, C, planes, comp,
+                        S(stream));
 }
 int mvb_nhwc_to_halo(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream) {
   return nhwc_halo_copy(src, dst, NS, H, W, C, 0, S(stream));

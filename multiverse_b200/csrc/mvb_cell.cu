@@ -261,7 +261,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
 template <int P>
 __global__ void pack_weights_kernel(const float* __restrict__ kernel, const float* __restrict__ biases,
                                     __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_packed,
-                                    int cx, int cxp, int cpad) {
+                                    int cx, int cxp, int cpad, int comp) {
   const long long ktot = 9LL * cpad;
   const long long total = (long long)kGates * ktot;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -271,13 +271,25 @@ __global__ void pack_weights_kernel(const float* __restrict__ kernel, const floa
     const int tap = k / cpad, kcn = k - tap * cpad;
     const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
     const int col = gate * kHidden + tile * TILE_CH + j;
-    float v = 0.f;
-    int cin = -1;
-    if (kcn < cx) cin = kcn;
-    else if (kcn >= cxp) cin = cx + (kcn - cxp);
-    if (cin >= 0) v = kernel[((long long)tap * (cx + kHidden) + cin) * kGates + col];
+    int cin = -1, blk = 0;
+    if (kcn >= cxp) cin = cx + (kcn - cxp);
+    else if (!comp) { if (kcn < cx) cin = kcn; }
+    else if (kcn < 4 * cx) { blk = kcn / cx; cin = kcn - blk * cx; }
+    const float v = (cin >= 0) ? kernel[((long long)tap * (cx + kHidden) + cin) * kGates + col] : 0.f;
     __nv_bfloat16 pl[P];
     split_planes<P>(v, pl);
+    if (comp && kcn < cxp && P == 2) {
+      // compensated x block (see nhwc_to_planes_comp): [W | W | W-w0-w1 | w1]
+      if (blk == 2) {
+        float r = v;
+#pragma unroll
+        for (int p = 0; p < P; ++p) r -= __bfloat162float(pl[p]);
+        split_planes<P>(r, pl);
+      } else if (blk == 3) {
+        pl[0] = pl[P - 1];
+        pl[P - 1] = __float2bfloat16_rn(0.f);
+      }
+    }
 #pragma unroll
     for (int p = 0; p < P; ++p) wp[(long long)p * total + i] = pl[p];
     if (k == 0) bias_packed[n] = biases[col];
@@ -341,17 +353,18 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
 }
 
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
-                      int cx, int P, cudaStream_t stream) {
+                      int cx, int P, int comp, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "pack_cell_weights: planes P=%d not in {1,2,3}", P);
   MVB_REQUIRE(cx >= 1, "pack_cell_weights: cx=%d", cx);
   const int cxp = (cx + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   const int cpad = cxp + kHidden;
+  MVB_REQUIRE(!comp || (P == 2 && 4 * cx <= cxp), "pack_cell_weights: compensated x block needs planes=2 and 4*cx <= %d", cxp);
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(w_planes);
   const int threads = 256, blocks = 1184;
   switch (P) {
-    case 1: pack_weights_kernel<1><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
-    case 2: pack_weights_kernel<2><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
-    default: pack_weights_kernel<3><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad); break;
+    case 1: pack_weights_kernel<1><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad, comp); break;
+    case 2: pack_weights_kernel<2><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad, comp); break;
+    default: pack_weights_kernel<3><<<blocks, threads, 0, stream>>>(kernel, biases, wp, bias_packed, cx, cxp, cpad, comp); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

@@ -13,11 +13,11 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              long long hp_plane_stride, int cpad_out, int ch_off_out, long long NS, int H, int W,
              int cpad, int P, float forget_bias, cudaStream_t stream);
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
-                      int cx, int P, cudaStream_t stream);
+                      int cx, int P, int comp, cudaStream_t stream);
 
 // mvb_layout.cu
 int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
-                   long long NS, int H, int W, int C, int P, cudaStream_t stream);
+                   long long NS, int H, int W, int C, int P, int comp, cudaStream_t stream);
 int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int C, int to_nhwc,
                    cudaStream_t stream);
 int enc_class_input(const float* scene_conv, const int* frame_idx, const int* label,

@@ -10,7 +10,7 @@ namespace mvb {
 template <int P>
 __global__ void nhwc_to_planes_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                       long long plane_stride, int cpad, int ch_off, long long NS,
-                                      Grid g, int C) {
+                                      Grid g, int C, int comp) {
   const long long total = NS * g.H * g.W * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -22,9 +22,29 @@ __global__ void nhwc_to_planes_kernel(const float* __restrict__ src, __nv_bfloat
     const long long s = t / g.H;
     const long long row = s * g.S + (long long)y * g.Wp + x;
     __nv_bfloat16 pl[P];
-    split_planes<P>(src[i], pl);
+    const float v = src[i];
+    split_planes<P>(v, pl);
+    __nv_bfloat16* d = dst + row * cpad + ch_off + c;
 #pragma unroll
-    for (int p = 0; p < P; ++p) dst[p * plane_stride + row * cpad + ch_off + c] = pl[p];
+    for (int p = 0; p < P; ++p) d[p * plane_stride] = pl[p];
+    if (comp && P == 2) {
+      // Compensated x block for large-magnitude inputs (the regression encoder is fed raw pixel
+      // offsets up to ~1.9e3, code/pred_models.py:232): the padded channels carry the terms the
+      // 3-product plane scheme drops, so the MMA itself restores fp32-grade accuracy:
+      //   A: [x | r=x-x0-x1 | x | x1]   B: [W | W | W-w0-w1 | w1]   (pack_weights_kernel)
+      float r = v;
+#pragma unroll
+      for (int p = 0; p < P; ++p) r -= __bfloat162float(pl[p]);
+      __nv_bfloat16 rp[P];
+      split_planes<P>(r, rp);
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        d[p * plane_stride + C] = rp[p];
+        d[p * plane_stride + 2 * C] = pl[p];
+      }
+      d[3 * C] = pl[P - 1];
+      d[(P - 1) * plane_stride + 3 * C] = __float2bfloat16_rn(0.f);
+    }
   }
 }
 
@@ -80,18 +100,19 @@ __global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
 }
 
 int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
-                   long long NS, int H, int W, int C, int P, cudaStream_t stream) {
+                   long long NS, int H, int W, int C, int P, int comp, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "nhwc_to_planes: planes P=%d", P);
   MVB_REQUIRE(src && dst_planes && NS > 0 && C > 0 && ch_off + C <= cpad, "nhwc_to_planes: bad args");
+  MVB_REQUIRE(!comp || (P == 2 && ch_off + 4 * C <= cpad - kHidden), "nhwc_to_planes: compensated block needs planes=2 and 4*C inside the x block");
   const Grid g = make_grid(H, W);
   const long long total = NS * H * W * C;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_planes);
   switch (P) {
-    case 1: nhwc_to_planes_kernel<1><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
-    case 2: nhwc_to_planes_kernel<2><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
-    default: nhwc_to_planes_kernel<3><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C); break;
+    case 1: nhwc_to_planes_kernel<1><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
+    case 2: nhwc_to_planes_kernel<2><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
+    default: nhwc_to_planes_kernel<3><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

@@ -1,0 +1,304 @@
+# coding=utf-8
+"""Rollout engine: the forward pass of Model.build_forward (code/pred_models.py:123-308) as a
+sequence of libmultiverse_b200 kernel launches on one CUDA stream.
+
+Host code only sequences launches and owns the (PyTorch-allocated) device buffers; every
+arithmetic step is a kernel of the C-ABI library:
+
+  scene CNN (:146-165)                      -> mvb_scene_conv_fwd x2, mvb_scene_time_mean
+  class encoder (:210-215, dynamic_rnn)      -> T x [mvb_enc_class_input, mvb_convlstm_cell_fwd]
+  regression encoder (:232-234)              -> T x [mvb_nhwc_to_planes, mvb_convlstm_cell_fwd]
+  greedy class decoder (:311-471, raw_rnn)   -> Tp x [mvb_gnn_attend_fwd, mvb_convlstm_cell_fwd,
+                                                     mvb_head_class_fwd (logits+argmax+emb)]
+  regression decoder (:298-305)              -> Tp x [mvb_convlstm_cell_fwd, mvb_head_reg_fwd]
+  beam decoder (:474-806)                    -> Tp x [mvb_head_class_fwd, mvb_beam_step,
+                                                     mvb_emb_onehot_fwd, mvb_gnn_attend_fwd,
+                                                     mvb_convlstm_cell_fwd] + mvb_beam_backtrace
+
+The (c,h) gather by parent beam (:611-623) is never a copy: mvb_beam_step emits a row map that
+the next GNN / cell launch reads its state through.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+P_ = "person_pred/"
+
+
+def _names(i):
+  """TF variable names of scale i (scopes at code/pred_models.py:140,160,193,200,
+  215,234,240,247,327,456,446,469,930-950)."""
+  return dict(
+      enc_class=(P_ + "encoder_grid_class_%d/enc_grid_%d/kernel" % (i, i),
+                 P_ + "encoder_grid_class_%d/enc_grid_%d/biases" % (i, i)),
+      enc_reg=(P_ + "encoder_grid_reg_%d/enc_grid_regress_%d/kernel" % (i, i),
+               P_ + "encoder_grid_reg_%d/enc_grid_regress_%d/biases" % (i, i)),
+      dec_class=(P_ + "decoder_grid_class_%d/decoder_rnn/dec_grid_%d/kernel" % (i, i),
+                 P_ + "decoder_grid_class_%d/decoder_rnn/dec_grid_%d/biases" % (i, i)),
+      dec_reg=(P_ + "decoder_grid_reg_%d/decoder_rnn/dec_grid_reg_%d/kernel" % (i, i),
+               P_ + "decoder_grid_reg_%d/decoder_rnn/dec_grid_reg_%d/biases" % (i, i)),
+      emb_class=(P_ + "decoder_grid_class_%d/decoder_rnn/grid_emb/W" % i,
+                 P_ + "decoder_grid_class_%d/decoder_rnn/grid_emb/b" % i),
+      emb_reg=(P_ + "decoder_grid_reg_%d/decoder_rnn/grid_emb/W" % i,
+               P_ + "decoder_grid_reg_%d/decoder_rnn/grid_emb/b" % i),
+      head_class=P_ + "hidden2grid_decoder_grid_class_%d/out_dec_grid/W" % i,
+      head_reg=P_ + "hidden2grid_decoder_grid_reg_%d/out_dec_grid/W" % i)
+
+
+class ScaleWeights(object):
+  """Packed / device-resident weights of one grid scale."""
+
+  def __init__(self, weights, i, planes):
+    nm = _names(i)
+    f = lambda n: weights[n].detach().to(torch.float32).contiguous()
+    self.enc_class = ops.PackedCell(f(nm["enc_class"][0]), f(nm["enc_class"][1]), planes)
+    self.enc_reg = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), planes, comp=True)
+    self.dec_class = ops.PackedCell(f(nm["dec_class"][0]), f(nm["dec_class"][1]), planes)
+    self.dec_reg = ops.PackedCell(f(nm["dec_reg"][0]), f(nm["dec_reg"][1]), planes)
+    self.emb_class = (f(nm["emb_class"][0]), f(nm["emb_class"][1]))
+    self.emb_reg = (f(nm["emb_reg"][0]), f(nm["emb_reg"][1]))
+    self.head_class = f(nm["head_class"])
+    self.head_reg = f(nm["head_reg"])
+
+
+class ConvRNNEngine(object):
+  """Inference engine for one config (batch size, grids, flags) and one weight set."""
+
+  def __init__(self, cfg, weights, device=None, planes=None):
+    self.cfg = cfg
+    self.device = device or torch.device("cuda", torch.cuda.current_device())
+    self.planes = planes or ops.DEFAULT_PLANES
+    assert cfg.enc_hidden_size == ops.HIDDEN and cfg.dec_hidden_size == ops.HIDDEN, \
+        "the kernels are specialised for hidden size 256 (every published config)"
+    assert cfg.use_scene_enc, "only the published use_scene_enc path is implemented"
+    assert cfg.convlstm_kernel == 3 and cfg.scene_conv_kernel == 3
+    assert cfg.scene_conv_dim == 64
+    assert getattr(cfg, "activation_func", "tanh") in ("tanh",) or \
+        getattr(cfg.activation_func, "__name__", "") == "tanh", "kernels implement tanh"
+    self.set_weights(weights)
+    self._bufs = {}
+
+  # ------------------------------------------------------------------ weights
+  def set_weights(self, weights):
+    dev = self.device
+    w = {k: (v if torch.is_tensor(v) else torch.as_tensor(v)).to(dev) for k, v in weights.items()}
+    self.scene_w = [(w[P_ + "scene_conv%d/W" % (i + 1)].float().contiguous(),
+                     w[P_ + "scene_conv%d/b" % (i + 1)].float().contiguous())
+                    for i in range(len(self.cfg.scene_grid_strides))]
+    self.scales = [ScaleWeights(w, i, self.planes) if self.cfg.use_grids[i] else None
+                   for i in range(len(self.cfg.scene_grids))]
+
+  # ------------------------------------------------------------------ buffers
+  def _buf(self, key, maker):
+    b = self._bufs.get(key)
+    if b is None:
+      b = maker()
+      self._bufs[key] = b
+    return b
+
+  def _xh(self, tag, ns, h, w, cpad):
+    return [self._buf((tag, j, ns, h, w, cpad),
+                      lambda: ops.alloc_xh(ns, h, w, cpad, self.planes, self.device))
+            for j in range(2)]
+
+  def _state(self, tag, ns, h, w):
+    return self._buf((tag, ns, h, w), lambda: ops.alloc_state(ns, h, w, self.device))
+
+  # ------------------------------------------------------------------ pieces
+  def scene_cnn(self, scene_feat, obs_scene):
+    """code/pred_models.py:146-165 on the unique frames; returns per-scale [F,h,w,64] maps and
+    the per-sample time means used by the graph attention (:826-828)."""
+    x = scene_feat
+    convs, means = [], []
+    for (W, b) in self.scene_w:
+      x = ops.scene_conv_fwd(x, W, b)
+      convs.append(x)
+      means.append(ops.scene_time_mean(x, obs_scene))
+    return convs, means
+
+  def encode_class(self, i, scene_conv, obs_scene_t, labels_t, xh_out):
+    """Class encoder (:210-215).  obs_scene_t / labels_t: int32 [T,N].  Writes the planes of the
+    last h into the h block of xh_out (if given) and returns (c, h32) halo buffers."""
+    h, w = self.cfg.scene_grids[i]
+    n = labels_t.shape[1]
+    t_len = labels_t.shape[0]
+    sw = self.scales[i]
+    xh = self._xh("enc_class", n, h, w, sw.enc_class.cpad)
+    c = [self._state("enc_c0", n, h, w), self._state("enc_c1", n, h, w)]
+    h32 = self._state("enc_h32", n, h, w)
+    # a previous call left the label pixels of its last two steps in the x blocks: clear them
+    for j in range(2):
+      xh[j][:, :, :sw.enc_class.cxp].zero_()
+    xh[0][:, :, sw.enc_class.cxp:].zero_()   # h_0 = 0
+    for t in range(t_len):
+      cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+      ops.enc_class_input(scene_conv, obs_scene_t[t], labels_t[t],
+                          labels_t[t - 2] if t >= 2 else None, cur, h, w)
+      last = t == t_len - 1
+      ops.cell_fwd(cur, sw.enc_class, None if t == 0 else c[t % 2], c[(t + 1) % 2],
+                   h32 if last else None, xh_out if last else nxt, h, w, n)
+    return c[t_len % 2], h32
+
+  def encode_reg(self, i, obs_reg_t, xh_out):
+    """Regression encoder (:232-234).  obs_reg_t fp32 [T,N,h,w,2]."""
+    h, w = self.cfg.scene_grids[i]
+    t_len, n = obs_reg_t.shape[0], obs_reg_t.shape[1]
+    sw = self.scales[i]
+    xh = self._xh("enc_reg", n, h, w, sw.enc_reg.cpad)
+    c = [self._state("encr_c0", n, h, w), self._state("encr_c1", n, h, w)]
+    h32 = self._state("encr_h32", n, h, w)
+    xh[0][:, :, sw.enc_reg.cxp:].zero_()
+    for t in range(t_len):
+      cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+      ops.nhwc_to_planes(obs_reg_t[t], cur, 0, h, w, comp=sw.enc_reg.comp)
+      last = t == t_len - 1
+      ops.cell_fwd(cur, sw.enc_reg, None if t == 0 else c[t % 2], c[(t + 1) % 2],
+                   h32 if last else None, xh_out if last else nxt, h, w, n)
+    return c[t_len % 2], h32
+
+  def decode_class_greedy(self, i, c_enc, h32_enc, first_ids, scene_mean, pred_len):
+    """Greedy class decoder (:311-471, appendix A.1).  Returns logits [Tp,N,HW], ids [Tp,N]."""
+    cfg = self.cfg
+    h, w = cfg.scene_grids[i]
+    n = first_ids.shape[0]
+    sw = self.scales[i]
+    xh = self._xh("dec_class", n, h, w, sw.dec_class.cpad)
+    c = [self._state("dec_c0", n, h, w), self._state("dec_c1", n, h, w)]
+    h32 = self._state("dec_h32", n, h, w)
+    logits = torch.empty((pred_len, n, h * w), dtype=torch.float32, device=self.device)
+    ids = torch.empty((pred_len, n), dtype=torch.int32, device=self.device)
+    We, be = sw.emb_class
+    ops.emb_onehot_fwd(first_ids, We, be, xh[0], h, w)
+    h_src, c_src = h32_enc, c_enc
+    for t in range(pred_len):
+      cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+      if cfg.use_gnn:
+        ops.gnn_attend_fwd(h_src, scene_mean, cur, h, w, n)
+      elif t == 0:
+        # no attention: the planes of the encoder state must already sit in cur's h block
+        pass
+      ops.cell_fwd(cur, sw.dec_class, c_src, c[(t + 1) % 2], h32,
+                   None if cfg.use_gnn else nxt, h, w, n)
+      c_src, h_src = c[(t + 1) % 2], h32
+      last = t == pred_len - 1
+      ops.head_class_fwd(h32, sw.head_class, logits[t], ids[t], None if last else We,
+                         None if last else be, None if last else nxt, h, w, n,
+                         planes=self.planes)
+    return logits, ids
+
+  def decode_reg(self, i, c_enc, first_input, pred_len, xh):
+    """Regression decoder (:298-305): greedy, no attention, raw 2-channel feedback.  `xh` are
+    the decoder operand buffers whose xh[0] h block already holds the encoder state planes."""
+    h, w = self.cfg.scene_grids[i]
+    n = first_input.shape[0]
+    sw = self.scales[i]
+    c = [self._state("decr_c0", n, h, w), self._state("decr_c1", n, h, w)]
+    h32 = self._state("decr_h32", n, h, w)
+    offs = torch.empty((pred_len, n, h * w, 2), dtype=torch.float32, device=self.device)
+    We, be = sw.emb_reg
+    ops.emb_dense_fwd(first_input, We, be, xh[0], h, w)
+    c_src = c_enc
+    for t in range(pred_len):
+      cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+      ops.cell_fwd(cur, sw.dec_reg, c_src, c[(t + 1) % 2], h32, nxt, h, w, n)
+      c_src = c[(t + 1) % 2]
+      last = t == pred_len - 1
+      ops.head_reg_fwd(h32, sw.head_reg, offs[t], None if last else We, None if last else be,
+                       None if last else nxt, h, w, n, planes=self.planes)
+    return offs
+
+  def decode_class_beam(self, i, c_enc, h32_enc, first_ids, scene_mean, pred_len):
+    """K-way beam decoder (:474-806, appendix A.2).  Returns (out_logits [N,B,Tp,V],
+    out_ids [N,B,Tp] int32, scores [N,B])."""
+    cfg = self.cfg
+    h, w = cfg.scene_grids[i]
+    n, b, v = first_ids.shape[0], cfg.beam_size, h * w
+    ns = n * b
+    dev = self.device
+    sw = self.scales[i]
+    xh = self._xh("beam", ns, h, w, sw.dec_class.cpad)
+    c = [self._state("beam_c0", ns, h, w), self._state("beam_c1", ns, h, w)]
+    h32 = self._state("beam_h32", ns, h, w)
+    step_logits = torch.empty((pred_len, n, b, v), dtype=torch.float32, device=dev)
+    step_ids = torch.empty((pred_len, n, b), dtype=torch.int32, device=dev)
+    step_par = torch.empty((pred_len, n, b), dtype=torch.int32, device=dev)
+    scores = [torch.zeros((n, b), dtype=torch.float32, device=dev) for _ in range(2)]
+    row_map = torch.empty((ns,), dtype=torch.int32, device=dev)
+    tile_map = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(b).contiguous()
+    We, be = sw.emb_class
+    # time = 0: tiled encoder state and last observed cell (:497-502, :527-531)
+    ops.emb_onehot_fwd(first_ids.repeat_interleave(b).contiguous(), We, be, xh[0], h, w)
+    if cfg.use_gnn:
+      ops.gnn_attend_fwd(h32_enc, scene_mean, xh[0], h, w, ns, beam=b, row_map=tile_map)
+    else:
+      raise NotImplementedError("beam search without use_gnn is not wired (no published config)")
+    ops.cell_fwd(xh[0], sw.dec_class, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
+    cur_c = 1
+    for time in range(1, pred_len + 1):
+      ops.head_class_fwd(h32, sw.head_class, step_logits[time - 1], None, None, None, None, h, w,
+                         ns, planes=self.planes)
+      s_in, s_out = scores[(time - 1) % 2], scores[time % 2]
+      ops.beam_step(step_logits[time - 1], s_in, s_out, step_ids[time - 1], step_par[time - 1],
+                    row_map, n, b, v, first_step=(time <= 1),
+                    zero_scores=(time <= cfg.fix_num_timestep), diverse=cfg.diverse_beam,
+                    gamma=cfg.diverse_gamma)
+      if time == pred_len:
+        break
+      nxt = xh[time % 2]
+      ops.emb_onehot_fwd(step_ids[time - 1].view(-1), We, be, nxt, h, w)
+      ops.gnn_attend_fwd(h32, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
+      ops.cell_fwd(nxt, sw.dec_class, c[cur_c], c[1 - cur_c], h32, None, h, w, ns, row_map=row_map)
+      cur_c = 1 - cur_c
+    out_ids = torch.empty((n, b, pred_len), dtype=torch.int32, device=dev)
+    out_logits = torch.empty((n, b, pred_len, v), dtype=torch.float32, device=dev)
+    ops.beam_backtrace(step_ids, step_par, step_logits, out_ids, out_logits)
+    return out_logits, out_ids, scores[pred_len % 2], dict(ids=step_ids, parents=step_par,
+                                                           logits=step_logits)
+
+  # ------------------------------------------------------------------ whole forward
+  def forward(self, feeds):
+    """feeds: device tensors
+         scene_feat fp32 [F,SH,SW,SC], obs_scene int32 [N,T],
+         grid_obs_labels[i] int32 [N,T], grid_obs_regress[i] fp32 [N,T,h,w,2]
+    Returns a dict shaped like the reference fetches: grid_pred_decoded[i] [N,Tp,h,w,1],
+    grid_pred_reg_decoded[i] [N,Tp,h,w,2] ([] for unused scales, :170-171) and
+    beam_outputs = [logits [N,B,Tp,V], ids [N,B,Tp], logprobs [N,B]] or None (:276)."""
+    cfg = self.cfg
+    tp = cfg.pred_len
+    obs_scene = feeds["obs_scene"].to(torch.int32).contiguous()
+    obs_scene_t = obs_scene.t().contiguous()
+    n = obs_scene.shape[0]
+    convs, means = self.scene_cnn(feeds["scene_feat"].float().contiguous(), obs_scene)
+    out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
+    for i, (h, w) in enumerate(cfg.scene_grids):
+      if not cfg.use_grids[i]:
+        out["grid_pred_decoded"].append([])
+        out["grid_pred_reg_decoded"].append([])
+        continue
+      sw = self.scales[i]
+      labels = feeds["grid_obs_labels"][i].to(torch.int32)
+      labels_t = labels.t().contiguous()
+      obs_reg = feeds["grid_obs_regress"][i].float()
+      obs_reg_t = obs_reg.transpose(0, 1).contiguous()
+      # class branch
+      xh_dec = self._xh("dec_class", n, h, w, sw.dec_class.cpad)
+      c_e, h_e = self.encode_class(i, convs[i], obs_scene_t, labels_t,
+                                   None if cfg.use_gnn else xh_dec[0])
+      if cfg.use_beam_search:
+        logits, ids, logprobs, _ = self.decode_class_beam(i, c_e, h_e, labels_t[-1].contiguous(),
+                                                          means[i], tp)
+        out["beam_outputs"] = [logits, ids, logprobs]
+        dec = logits[:, 0].reshape(n, tp, h, w, 1)                      # :799-803
+      else:
+        lg, _ = self.decode_class_greedy(i, c_e, h_e, labels_t[-1].contiguous(), means[i], tp)
+        dec = lg.permute(1, 0, 2).reshape(n, tp, h, w, 1)
+      # regression branch
+      xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad)
+      c_r, _ = self.encode_reg(i, obs_reg_t, xh_reg[0])
+      offs = self.decode_reg(i, c_r, obs_reg_t[-1], tp, xh_reg)
+      reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)
+      out["grid_pred_decoded"].append(dec)
+      out["grid_pred_reg_decoded"].append(reg)
+    return out

@@ -49,7 +49,7 @@ def reset_launch_count():
 class PackedCell(object):
   """Device-resident packed weights of one ConvLSTM cell (see mvb_pack_cell_weights)."""
 
-  def __init__(self, kernel, biases, planes=None):
+  def __init__(self, kernel, biases, planes=None, comp=False):
     planes = planes or DEFAULT_PLANES
     assert kernel.dim() == 4 and kernel.shape[0] == 3 and kernel.shape[1] == 3
     assert kernel.shape[3] == 4 * HIDDEN
@@ -57,13 +57,14 @@ class PackedCell(object):
     self.cxp = (self.cx + 31) // 32 * 32
     self.cpad = self.cxp + HIDDEN
     self.planes = planes
+    self.comp = bool(comp) and planes == 2 and 4 * self.cx <= self.cxp
     kernel = kernel.detach().to(torch.float32).contiguous()
     biases = biases.detach().to(torch.float32).contiguous()
     self.w = torch.empty((planes, 4 * HIDDEN, 9 * self.cpad), dtype=torch.bfloat16,
                          device=kernel.device)
     self.bias = torch.empty((4 * HIDDEN,), dtype=torch.float32, device=kernel.device)
     _lib.call("mvb_pack_cell_weights", _p(kernel), _p(biases), _p(self.w), _p(self.bias),
-              self.cx, planes, _stream())
+              self.cx, planes, int(self.comp), _stream())
 
 
 def alloc_xh(ns, h, w, cpad, planes, device):
@@ -90,10 +91,10 @@ def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
             packed.cpad, packed.planes, float(forget_bias), _stream())
 
 
-def nhwc_to_planes(src, xh, ch_off, h, w):
+def nhwc_to_planes(src, xh, ch_off, h, w, comp=False):
   ns, c = src.shape[0], src.shape[-1]
   _lib.call("mvb_nhwc_to_planes", _p(src), _p(xh), xh.stride(0), xh.shape[2], ch_off, ns, h, w,
-            c, xh.shape[0], _stream())
+            c, xh.shape[0], int(comp), _stream())
 
 
 def nhwc_to_halo(src, dst, h, w):

@@ -1,0 +1,176 @@
+# coding=utf-8
+"""torch-CPU fp32 restatement of the reference forward pass, used ONLY as the timed CPU baseline
+(bench.py ``cpu_baseline`` / ``--impl reference``) and as an independent cross-check of
+``oracle/multiverse_ref.py`` in tests.  TEST INFRASTRUCTURE - never imported by multiverse_b200.
+
+PARITY UNPINNED (see multiverse_ref.py): TensorFlow 1.15 cannot run here, so "the reference's
+own CPU path" is this restatement of code/pred_models.py with the same op decomposition TF uses
+(conv2d -> oneDNN convolution, dense [HW,HW] graph attention via batched matmul, full sort for
+the diverse-beam rank), running on all host threads.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import multiverse_ref as R
+
+
+def conv2d_same(x, w, stride=1):
+  """tf.nn.conv2d(..., "SAME") on NHWC tensors / HWIO filters (code/pred_models.py:1363)."""
+  n, h, wd, c = x.shape
+  kh, kw = w.shape[0], w.shape[1]
+  _, pt, pb = R.same_pad(h, kh, stride)
+  _, pl, pr = R.same_pad(wd, kw, stride)
+  xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+  y = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=stride)
+  return y.permute(0, 2, 3, 1)
+
+
+def convlstm_cell(x, c, h, kernel, biases, forget_bias=1.0):
+  """ConvLSTMCell.call (TF 1.15), code/pred_models.py:189-202,:236-249."""
+  g = conv2d_same(torch.cat([x, h], dim=-1), kernel) + biases
+  gi, gj, gf, go = torch.split(g, g.shape[-1] // 4, dim=-1)
+  new_c = torch.sigmoid(gf + forget_bias) * c + torch.sigmoid(gi) * torch.tanh(gj)
+  return new_c, torch.tanh(new_c) * torch.sigmoid(go)
+
+
+def neighbour_mask(h, w):
+  eye = torch.eye(h * w).reshape(h * w, h, w, 1)
+  return conv2d_same(eye, torch.ones(3, 3, 1, 1)).reshape(h * w, h * w)
+
+
+def gnn_dense(hs, scene_mean, mask):
+  """gnn_edge + gnn_mask_edge(exp_mask) + gnn_node + residual, code/pred_models.py:808-909,:378."""
+  n, h, w, d = hs.shape
+  feats = hs.reshape(n, h * w, d)
+  if scene_mean is not None:
+    feats = torch.cat([feats, scene_mean.reshape(n, h * w, -1)], dim=-1)
+  fn = feats * torch.rsqrt(torch.clamp((feats * feats).sum(-1, keepdim=True), min=1e-12))
+  edge = torch.bmm(fn, fn.transpose(1, 2)) + (1.0 - mask)[None] * -1e30
+  a = torch.softmax(edge, dim=-1)
+  return hs + torch.bmm(a, hs.reshape(n, h * w, d)).reshape(n, h, w, d)
+
+
+def grid_emb(x, W, b):
+  return torch.tanh(conv2d_same(x, W) + b)
+
+
+def encoder(inputs, kernel, biases, ch):
+  n, t, h, w, _ = inputs.shape
+  c = torch.zeros(n, h, w, ch)
+  hs = torch.zeros(n, h, w, ch)
+  for s in range(t):
+    c, hs = convlstm_cell(inputs[:, s], c, hs, kernel, biases)
+  return c, hs
+
+
+def one_hot_map(ids, h, w):
+  return F.one_hot(ids.long(), h * w).float().reshape(-1, h, w, 1)
+
+
+def decoder_greedy(first, state, tp, cell_w, emb_w, head_w, scene_mean, mask, use_gnn, onehot):
+  """Model.grid_decoder at inference, code/pred_models.py:311-471."""
+  c, h = state
+  n, hh, ww, p = first.shape
+  inp, outs = first, []
+  for _ in range(tp):
+    h_in = gnn_dense(h, scene_mean, mask) if use_gnn else h
+    c, h = convlstm_cell(grid_emb(inp, *emb_w), c, h_in, *cell_w)
+    o = conv2d_same(h, head_w)
+    outs.append(o)
+    inp = one_hot_map(o.reshape(n, -1).argmax(1), hh, ww) if onehot else o
+  return torch.stack(outs, 1)
+
+
+def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, diverse, gamma,
+                 fix_num_timestep):
+  """Model.grid_decoder_beam_search, code/pred_models.py:474-806 (diverse rank through a full
+  sort, as add_div_penalty :1197-1223 does)."""
+  c0, h0 = state
+  n, hh, ww, _ = h0.shape
+  v = hh * ww
+  rep = lambda t: t.repeat_interleave(b, dim=0)
+  c, h, inp, sm = rep(c0), rep(h0), rep(first), rep(scene_mean)
+  score = torch.zeros(n, b)
+  ids_l, par_l, log_l = [], [], []
+
+  def step(inp, c, h):
+    return convlstm_cell(grid_emb(inp, *emb_w), c, gnn_dense(h, sm, mask), *cell_w)
+
+  c, h = step(inp, c, h)
+  for time in range(1, tp + 1):
+    logits = conv2d_same(h, head_w).reshape(n, b, v)
+    lp = torch.log_softmax(logits, -1) + score[:, :, None]
+    if diverse:
+      order = torch.argsort(lp, dim=-1, descending=True, stable=True)
+      rank = torch.empty_like(order)
+      rank.scatter_(-1, order, torch.arange(v).expand_as(order))
+      lp = lp + math.log(gamma) * rank.float()
+    cand = lp.reshape(n, b * v) if time > 1 else lp[:, 0]
+    sc, idx = torch.topk(cand, b, dim=-1, sorted=True)
+    if time <= fix_num_timestep:
+      sc = torch.zeros_like(sc)
+    ids, par = idx % v, idx // v
+    ids_l.append(ids); par_l.append(par); log_l.append(logits)
+    score = sc
+    flat = (par + (torch.arange(n) * b)[:, None]).reshape(-1)
+    c, h = c[flat], h[flat]
+    inp = one_hot_map(ids.reshape(-1), hh, ww)
+    if time == tp:
+      break
+    c, h = step(inp, c, h)
+  parents = torch.arange(b)[None].repeat(n, 1)
+  rows = torch.arange(n)[:, None]
+  out_ids = torch.zeros(n, b, tp, dtype=torch.long)
+  out_logits = torch.zeros(n, b, tp, v)
+  for tau in range(tp - 1, -1, -1):
+    out_ids[:, :, tau] = ids_l[tau][rows, parents]
+    out_logits[:, :, tau] = log_l[tau][rows, parents]
+    parents = par_l[tau][rows, parents]
+  return out_logits, out_ids, score
+
+
+@torch.no_grad()
+def forward(cfg, weights, feeds):
+  """Model.build_forward at inference (code/pred_models.py:123-308), fp32, torch CPU."""
+  w = {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in weights.items()}
+  n = cfg.batch_size
+  scene_feat = torch.from_numpy(feeds["scene_feat"]).float()
+  obs_scene = torch.from_numpy(feeds["obs_scene"]).long()
+  x = scene_feat[obs_scene.reshape(-1)]              # embedding_lookup, :148-152
+  convs = []
+  for i in range(len(cfg.scene_grid_strides)):
+    x = torch.tanh(conv2d_same(x, w["person_pred/scene_conv%d/W" % (i + 1)], 2)
+                   + w["person_pred/scene_conv%d/b" % (i + 1)])
+    convs.append(x.reshape((n, -1) + tuple(x.shape[1:])))
+  out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
+  for i, (h, ww) in enumerate(cfg.scene_grids):
+    if not cfg.use_grids[i]:
+      out["grid_pred_decoded"].append([]); out["grid_pred_reg_decoded"].append([])
+      continue
+    sw = R.scale_weights(w, i)
+    labels = torch.from_numpy(feeds["grid_obs_labels"][i]).long()
+    onehot = F.one_hot(labels, h * ww).float().reshape(n, -1, h, ww, 1)
+    obs_reg = torch.from_numpy(feeds["grid_obs_regress"][i]).float()
+    mask = neighbour_mask(h, ww)
+    enc = encoder(convs[i] * onehot, sw.enc_class[0], sw.enc_class[1], cfg.enc_hidden_size)
+    enc_r = encoder(obs_reg, sw.enc_reg[0], sw.enc_reg[1], cfg.enc_hidden_size)
+    scene_mean = convs[i].mean(1)
+    if cfg.use_beam_search:
+      lg, ids, sc = decoder_beam(onehot[:, -1], enc, cfg.pred_len, cfg.beam_size, sw.dec_class,
+                                 sw.emb_class, sw.head_class, scene_mean, mask, cfg.diverse_beam,
+                                 cfg.diverse_gamma, cfg.fix_num_timestep)
+      out["beam_outputs"] = [lg.numpy(), ids.numpy().astype(np.int32), sc.numpy()]
+      dec = lg[:, 0].reshape(n, cfg.pred_len, h, ww, 1)
+    else:
+      dec = decoder_greedy(onehot[:, -1], enc, cfg.pred_len, sw.dec_class, sw.emb_class,
+                           sw.head_class, scene_mean, mask, cfg.use_gnn, True)
+    reg = decoder_greedy(obs_reg[:, -1], enc_r, cfg.pred_len, sw.dec_reg, sw.emb_reg, sw.head_reg,
+                         None, None, False, False)
+    out["grid_pred_decoded"].append(dec.numpy())
+    out["grid_pred_reg_decoded"].append(reg.numpy())
+  return out

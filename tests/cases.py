@@ -1,0 +1,84 @@
+# coding=utf-8
+"""Seeded unit-case inputs shared by tests/golden/make_golden.py and the parity tests.
+
+Inputs are regenerated from the seed (the 12 MB ConvLSTM kernels are not committed); every golden
+file stores a checksum of the regenerated inputs so a drifting generator is detected, plus the
+oracle's fp64 outputs."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+CELL_CASES = {
+    # name: (ns, h, w, cx, x_scale, seed)
+    "dec_cx32": (2, 6, 5, 32, 1.0, 11),
+    "enc_class_cx64": (3, 5, 7, 64, 1.0, 12),
+    "enc_reg_cx2": (2, 7, 4, 2, 600.0, 13),      # raw pixel offsets: large magnitude
+    "tile_edge": (5, 9, 5, 32, 1.0, 14),          # 300 halo rows: crosses a 128-row M tile
+}
+
+
+def checksum(*arrays):
+  return float(sum(float(np.sum(np.asarray(a, dtype=np.float64))) for a in arrays))
+
+
+def cell_case(name):
+  ns, h, w, cx, xs, seed = CELL_CASES[name]
+  rng = np.random.default_rng(seed)
+  ch = 256
+  lim = math.sqrt(6.0 / (9 * (cx + ch) + 9 * 4 * ch))
+  kernel = rng.uniform(-lim, lim, size=(3, 3, cx + ch, 4 * ch)).astype(np.float32)
+  biases = (rng.standard_normal(4 * ch) * 0.1).astype(np.float32)
+  x = (rng.standard_normal((ns, h, w, cx)) * xs).astype(np.float32)
+  hh = np.tanh(rng.standard_normal((ns, h, w, ch))).astype(np.float32)
+  c = rng.standard_normal((ns, h, w, ch)).astype(np.float32)
+  return dict(x=x, h=hh, c=c, kernel=kernel, biases=biases)
+
+
+def gnn_case(seed=21, ns=3, h=5, w=4):
+  rng = np.random.default_rng(seed)
+  return dict(h=np.tanh(rng.standard_normal((ns, h, w, 256))).astype(np.float32),
+              scene=np.tanh(rng.standard_normal((ns, h, w, 64))).astype(np.float32))
+
+
+def head_case(seed=31, ns=3, h=6, w=5, e=32):
+  rng = np.random.default_rng(seed)
+  return dict(h=np.tanh(rng.standard_normal((ns, h, w, 256))).astype(np.float32),
+              Wo1=(rng.standard_normal((3, 3, 256, 1)) * 0.1).astype(np.float32),
+              Wo2=(rng.standard_normal((3, 3, 256, 2)) * 0.1).astype(np.float32),
+              We1=(rng.standard_normal((3, 3, 1, e)) * 0.5).astype(np.float32),
+              We2=(rng.standard_normal((3, 3, 2, e)) * 0.5).astype(np.float32),
+              be=(rng.standard_normal(e) * 0.2).astype(np.float32))
+
+
+def beam_case(seed=41, n=3, b=5, v=30):
+  rng = np.random.default_rng(seed)
+  logits = (rng.standard_normal((n, b, v)) * 2).astype(np.float32)
+  logits[0, 1, 7] = logits[0, 1, 3]          # exact tie inside a row (rank / top-k tie-break)
+  score = (-np.abs(rng.standard_normal((n, b)))).astype(np.float32)
+  return dict(logits=logits, score=score)
+
+
+def scene_case(seed=51, f=3, sh=12, sw=10, sc=11):
+  rng = np.random.default_rng(seed)
+  seg = rng.integers(0, sc, size=(f, sh, sw))
+  feat = np.eye(sc, dtype=np.float32)[seg]
+  return dict(scene_feat=feat,
+              W1=(rng.standard_normal((3, 3, sc, 64)) * 0.2).astype(np.float32),
+              b1=(rng.standard_normal(64) * 0.1).astype(np.float32),
+              W2=(rng.standard_normal((3, 3, 64, 64)) * 0.1).astype(np.float32),
+              b2=(rng.standard_normal(64) * 0.1).astype(np.float32),
+              obs_scene=rng.integers(0, f, size=(4, 8)).astype(np.int32))
+
+
+ROLLOUTS = {
+    # name: config overrides (oracle.default_config), seed
+    "greedy_two_scale": (dict(batch_size=2), 0),
+    "beam_k20_diverse": (dict(batch_size=2, use_grids=[True, False], use_beam_search=True,
+                              beam_size=20, diverse_beam=True, diverse_gamma=0.01,
+                              fix_num_timestep=1), 1),
+    "beam_k5_plain": (dict(batch_size=2, use_grids=[False, True], use_beam_search=True,
+                           beam_size=5, diverse_beam=False, fix_num_timestep=0), 2),
+    "greedy_native_18x32": (dict(batch_size=2, scene_h=36, scene_w=64, use_grids=[True, False]), 3),
+}

@@ -1,0 +1,324 @@
+# coding=utf-8
+"""GPU parity tests: every kernel of libmultiverse_b200 (called through the C ABI via
+multiverse_b200.ops) against the CPU oracle's committed fp64 vectors and live oracle runs.
+
+Bars (BASELINE.json north_star): arg-max / beam ids bit-exact, (h,c) and offsets <= 1e-4 relative
+(measured as max|diff| / max|ref| per tensor)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import multiverse_ref as R
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-4     # the north_star's fp32 bar
+TIGHT = 3e-5   # what the P=2 plane scheme actually delivers per kernel
+
+
+def gold(name):
+  return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def rel(a, b):
+  a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+  return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+  from multiverse_b200 import build
+  build.build()
+  return torch.device("cuda:0")
+
+
+def T(a, dev):
+  return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def run_cell(d, dev, planes, comp=False, zero_c=False):
+  from multiverse_b200 import ops
+  ns, h, w, cx = d["x"].shape
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), planes, comp=comp)
+  xh = ops.alloc_xh(ns, h, w, pk.cpad, planes, dev)
+  xh2 = ops.alloc_xh(ns, h, w, pk.cpad, planes, dev)
+  ops.nhwc_to_planes(T(d["x"], dev), xh, 0, h, w, comp=pk.comp)
+  ops.nhwc_to_planes(T(d["h"], dev), xh, pk.cxp, h, w)
+  c_in = ops.alloc_state(ns, h, w, dev)
+  ops.nhwc_to_halo(T(d["c"], dev), c_in, h, w)
+  c_out = ops.alloc_state(ns, h, w, dev); h_out = ops.alloc_state(ns, h, w, dev)
+  ops.cell_fwd(xh, pk, None if zero_c else c_in, c_out, h_out, xh2, h, w, ns)
+  co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
+  ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
+  planes_sum = xh2[:, :, pk.cxp:].float().sum(0).view(ns, h + 1, w + 1, 256)
+  halo = xh2.float().view(planes, ns, h + 1, w + 1, -1)
+  assert float(halo[:, :, h].abs().max()) == 0.0 and float(halo[:, :, :, w].abs().max()) == 0.0, \
+      "kernel wrote into the zero halo"
+  return co.cpu().numpy(), ho.cpu().numpy(), planes_sum[:, :h, :w].cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(cases.CELL_CASES))
+def test_cell_golden(dev, name):
+  d = cases.cell_case(name); g = gold("cell_" + name)
+  comp = name == "enc_reg_cx2"
+  c, h, hp = run_cell(d, dev, 2, comp=comp)
+  assert rel(c, g["c"]) < TIGHT and rel(h, g["h"]) < TIGHT
+  assert np.abs(hp - h).max() < 2e-5          # bf16 planes of h' sum back to h'
+  c0, h0, _ = run_cell(d, dev, 2, comp=comp, zero_c=True)
+  assert rel(c0, g["c_zero"]) < TIGHT and rel(h0, g["h_zero"]) < TIGHT
+
+
+def test_cell_three_planes_and_plain_bf16(dev):
+  d = cases.cell_case("dec_cx32"); g = gold("cell_dec_cx32")
+  c3, h3, _ = run_cell(d, dev, 3)
+  assert rel(c3, g["c"]) < TIGHT and rel(h3, g["h"]) < TIGHT
+  c1, h1, _ = run_cell(d, dev, 1)             # plain bf16: works, but misses the fp32 bar
+  assert rel(h1, g["h"]) < 2e-2 and rel(h1, g["h"]) > TOL
+
+
+def test_cell_large_input_needs_compensation(dev):
+  d = cases.cell_case("enc_reg_cx2"); g = gold("cell_enc_reg_cx2")
+  _, h_comp, _ = run_cell(d, dev, 2, comp=True)
+  _, h_plain, _ = run_cell(d, dev, 2, comp=False)
+  assert rel(h_comp, g["h"]) < TIGHT
+  assert rel(h_comp, g["h"]) < rel(h_plain, g["h"])
+
+
+def test_cell_is_deterministic_and_batch_separable(dev):
+  d = cases.cell_case("tile_edge")
+  c_a, h_a, _ = run_cell(d, dev, 2)
+  c_b, h_b, _ = run_cell(d, dev, 2)
+  assert np.array_equal(c_a, c_b) and np.array_equal(h_a, h_b)
+  sub = {k: (v[1:3] if k in ("x", "h", "c") else v) for k, v in d.items()}
+  c_s, h_s, _ = run_cell(sub, dev, 2)
+  assert np.array_equal(c_s, c_a[1:3]) and np.array_equal(h_s, h_a[1:3])   # rows never mix
+
+
+def test_cell_row_map_gathers_state(dev):
+  from multiverse_b200 import ops
+  d = cases.cell_case("dec_cx32")
+  ns, h, w, cx = d["x"].shape
+  perm = np.array([1, 1], dtype=np.int32)
+  q = {k: v.astype(np.float64) for k, v in d.items()}
+  c_ref, h_ref = R.convlstm_cell(q["x"], q["c"][perm], q["h"], q["kernel"], q["biases"])
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), 2)
+  xh = ops.alloc_xh(ns, h, w, pk.cpad, 2, dev)
+  ops.nhwc_to_planes(T(d["x"], dev), xh, 0, h, w); ops.nhwc_to_planes(T(d["h"], dev), xh, pk.cxp, h, w)
+  c_in = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(d["c"], dev), c_in, h, w)
+  c_out = ops.alloc_state(ns, h, w, dev); h_out = ops.alloc_state(ns, h, w, dev)
+  ops.cell_fwd(xh, pk, c_in, c_out, h_out, None, h, w, ns, row_map=T(perm, dev))
+  co = torch.empty((ns, h, w, 256), device=dev); ops.halo_to_nhwc(c_out, co, h, w)
+  assert rel(co.cpu().numpy(), c_ref) < TIGHT
+
+
+def test_layout_round_trip(dev):
+  from multiverse_b200 import ops
+  x = torch.randn(3, 7, 5, 256, device=dev)
+  halo = ops.alloc_state(3, 7, 5, dev)
+  ops.nhwc_to_halo(x, halo, 7, 5)
+  back = torch.empty_like(x)
+  ops.halo_to_nhwc(halo, back, 7, 5)
+  assert torch.equal(x, back)
+  v = halo.view(3, 8, 6, 256)
+  assert float(v[:, 7].abs().max()) == 0 and float(v[:, :, 5].abs().max()) == 0
+
+
+@pytest.mark.parametrize("with_scene", [True, False])
+def test_gnn_golden(dev, with_scene):
+  from multiverse_b200 import ops
+  d = cases.gnn_case(); g = gold("gnn")
+  ns, h, w, _ = d["h"].shape
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(d["h"], dev), h32, h, w)
+  xh = ops.alloc_xh(ns, h, w, 288, 2, dev)
+  ops.gnn_attend_fwd(h32, T(d["scene"], dev) if with_scene else None, xh, h, w, ns)
+  out = xh[:, :, 32:].float().sum(0).view(ns, h + 1, w + 1, 256)[:, :h, :w].cpu().numpy()
+  assert rel(out, g["with_scene" if with_scene else "no_scene"]) < TIGHT
+  assert float(xh[:, :, :32].abs().max()) == 0.0
+
+
+def test_gnn_row_map_and_beam_tiling(dev):
+  from multiverse_b200 import ops
+  d = cases.gnn_case()
+  ns, h, w, _ = d["h"].shape
+  b = 2
+  rows = np.array([2, 0, 1, 1, 0, 2], dtype=np.int32)       # beam row s reads h of sample row rows[s]
+  ref = R.gnn_dense(d["h"].astype(np.float64)[rows], np.repeat(d["scene"].astype(np.float64), b, 0))
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(d["h"], dev), h32, h, w)
+  xh = ops.alloc_xh(ns * b, h, w, 288, 2, dev)
+  ops.gnn_attend_fwd(h32, T(d["scene"], dev), xh, h, w, ns * b, beam=b, row_map=T(rows, dev))
+  out = xh[:, :, 32:].float().sum(0).view(ns * b, h + 1, w + 1, 256)[:, :h, :w].cpu().numpy()
+  assert rel(out, ref) < TIGHT
+
+
+def test_heads_and_embeddings_golden(dev):
+  from multiverse_b200 import ops
+  d = cases.head_case(); g = gold("head")
+  ns, h, w, _ = d["h"].shape
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(d["h"], dev), h32, h, w)
+  xh = ops.alloc_xh(ns, h, w, 288, 2, dev)
+  logits = torch.empty((ns, h * w), device=dev); ids = torch.empty((ns,), dtype=torch.int32, device=dev)
+  ops.head_class_fwd(h32, T(d["Wo1"], dev), logits, ids, T(d["We1"], dev), T(d["be"], dev), xh, h, w, ns)
+  assert rel(logits.cpu().numpy().reshape(ns, h, w, 1), g["logits"]) < TIGHT
+  assert np.array_equal(ids.cpu().numpy(), g["ids"])
+  emb = xh[:, :, :32].float().sum(0).view(ns, h + 1, w + 1, 32)[:, :h, :w].cpu().numpy()
+  assert rel(emb, g["emb_onehot"]) < TIGHT
+  xh.zero_()
+  ops.emb_onehot_fwd(T(g["ids"], dev), T(d["We1"], dev), T(d["be"], dev), xh, h, w)
+  emb = xh[:, :, :32].float().sum(0).view(ns, h + 1, w + 1, 32)[:, :h, :w].cpu().numpy()
+  assert rel(emb, g["emb_onehot"]) < TIGHT
+  xh.zero_()
+  off = torch.empty((ns, h * w, 2), device=dev)
+  ops.head_reg_fwd(h32, T(d["Wo2"], dev), off, T(d["We2"], dev), T(d["be"], dev), xh, h, w, ns)
+  assert rel(off.cpu().numpy().reshape(ns, h, w, 2), g["offsets"]) < TIGHT
+  emb = xh[:, :, :32].float().sum(0).view(ns, h + 1, w + 1, 32)[:, :h, :w].cpu().numpy()
+  assert rel(emb, g["emb_dense"]) < TIGHT
+  xh.zero_()
+  ops.emb_dense_fwd(T(g["offsets"].astype(np.float32), dev), T(d["We2"], dev), T(d["be"], dev), xh, h, w)
+  emb = xh[:, :, :32].float().sum(0).view(ns, h + 1, w + 1, 32)[:, :h, :w].cpu().numpy()
+  assert rel(emb, g["emb_dense"]) < TIGHT
+  assert float(xh[:, :, 32:].abs().max()) == 0.0 and float(xh.view(2, ns, h + 1, w + 1, -1)[:, :, h].abs().max()) == 0.0
+
+
+def test_argmax_first_index_on_ties(dev):
+  from multiverse_b200 import ops
+  ns, h, w = 2, 4, 3
+  hh = np.zeros((ns, h, w, 256), dtype=np.float32)
+  hh[0, 1, 1, 0] = 1.0; hh[0, 2, 2, 0] = 1.0       # two identical maxima -> lower flat index
+  hh[1, 3, 0, 0] = 2.0
+  Wo = np.zeros((3, 3, 256, 1), dtype=np.float32); Wo[1, 1, 0, 0] = 1.0
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(hh, dev), h32, h, w)
+  logits = torch.empty((ns, h * w), device=dev); ids = torch.empty((ns,), dtype=torch.int32, device=dev)
+  ops.head_class_fwd(h32, T(Wo, dev), logits, ids, None, None, None, h, w, ns)
+  assert ids.cpu().tolist() == [1 * w + 1, 3 * w + 0]
+
+
+@pytest.mark.parametrize("tag,first,zero,div", [("first", 1, 1, 1), ("mid", 0, 0, 1), ("plain", 0, 0, 0),
+                                                ("first_plain", 1, 0, 0)])
+def test_beam_step_golden(dev, tag, first, zero, div):
+  from multiverse_b200 import ops
+  d = cases.beam_case(); g = gold("beam_step")
+  n, b, v = d["logits"].shape
+  so = torch.empty((n, b), device=dev)
+  ids = torch.empty((n, b), dtype=torch.int32, device=dev); par = torch.empty_like(ids)
+  rm = torch.empty((n * b,), dtype=torch.int32, device=dev)
+  ops.beam_step(T(d["logits"], dev), T(d["score"], dev), so, ids, par, rm, n, b, v, first, zero, div, 0.01)
+  assert np.array_equal(ids.cpu().numpy(), g[tag + "_ids"])
+  assert np.array_equal(par.cpu().numpy(), g[tag + "_parents"])
+  assert np.abs(so.cpu().numpy() - g[tag + "_score"]).max() < 2e-5
+  assert np.array_equal(rm.cpu().numpy().reshape(n, b), g[tag + "_parents"] + (np.arange(n) * b)[:, None])
+
+
+def test_beam_backtrace_matches_oracle(dev):
+  from multiverse_b200 import ops
+  rng = np.random.default_rng(7)
+  tp, n, b, v = 6, 3, 4, 11
+  ids = rng.integers(0, v, size=(tp, n, b)).astype(np.int32)
+  par = rng.integers(0, b, size=(tp, n, b)).astype(np.int32)
+  lg = rng.standard_normal((tp, n, b, v)).astype(np.float32)
+  out_ids = torch.empty((n, b, tp), dtype=torch.int32, device=dev)
+  out_lg = torch.empty((n, b, tp, v), device=dev)
+  ops.beam_backtrace(T(ids, dev), T(par, dev), T(lg, dev), out_ids, out_lg)
+  p = np.tile(np.arange(b)[None], (n, 1)); rows = np.arange(n)[:, None]
+  for tau in range(tp - 1, -1, -1):     # code/pred_models.py:727-749, literally
+    assert np.array_equal(out_ids[:, :, tau].cpu().numpy(), ids[tau][rows, p])
+    assert np.array_equal(out_lg[:, :, tau].cpu().numpy(), lg[tau][rows, p])
+    p = par[tau][rows, p]
+
+
+def test_scene_cnn_golden(dev):
+  from multiverse_b200 import ops
+  d = cases.scene_case(); g = gold("scene")
+  c1 = ops.scene_conv_fwd(T(d["scene_feat"], dev), T(d["W1"], dev), T(d["b1"], dev))
+  c2 = ops.scene_conv_fwd(c1, T(d["W2"], dev), T(d["b2"], dev))
+  idx = d["obs_scene"]
+  assert rel(c1.cpu().numpy()[idx], g["conv1"]) < TIGHT and rel(c2.cpu().numpy()[idx], g["conv2"]) < TIGHT
+  m1 = ops.scene_time_mean(c1, T(idx, dev)); m2 = ops.scene_time_mean(c2, T(idx, dev))
+  assert rel(m1.cpu().numpy(), g["mean1"]) < TIGHT and rel(m2.cpu().numpy(), g["mean2"]) < TIGHT
+
+
+def test_enc_class_input_sets_and_clears(dev):
+  from multiverse_b200 import ops
+  ns, h, w = 3, 5, 4
+  sc = torch.randn(2, h, w, 64, device=dev)
+  xh = ops.alloc_xh(ns, h, w, 320, 2, dev)
+  fi = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)
+  l0 = torch.tensor([3, 7, 19], dtype=torch.int32, device=dev)
+  l1 = torch.tensor([3, 8, 0], dtype=torch.int32, device=dev)
+  ops.enc_class_input(sc, fi, l0, None, xh, h, w)
+  ops.enc_class_input(sc, fi, l1, l0, xh, h, w)
+  dense = xh[:, :, :64].float().sum(0).view(ns, h + 1, w + 1, 64)[:, :h, :w]
+  want = torch.zeros(ns, h * w, 64, device=dev)
+  for s in range(ns):
+    want[s, int(l1[s])] = sc[int(fi[s])].view(h * w, 64)[int(l1[s])]
+  assert float((dense.reshape(ns, h * w, 64) - want).abs().max()) < 1e-4
+
+
+def to_dev(feeds, dev):
+  return dict(scene_feat=T(feeds["scene_feat"], dev), obs_scene=T(feeds["obs_scene"], dev),
+              grid_obs_labels=[T(a, dev) for a in feeds["grid_obs_labels"]],
+              grid_obs_regress=[T(a, dev) for a in feeds["grid_obs_regress"]])
+
+
+@pytest.mark.parametrize("name", sorted(cases.ROLLOUTS))
+def test_rollout_golden(dev, name):
+  """Whole forward (scene CNN -> encoders -> decoders) against the oracle's fp64 rollouts:
+  greedy two-scale, K=20 diverse beam, K=5 plain beam on the coarse grid, native 18x32 grid."""
+  from multiverse_b200.engine import ConvRNNEngine
+  over, seed = cases.ROLLOUTS[name]
+  cfg = R.default_config(**over)
+  w = R.make_weights(cfg, seed); f = R.make_inputs(cfg, seed)
+  g = gold("rollout_" + name)
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  out = eng.forward(to_dev(f, dev))
+  n, tp = cfg.batch_size, cfg.pred_len
+  for i in range(len(cfg.scene_grids)):
+    if not cfg.use_grids[i]:
+      assert out["grid_pred_decoded"][i] == [] and out["grid_pred_reg_decoded"][i] == []
+      continue
+    lg = out["grid_pred_decoded"][i].cpu().numpy(); reg = out["grid_pred_reg_decoded"][i].cpu().numpy()
+    assert lg.shape == g["logits_%d" % i].shape and reg.shape == g["reg_%d" % i].shape
+    assert rel(lg, g["logits_%d" % i]) < TOL
+    assert rel(reg, g["reg_%d" % i]) < TOL
+    if not cfg.use_beam_search:
+      safe = g["margin_%d" % i] > 1e-4         # fp64 top-1/top-2 margin >> kernel error
+      a = lg.reshape(n, tp, -1).argmax(-1); b = g["logits_%d" % i].reshape(n, tp, -1).argmax(-1)
+      assert safe.mean() > 0.9 and np.array_equal(a[safe], b[safe])
+  if cfg.use_beam_search:
+    blg, ids, lp = [t.cpu().numpy() for t in out["beam_outputs"]]
+    assert ids.dtype == np.int32 and np.array_equal(ids, g["beam_ids"])
+    assert np.abs(lp - g["beam_logprobs"]).max() < 1e-3
+    assert rel(blg[:, :3], g["beam_logits_top3"]) < TOL
+  # second call on the same engine (buffer reuse) is bit-identical
+  out2 = eng.forward(to_dev(f, dev))
+  for i in range(len(cfg.scene_grids)):
+    if cfg.use_grids[i]:
+      assert torch.equal(out["grid_pred_decoded"][i], out2["grid_pred_decoded"][i])
+      assert torch.equal(out["grid_pred_reg_decoded"][i], out2["grid_pred_reg_decoded"][i])
+
+
+def test_full_size_properties(dev):
+  """BASELINE-size batch (config 3 shape, N=64 here): size-independent properties - a batch is the
+  concatenation of its shards (what multi-GPU sharding relies on), outputs are finite, halos stay
+  zero, and the fetched logits arg-max equals the ids the decoder fed back."""
+  from multiverse_b200.engine import ConvRNNEngine
+  cfg = R.default_config(batch_size=64)
+  w = R.make_weights(cfg, 9); f = R.make_inputs(cfg, 9)
+  wt = {k: torch.from_numpy(v) for k, v in w.items()}
+  full = ConvRNNEngine(cfg, wt, dev, 2).forward(to_dev(f, dev))
+  half_cfg = R.default_config(batch_size=32)
+  eng_h = ConvRNNEngine(half_cfg, wt, dev, 2)
+  for lo in (0, 32):
+    sl = slice(lo, lo + 32)
+    fh = dict(scene_feat=f["scene_feat"][sl], obs_scene=f["obs_scene"][sl] - lo,
+              grid_obs_labels=[a[sl] for a in f["grid_obs_labels"]],
+              grid_obs_regress=[a[sl] for a in f["grid_obs_regress"]])
+    part = eng_h.forward(to_dev(fh, dev))
+    for i in range(2):
+      assert torch.equal(part["grid_pred_decoded"][i], full["grid_pred_decoded"][i][sl])
+      assert torch.equal(part["grid_pred_reg_decoded"][i], full["grid_pred_reg_decoded"][i][sl])
+  for i in range(2):
+    assert bool(torch.isfinite(full["grid_pred_decoded"][i]).all())
+    assert bool(torch.isfinite(full["grid_pred_reg_decoded"][i]).all())
