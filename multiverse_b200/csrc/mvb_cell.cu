@@ -110,7 +110,11 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
       const long long m0 = (t / N_TILES) * BLOCK_M;
       const int n0 = (int)(t % N_TILES) * BLOCK_N;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / kc, q = kb - tap * kc;
+        // chunk-major K order: the 9 taps of one 32-channel chunk are consecutive (their A boxes
+        // overlap in L2), and the x block - whose terms can be orders of magnitude larger than the
+        // h terms (raw pixel offsets in the regression encoder) - is accumulated first, so the
+        // small h products are never added onto a large transient partial sum.
+        const int q = kb / 9, tap = kb - q * 9;
         const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
