@@ -1,0 +1,323 @@
+# coding=utf-8
+"""Benchmark of the Multiverse ConvRNN hot path on B200 (contract: see the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3] [--impl reference]
+  (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one pass of the hot path over one batch of synthetic trajectories
+(multiverse_b200/synthetic.py):
+  c4 (default, the configuration BASELINE.json's metric is quoted on): obs8 -> pred12, K=20
+      diverse beam (gamma 0.01, fix_num_timestep 1) on the 36x18 grid + greedy offset decoder,
+      global batch 512, sharded over the ranks (strong scaling, no data-path collective).
+  c3: greedy two-scale 36x18 + 18x9 with graph attention, global batch 256.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "trajectories/sec (obs8->pred12, K=20)"
+WORKLOADS = {
+    "c4": dict(global_batch=512, cfg=dict(use_grids=[True, False], use_beam_search=True, beam_size=20,
+                                         diverse_beam=True, diverse_gamma=0.01, fix_num_timestep=1),
+               desc="multifuture K=20 diverse beam, 36x18 grid, + greedy offset decoder"),
+    "c3": dict(global_batch=256, cfg=dict(use_grids=[True, True]),
+               desc="greedy two-scale 36x18+18x9, graph attention, class+offset heads"),
+}
+
+
+def cell_flops(h, w, cx):
+  """Algorithmic FLOPs of one cell step per sample row: 2*HW*9*(Cx+Ch)*4Ch."""
+  return 2.0 * h * w * 9 * (cx + 256) * 1024
+
+
+def flops_per_trajectory(cfg):
+  tot = 0.0
+  for i, (h, w) in enumerate(cfg.scene_grids):
+    if not cfg.use_grids[i]:
+      continue
+    k = cfg.beam_size if cfg.use_beam_search else 1
+    tot += cfg.obs_len * (cell_flops(h, w, 64) + cell_flops(h, w, 2))
+    tot += cfg.pred_len * (k * cell_flops(h, w, cfg.emb_size) + cell_flops(h, w, cfg.emb_size))
+  return tot
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "200"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+    self.proc.terminate()
+    sm, mx, reasons = [], None, set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx = float(r[2])
+      except Exception:
+        continue
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, samples=len(sm),
+                reasons=sorted(reasons))
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return dict(bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+  return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def cpu_reference_run(cfg_over, n_sample, seed, repeats=1):
+  """The reference algorithm on the host cores: torch-CPU fp32 restatement of
+  code/pred_models.py (oracle/multiverse_ref_torch.py; TF 1.15 is not installable).  Returns
+  (trajectories/sec, seconds, threads)."""
+  from multiverse_b200 import synthetic
+  from oracle import multiverse_ref_torch as RT
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  cfg = synthetic.make_config(batch_size=n_sample, **cfg_over)
+  w = synthetic.make_weights(cfg, seed)
+  f = synthetic.make_feeds(cfg, n_sample, seed)
+  t0 = time.perf_counter()
+  for _ in range(repeats):
+    RT.forward(cfg, w, f)
+  dt = (time.perf_counter() - t0) / repeats
+  return n_sample / dt, dt, threads
+
+
+def run_reference(args, wl):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  n_sample = 2
+  for _ in range(args.warmup):
+    cpu_reference_run(wl["cfg"], n_sample, 1)
+  vals = []
+  for _ in range(args.steps):
+    v, dt, threads = cpu_reference_run(wl["cfg"], n_sample, 1)
+    vals.append((v, dt))
+  tot_t = sum(d for _, d in vals)
+  value = n_sample * len(vals) / tot_t
+  line = dict(impl="reference", metric=METRIC, value=value, unit="trajectories/s", n_gpus=args.gpus,
+              steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * tot_t / len(vals),
+              higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+              config=dict(workload=args.workload + ": " + wl["desc"], global_batch=wl["global_batch"],
+                          sample_per_step=n_sample, obs_len=8, pred_len=12),
+              cpu_baseline=dict(value=value, unit="trajectories/s", cores=threads, kind="port",
+                                sample="%d trajectories per step through the torch-CPU restatement of "
+                                       "code/pred_models.py (TF 1.15 not installable)" % n_sample),
+              e2e=dict(value=value, unit="trajectories/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200")
+  ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+  ap.add_argument("--global-batch", type=int, default=0)
+  ap.add_argument("--planes", type=int, default=2)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  wl = WORKLOADS[args.workload]
+  if args.impl == "reference":
+    return run_reference(args, wl)
+  args.warmup = max(args.warmup, 3)
+
+  from multiverse_b200 import build, ops, synthetic
+  from multiverse_b200.engine import ConvRNNEngine
+  build.build()
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+  gb = args.global_batch or wl["global_batch"]
+  assert gb % world == 0
+  n_local = gb // world
+
+  cfg = synthetic.make_config(batch_size=n_local, **wl["cfg"])
+  weights = synthetic.make_weights(cfg)
+  # the batch shards by trajectory: rank r takes rows [r*n_local, (r+1)*n_local) and the scene
+  # frames they index (re-compacted per shard like code/pred_utils.py:680-704)
+  feeds_all = synthetic.make_feeds(cfg, gb)
+  sl = slice(rank * n_local, (rank + 1) * n_local)
+  host = dict(scene_feat=feeds_all["scene_feat"][sl], obs_scene=feeds_all["obs_scene"][sl] - rank * n_local,
+              grid_obs_labels=[a[sl] for a in feeds_all["grid_obs_labels"]],
+              grid_obs_regress=[a[sl] for a in feeds_all["grid_obs_regress"]])
+  pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+  host_pinned = dict(scene_feat=pin(host["scene_feat"]), obs_scene=pin(host["obs_scene"]),
+                     grid_obs_labels=[pin(a) for a in host["grid_obs_labels"]],
+                     grid_obs_regress=[pin(a) for a in host["grid_obs_regress"]])
+
+  def h2d():
+    g = lambda t: t.to(dev, non_blocking=True)
+    return dict(scene_feat=g(host_pinned["scene_feat"]), obs_scene=g(host_pinned["obs_scene"]),
+                grid_obs_labels=[g(a) for a in host_pinned["grid_obs_labels"]],
+                grid_obs_regress=[g(a) for a in host_pinned["grid_obs_regress"]])
+
+  h2d_bytes = sum(t.numel() * t.element_size() for t in
+                  [host_pinned["scene_feat"], host_pinned["obs_scene"]] + host_pinned["grid_obs_labels"]
+                  + host_pinned["grid_obs_regress"])
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in weights.items()}, dev, args.planes)
+  dev_feeds = h2d()
+  torch.cuda.synchronize()
+
+  def outputs_of(out):
+    ts = [t for t in out["grid_pred_decoded"] + out["grid_pred_reg_decoded"] if torch.is_tensor(t)]
+    if out["beam_outputs"] is not None:
+      ts += list(out["beam_outputs"])
+    return ts
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  # ---- device-resident throughput (`value`) -------------------------------------------------
+  for _ in range(args.warmup):
+    eng.forward(dev_feeds)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  ops.reset_launch_count()
+  eng.cell_events = []
+  ms_total = timed(lambda: eng.forward(dev_feeds), args.steps)
+  launches = ops.launch_count()
+  events = eng.cell_events
+  eng.cell_events = None
+  clocks = sampler.stop() if rank == 0 else None
+  value = gb * args.steps / (ms_total * 1e-3)
+
+  # ---- end to end through host buffers (`e2e`) ----------------------------------------------
+  out0 = eng.forward(dev_feeds)
+  host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outputs_of(out0)]
+  d2h_bytes = sum(t.numel() * t.element_size() for t in host_out)
+
+  def e2e_step():
+    out = eng.forward(h2d())
+    for dst, src in zip(host_out, outputs_of(out)):
+      dst.copy_(src, non_blocking=True)
+
+  for _ in range(2):
+    e2e_step()
+  ms_e2e = timed(e2e_step, args.steps)
+  e2e_value = gb * args.steps / (ms_e2e * 1e-3)
+
+  if rank != 0:
+    if dist is not None:
+      dist.destroy_process_group()
+    return
+
+  # ---- roofline of the dominant kernel (fused ConvLSTM cell), measured live ------------------
+  peaks = load_peaks()
+  dom_tag = "beam" if cfg.use_beam_search else "dec_class"
+  h0, w0 = [g for g, u in zip(cfg.scene_grids, cfg.use_grids) if u][0]
+  rows = n_local * (cfg.beam_size if cfg.use_beam_search else 1)
+  durs = [e0.elapsed_time(e1) for tag, cx, e0, e1 in events if tag == dom_tag]
+  all_cell_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in events)
+  avg_ms = float(np.mean(durs))
+  fl = cell_flops(h0, w0, cfg.emb_size) * rows
+  achieved = fl / (avg_ms * 1e-3) / 1e12
+  traffic = None
+  tp = os.path.join(ROOT, "profiles", "cell_traffic.json")
+  if os.path.exists(tp):
+    try:
+      traffic = json.load(open(tp)).get("%s_rows%d" % (args.workload, rows))
+    except Exception:
+      traffic = None
+  roofline = dict(bound="tensor", kernel="cell_fwd_kernel<P=%d> (%s step, %d sample rows of %dx%d)" % (
+                      args.planes, dom_tag, rows, h0, w0),
+                  achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                  frac=achieved / peaks["bf16_sustained"], traffic=traffic,
+                  peak_source=peaks["source"] + ", bf16 dense sustained (kernel timed inside a long step)",
+                  note="algorithmic FLOPs 2*M*N*K; fp32 parity needs %d bf16 tensor passes per product, so "
+                       "the ceiling of this fraction is %.3f" % (args.planes * (args.planes + 1) // 2,
+                                                                 2.0 / (args.planes * (args.planes + 1))),
+                  launches_timed=len(durs), avg_launch_ms=avg_ms,
+                  cell_share_of_step=all_cell_ms / ms_total)
+
+  # ---- CPU baseline beside it (N=1 only) ------------------------------------------------------
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    n_s = 4 if cfg.use_beam_search else 8
+    v, dt, threads = cpu_reference_run(wl["cfg"], n_s, 1)
+    cpu = dict(value=v, unit="trajectories/s", cores=threads, kind="port",
+               sample="%d trajectories, one pass (%.1f s) of the torch-CPU restatement of "
+                      "code/pred_models.py on all host threads; TF 1.15 is not installable" % (n_s, dt))
+
+  line = dict(metric=METRIC, value=value, unit="trajectories/s", n_gpus=world, steps=args.steps,
+              warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
+              scaling="strong", vs_baseline=None, dtype="bf16x%d planes -> f32 accumulate" % args.planes,
+              data="synthetic",
+              config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
+                          obs_len=cfg.obs_len, pred_len=cfg.pred_len, beam=cfg.beam_size,
+                          parallelism="trajectory-sharded x%d, no collective" % world,
+                          l2="working set per step (%.1f GB of state) >> 126 MB L2, no flush needed"
+                             % (rows * (h0 + 1) * (w0 + 1) * 256 * 4 * 3 / 1e9),
+                          gflop_per_trajectory=flops_per_trajectory(cfg) / 1e9),
+              clocks=clocks, e2e=dict(value=e2e_value, unit="trajectories/s", ms_per_step=ms_e2e / args.steps,
+                                      h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=d2h_bytes * world),
+              gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+  print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -79,6 +79,7 @@ class ConvRNNEngine(object):
         getattr(cfg.activation_func, "__name__", "") == "tanh", "kernels implement tanh"
     self.set_weights(weights)
     self._bufs = {}
+    self.cell_events = None   # set to [] to record (tag, cx, start, end) events per cell launch
 
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
@@ -105,6 +106,17 @@ class ConvRNNEngine(object):
 
   def _state(self, tag, ns, h, w):
     return self._buf((tag, ns, h, w), lambda: ops.alloc_state(ns, h, w, self.device))
+
+  def _cell(self, tag, *args, **kw):
+    """ops.cell_fwd, optionally bracketed by CUDA events on the launching stream (bench.py's
+    live roofline measurement of the dominant kernel)."""
+    if self.cell_events is None:
+      return ops.cell_fwd(*args, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.cell_fwd(*args, **kw)
+    e1.record()
+    self.cell_events.append((tag, args[1].cx, e0, e1))
 
   # ------------------------------------------------------------------ pieces
   def scene_cnn(self, scene_feat, obs_scene):
@@ -137,7 +149,7 @@ class ConvRNNEngine(object):
       ops.enc_class_input(scene_conv, obs_scene_t[t], labels_t[t],
                           labels_t[t - 2] if t >= 2 else None, cur, h, w)
       last = t == t_len - 1
-      ops.cell_fwd(cur, sw.enc_class, None if t == 0 else c[t % 2], c[(t + 1) % 2],
+      self._cell("enc_class", cur, sw.enc_class, None if t == 0 else c[t % 2], c[(t + 1) % 2],
                    h32 if last else None, xh_out if last else nxt, h, w, n)
     return c[t_len % 2], h32
 
@@ -154,7 +166,7 @@ class ConvRNNEngine(object):
       cur, nxt = xh[t % 2], xh[(t + 1) % 2]
       ops.nhwc_to_planes(obs_reg_t[t], cur, 0, h, w, comp=sw.enc_reg.comp)
       last = t == t_len - 1
-      ops.cell_fwd(cur, sw.enc_reg, None if t == 0 else c[t % 2], c[(t + 1) % 2],
+      self._cell("enc_reg", cur, sw.enc_reg, None if t == 0 else c[t % 2], c[(t + 1) % 2],
                    h32 if last else None, xh_out if last else nxt, h, w, n)
     return c[t_len % 2], h32
 
@@ -179,7 +191,7 @@ class ConvRNNEngine(object):
       elif t == 0:
         # no attention: the planes of the encoder state must already sit in cur's h block
         pass
-      ops.cell_fwd(cur, sw.dec_class, c_src, c[(t + 1) % 2], h32,
+      self._cell("dec_class", cur, sw.dec_class, c_src, c[(t + 1) % 2], h32,
                    None if cfg.use_gnn else nxt, h, w, n)
       c_src, h_src = c[(t + 1) % 2], h32
       last = t == pred_len - 1
@@ -202,7 +214,7 @@ class ConvRNNEngine(object):
     c_src = c_enc
     for t in range(pred_len):
       cur, nxt = xh[t % 2], xh[(t + 1) % 2]
-      ops.cell_fwd(cur, sw.dec_reg, c_src, c[(t + 1) % 2], h32, nxt, h, w, n)
+      self._cell("dec_reg", cur, sw.dec_reg, c_src, c[(t + 1) % 2], h32, nxt, h, w, n)
       c_src = c[(t + 1) % 2]
       last = t == pred_len - 1
       ops.head_reg_fwd(h32, sw.head_reg, offs[t], None if last else We, None if last else be,
@@ -234,7 +246,7 @@ class ConvRNNEngine(object):
       ops.gnn_attend_fwd(h32_enc, scene_mean, xh[0], h, w, ns, beam=b, row_map=tile_map)
     else:
       raise NotImplementedError("beam search without use_gnn is not wired (no published config)")
-    ops.cell_fwd(xh[0], sw.dec_class, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
+    self._cell("beam", xh[0], sw.dec_class, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
     cur_c = 1
     for time in range(1, pred_len + 1):
       ops.head_class_fwd(h32, sw.head_class, step_logits[time - 1], None, None, None, None, h, w,
@@ -249,7 +261,7 @@ class ConvRNNEngine(object):
       nxt = xh[time % 2]
       ops.emb_onehot_fwd(step_ids[time - 1].view(-1), We, be, nxt, h, w)
       ops.gnn_attend_fwd(h32, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
-      ops.cell_fwd(nxt, sw.dec_class, c[cur_c], c[1 - cur_c], h32, None, h, w, ns, row_map=row_map)
+      self._cell("beam", nxt, sw.dec_class, c[cur_c], c[1 - cur_c], h32, None, h, w, ns, row_map=row_map)
       cur_c = 1 - cur_c
     out_ids = torch.empty((n, b, pred_len), dtype=torch.int32, device=dev)
     out_logits = torch.empty((n, b, pred_len, v), dtype=torch.float32, device=dev)

@@ -1,0 +1,416 @@
+# coding=utf-8
+"""The reference's `pred_models` call surface on top of the B200 engine.
+
+Mirrors code/pred_models.py of JunweiLiang/Multiverse: `get_model` (:19), `Model` (:32) with the
+same placeholder / fetch attribute names, `get_feed_dict` (:1042-1194), `Trainer` (:1636) and
+`Tester` (:1745) with the same `step` return conventions, so code/train.py, code/test.py,
+code/multifuture_inference.py (which subclasses Model, :301) and code/pred_utils.py run with
+their source unchanged once `multiverse_b200/dropin` is first on sys.path (it provides
+`pred_models` and the `tensorflow`-named shim).  north_star's enc_cell / dec_cell / decode are
+exposed as methods for unit testing.
+
+Host code here only packs numpy feeds and sequences kernel launches (multiverse_b200.engine);
+there is no graph and no CPU compute path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+_DROPIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
+
+
+def _shim():
+  m = sys.modules.get("tensorflow")
+  if m is not None:
+    if not hasattr(m, "_GRAPH"):
+      raise RuntimeError("a real `tensorflow` module is imported; multiverse_b200.pred_models "
+                         "needs its shim (multiverse_b200/dropin) first on sys.path")
+    return m
+  if _DROPIN not in sys.path:
+    sys.path.insert(0, _DROPIN)
+  import tensorflow  # noqa: F401  (the shim)
+  return sys.modules["tensorflow"]
+
+
+tf = _shim()
+
+
+class Handle(object):
+  """Placeholder or fetch handle owned by a Model (what `sess.run` receives)."""
+
+  def __init__(self, owner, kind, name, index=None):
+    self.owner, self.kind, self.name, self.index = owner, kind, name, index
+
+  def __repr__(self):
+    return "<%s %s%s>" % (self.kind, self.name, "" if self.index is None else "[%d]" % self.index)
+
+
+def get_model(config, gpuid):
+  """code/pred_models.py:19-30."""
+  with tf.name_scope(config.modelname), tf.device("/gpu:%d" % gpuid):
+    model = Model(config, "%s" % config.modelname)
+  model.gpuid = gpuid
+  return model
+
+
+def _glorot(shape, rng):
+  fan_in, fan_out = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
+  lim = np.sqrt(6.0 / (fan_in + fan_out))
+  return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def _he(shape, rng):
+  # tf.variance_scaling_initializer(scale=2.0): truncated normal, stddev sqrt(2/fan_in)/.8796
+  fan_in = shape[0] * shape[1] * shape[2]
+  std = np.sqrt(2.0 / fan_in) / 0.87962566103423978
+  return (np.clip(rng.standard_normal(shape), -2, 2) * std).astype(np.float32)
+
+
+class Model(object):
+  """code/pred_models.py:32-121.  Reads the same `config.*` attributes."""
+
+  def __init__(self, config, scope):
+    self.scope = scope
+    self.config = config
+    self.gpuid = 0
+    self._engine = None
+    self._stale = True
+    self._rng = np.random.default_rng(getattr(config, "seed", 0) or 0)
+    self._own_vars = []
+
+    self.global_step = self._var("global_step", (), dtype="int32", trainable=False)
+    N = self.N = config.batch_size
+    self.SH, self.SW, self.SC = config.scene_h, config.scene_w, config.scene_class
+    self.beam_size = config.beam_size
+    ph = lambda name, idx=None: Handle(self, "placeholder", name, idx)
+    self.obs_length = ph("obs_length")
+    self.pred_length = ph("pred_length")
+    self.is_train = ph("is_train")
+    self.obs_scene = ph("obs_scene")
+    self.obs_scene_mask = ph("obs_scene_mask")
+    self.scene_feat = ph("scene_feat")
+    (self.grid_pred_labels, self.grid_pred_targets, self.grid_obs_labels, self.grid_obs_targets,
+     self.grid_obs_regress, self.grid_pred_labels_T, self.grid_pred_regress) = [[] for _ in range(7)]
+    for i, _ in enumerate(config.scene_grids):
+      self.grid_pred_labels.append(ph("grid_pred_labels", i))
+      self.grid_pred_targets.append(ph("grid_pred_targets", i))
+      self.grid_obs_labels.append(ph("grid_obs_labels", i))
+      self.grid_obs_targets.append(ph("grid_obs_targets", i))
+      self.grid_obs_regress.append(ph("grid_obs_regress", i))
+      self.grid_pred_labels_T.append(ph("grid_pred_labels_T", i))
+      self.grid_pred_regress.append(ph("grid_pred_regress", i))
+    self.beam_outputs = None
+    self.loss = None
+    self.build_forward()
+    if config.is_train:
+      self.build_loss()
+
+  # ---------------------------------------------------------------- variables
+  def _var(self, name, shape, dtype="float32", init=None, trainable=True):
+    fn = None
+    if init is not None:
+      fn = lambda shp, init=init: init(tuple(shp), self._rng)
+    v = tf.Variable(name, shape, dtype=dtype, initializer=fn, trainable=trainable, owner=self)
+    tf._GRAPH.add(v)
+    self._own_vars.append(v)
+    return v
+
+  def _variables_changed(self):
+    self._stale = True
+
+  def _sync_to_host(self):
+    pass  # inference never modifies variables on the device
+
+  def weights(self):
+    return {v.name.split(":")[0]: v.value for v in self._own_vars if v.dtype == "float32"}
+
+  # ---------------------------------------------------------------- graph
+  def build_forward(self):
+    """code/pred_models.py:123-308: declares the variables under the reference's names and the
+    fetch handles; the computation itself is ConvRNNEngine.forward."""
+    cfg = self.config
+    assert cfg.use_scene_enc, "only the published --use_scene_enc models are implemented"
+    zeros = lambda shp, rng: np.zeros(shp, dtype=np.float32)
+    cin = cfg.scene_class
+    for i in range(len(cfg.scene_grid_strides)):
+      self._var("person_pred/scene_conv%d/W" % (i + 1), (3, 3, cin, cfg.scene_conv_dim), init=_he)
+      self._var("person_pred/scene_conv%d/b" % (i + 1), (cfg.scene_conv_dim,), init=zeros)
+      cin = cfg.scene_conv_dim
+    ch, e, k = cfg.enc_hidden_size, cfg.emb_size, cfg.convlstm_kernel
+    self.grid_pred_decoded, self.grid_pred_reg_decoded = [], []
+    p = "person_pred/"
+    for i, _ in enumerate(cfg.scene_grids):
+      if not cfg.use_grids[i]:
+        self.grid_pred_decoded.append([])            # :170-171
+        self.grid_pred_reg_decoded.append([])
+        continue
+      cell = lambda name, cx: (self._var(name + "/kernel", (k, k, cx + ch, 4 * ch), init=_glorot),
+                               self._var(name + "/biases", (4 * ch,), init=zeros))
+      cell(p + "encoder_grid_class_%d/enc_grid_%d" % (i, i), cfg.scene_conv_dim)
+      cell(p + "encoder_grid_reg_%d/enc_grid_regress_%d" % (i, i), 2)
+      for kind, cname, pdim in (("class", "dec_grid_%d" % i, 1), ("reg", "dec_grid_reg_%d" % i, 2)):
+        d = p + "decoder_grid_%s_%d/decoder_rnn/" % (kind, i)
+        cell(d + cname, e)
+        self._var(d + "grid_emb/W", (3, 3, pdim, e), init=_he)
+        self._var(d + "grid_emb/b", (e,), init=zeros)
+        self._var(p + "hidden2grid_decoder_grid_%s_%d/out_dec_grid/W" % (kind, i), (3, 3, ch, pdim), init=_he)
+      self.grid_pred_decoded.append(Handle(self, "fetch", "grid_pred_decoded", i))
+      self.grid_pred_reg_decoded.append(Handle(self, "fetch", "grid_pred_reg_decoded", i))
+    if cfg.use_beam_search:
+      assert not cfg.is_train                        # :261-262
+      assert sum(cfg.use_grids) == 1, "only one scale test at a time"
+      self.beam_outputs = [Handle(self, "fetch", "beam_outputs", j) for j in range(3)]   # :276
+
+  def build_loss(self):
+    """code/pred_models.py:961-1040 (handles; evaluated by the training path)."""
+    self.pred_grid_loss = []
+    for i, _ in enumerate(self.config.scene_grids):
+      if self.config.use_grids[i]:
+        self.pred_grid_loss.extend([Handle(self, "fetch", "classification_loss", i),
+                                    Handle(self, "fetch", "regression_loss", i)])
+    self.wd_loss = Handle(self, "fetch", "wd_loss")
+    self.loss = Handle(self, "fetch", "loss")
+
+  # ---------------------------------------------------------------- feeds
+  def get_feed_dict(self, batch, is_train=False):
+    """code/pred_models.py:1042-1194, vectorised.  `batch` is a pred_utils.Dataset whose
+    `.data` holds obs_grid_class / pred_grid_class [num_scale,T], obs/pred_grid_target_all_<j>
+    [T,h,w,2], batch_scene_feat [F,SH,SW,SC] and batch_obs_scene [[idx],...]."""
+    cfg = self.config
+    N, T_in, T_pred = self.N, cfg.obs_len, cfg.pred_len
+    data = batch.data
+    fd = {self.obs_length: np.full((N,), T_in, dtype="int32"),
+          self.pred_length: np.full((N,), T_pred, dtype="int32"),
+          self.is_train: is_train}
+    n_have = len(data["obs_grid_class"])
+    for j, (h, w) in enumerate(cfg.scene_grids):
+      labels = np.zeros((N, T_in), dtype="int32")
+      if n_have:
+        labels[:n_have] = np.stack([np.asarray(a)[j, :] for a in data["obs_grid_class"]])
+      fd[self.grid_obs_labels[j]] = labels           # :1186-1191 (every scale, used or not)
+      if not cfg.use_grids[j]:
+        continue
+      obs_reg = np.zeros((N, T_in, h, w, 2), dtype="float32")
+      obs_reg[:n_have] = np.stack(data["obs_grid_target_all_%d" % j])
+      fd[self.grid_obs_regress[j]] = obs_reg
+      if is_train or cfg.use_gt_grid:
+        pred_reg = np.zeros((N, T_pred, h, w, 2), dtype="float32")
+        pred_reg[:n_have] = np.stack(data["pred_grid_target_all_%d" % j])
+        cls = np.stack([np.asarray(a)[j, :] for a in data["pred_grid_class"]])
+        if cfg.use_soft_grid_class:
+          pred_lab = np.zeros((N, T_pred, h, w, 1), dtype="float32")
+          pred_lab[:n_have] = _soft_labels(cls, h, w, cfg.soft_grid)
+        else:
+          pred_lab = np.zeros((N, T_pred), dtype="float32")
+          pred_lab[:n_have] = cls
+        fd[self.grid_pred_regress[j]] = pred_reg
+        fd[self.grid_pred_labels_T[j]] = pred_lab
+      else:
+        fd[self.grid_pred_regress[j]] = np.zeros((N, T_pred, h, w, 2), dtype="float32")
+        fd[self.grid_pred_labels_T[j]] = (np.zeros((N, T_pred, h, w, 1), dtype="int32")
+                                          if cfg.use_soft_grid_class else
+                                          np.zeros((N, T_pred), dtype="int32"))
+    obs_scene = np.zeros((N, T_in), dtype="int32")
+    mask = np.zeros((N, T_in), dtype="bool")
+    for i, row in enumerate(data["batch_obs_scene"]):
+      idx = np.asarray(row).reshape(len(row), -1)[:, 0]
+      obs_scene[i, :len(idx)] = idx
+      mask[i, :len(idx)] = True
+    fd[self.obs_scene] = obs_scene
+    fd[self.obs_scene_mask] = mask
+    fd[self.scene_feat] = data["batch_scene_feat"]
+    return fd
+
+  # ---------------------------------------------------------------- execution
+  def _ensure_engine(self):
+    import torch
+    from . import build, engine
+    if self._engine is None:
+      build.build()
+      dev = torch.device("cuda", self.gpuid)
+      torch.cuda.set_device(dev)
+      w = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.weights().items()}
+      self._engine = engine.ConvRNNEngine(_engine_config(self.config), w, dev)
+      self._stale = False
+    elif self._stale:
+      import torch as _t
+      self._engine.set_weights({k: _t.from_numpy(np.ascontiguousarray(v))
+                                for k, v in self.weights().items()})
+      self._stale = False
+    return self._engine
+
+  def _device_feeds(self, feed):
+    import torch
+    eng = self._ensure_engine()
+    dev = eng.device
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=True)
+    cfg = self.config
+    out = dict(scene_feat=up(feed[self.scene_feat], np.float32),
+               obs_scene=up(feed[self.obs_scene], np.int32),
+               grid_obs_labels=[None] * len(cfg.scene_grids),
+               grid_obs_regress=[None] * len(cfg.scene_grids))
+    for i in range(len(cfg.scene_grids)):
+      if cfg.use_grids[i]:
+        out["grid_obs_labels"][i] = up(feed[self.grid_obs_labels[i]], np.int32)
+        out["grid_obs_regress"][i] = up(feed[self.grid_obs_regress[i]], np.float32)
+    return out
+
+  def _run(self, handles, feed):
+    """What `sess.run(fetches, feed_dict)` does for this model: one engine forward per call,
+    numpy arrays out in the reference's shapes."""
+    need_fwd = any(isinstance(h, Handle) and h.kind == "fetch" and
+                   h.name in ("grid_pred_decoded", "grid_pred_reg_decoded", "beam_outputs")
+                   for h in handles)
+    if any(isinstance(h, Handle) and h.name in ("loss", "wd_loss", "classification_loss",
+                                                "regression_loss", "train_op") for h in handles):
+      raise NotImplementedError("the training fetches (loss / train_op) are not implemented yet: "
+                                "forward inference only in this round (SURVEY.md §8 rows a12-a13)")
+    res = self._engine_forward(feed) if need_fwd else None
+    out = []
+    for h in handles:
+      if isinstance(h, tf.Variable):
+        out.append(h.eval())
+      elif h.name == "beam_outputs":
+        out.append(res["beam_outputs"][h.index].cpu().numpy())
+      elif h.kind == "fetch":
+        out.append(res[h.name][h.index].cpu().numpy())
+      else:
+        raise ValueError("cannot fetch %r" % (h,))
+    return out
+
+  def _engine_forward(self, feed):
+    eng = self._ensure_engine()
+    return eng.forward(self._device_feeds(feed))
+
+  # ---------------------------------------------------------------- unit-test surface
+  def enc_cell(self, x, state, scale=0, kind="class"):
+    """One encoder ConvLSTM step (enc_cell_obs_grid / enc_cell_obs_grid_reg, :189-202) on NHWC
+    numpy inputs: x [N,h,w,Cx], state=(c,h) [N,h,w,256] -> (c', h')."""
+    return self._cell_step("enc_" + kind, x, state, scale)
+
+  def dec_cell(self, x, state, scale=0, kind="class"):
+    """One decoder ConvLSTM step (dec_cell_grid / dec_cell_grid_reg, :236-249); x is the
+    embedded input [N,h,w,emb_size]."""
+    return self._cell_step("dec_" + kind, x, state, scale)
+
+  def _cell_step(self, which, x, state, scale):
+    import torch
+    from . import ops
+    eng = self._ensure_engine()
+    dev = eng.device
+    pk = getattr(eng.scales[scale], which)
+    n, h, w, _ = x.shape
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    xh = ops.alloc_xh(n, h, w, pk.cpad, pk.planes, dev)
+    ops.nhwc_to_planes(up(x), xh, 0, h, w, comp=pk.comp)
+    ops.nhwc_to_planes(up(state[1]), xh, pk.cxp, h, w)
+    c_in = ops.alloc_state(n, h, w, dev)
+    ops.nhwc_to_halo(up(state[0]), c_in, h, w)
+    c_out, h_out = ops.alloc_state(n, h, w, dev), ops.alloc_state(n, h, w, dev)
+    ops.cell_fwd(xh, pk, c_in, c_out, h_out, None, h, w, n)
+    co = torch.empty((n, h, w, 256), device=dev)
+    ho = torch.empty((n, h, w, 256), device=dev)
+    ops.halo_to_nhwc(c_out, co, h, w)
+    ops.halo_to_nhwc(h_out, ho, h, w)
+    return co.cpu().numpy(), ho.cpu().numpy()
+
+  def decode(self, feed):
+    """Whole rollout for a feed dict (grid_decoder / grid_decoder_beam_search, :311-806):
+    returns (grid_pred_decoded, grid_pred_reg_decoded, beam_outputs) as numpy."""
+    res = self._engine_forward(feed)
+    npy = lambda t: t.cpu().numpy() if hasattr(t, "cpu") else t
+    return ([npy(t) for t in res["grid_pred_decoded"]], [npy(t) for t in res["grid_pred_reg_decoded"]],
+            None if res["beam_outputs"] is None else [npy(t) for t in res["beam_outputs"]])
+
+
+def _engine_config(config):
+  """The subset of `config` the engine reads, with the activation token normalised."""
+  from types import SimpleNamespace
+  act = config.activation_func
+  name = act if isinstance(act, str) else getattr(act, "__name__", "tanh")
+  if name != "tanh":
+    raise NotImplementedError("activation %r: the kernels implement tanh (every published config)" % name)
+  keys = ("batch_size scene_h scene_w scene_class scene_conv_dim scene_conv_kernel scene_grid_strides "
+          "scene_grids use_grids enc_hidden_size dec_hidden_size emb_size convlstm_kernel use_scene_enc "
+          "use_gnn use_beam_search beam_size diverse_beam diverse_gamma fix_num_timestep obs_len "
+          "pred_len").split()
+  d = {k: getattr(config, k) for k in keys}
+  d["activation_func"] = "tanh"
+  for flag in ("use_single_decoder", "use_teacher_forcing"):
+    if getattr(config, flag, False):
+      raise NotImplementedError("--%s is not implemented (no published config uses it)" % flag)
+  if getattr(config, "keep_prob", 1.0) != 1.0 and getattr(config, "is_train", False):
+    raise NotImplementedError("dropout (keep_prob < 1) is not implemented; every published config uses 1.0")
+  return SimpleNamespace(**d)
+
+
+def _soft_labels(cls, h, w, mode):
+  """Soft grid labels of code/pred_models.py:1085-1136 (3x3 / 5x5 neighbourhood smoothing)."""
+  from scipy import ndimage
+  tables = {1: (0.1, 1.0), 2: (0.01, 1.0), 3: (0.05, 1.0), 4: (0.0125, 0.9), 5: (0.05, 0.6), 6: (0.1, 0.2)}
+  if mode == 7:
+    k = np.full((5, 5), 0.0625)
+    k[1:4, 1:4] = 0.0125
+    k[2, 2] = 0.8
+  else:
+    side, centre = tables[mode]
+    k = np.full((3, 3), side)
+    k[1, 1] = centre
+  n, t = cls.shape
+  out = np.zeros((n, t, h, w, 1), dtype="float32")
+  for i in range(n):
+    for s in range(t):
+      m = np.zeros((h * w,), dtype="float")
+      m[cls[i, s]] = 1.0
+      out[i, s, :, :, 0] = ndimage.convolve(m.reshape(h, w), k, mode="constant", cval=0.0)
+  return out
+
+
+class Trainer(object):
+  """code/pred_models.py:1636-1742."""
+
+  def __init__(self, model, config):
+    self.config = config
+    self.model = model
+    self.global_step = model.global_step
+    self.loss = model.loss
+    self.wd_loss = model.wd_loss
+    if config.optimizer not in ("momentum", "adadelta", "adam", "rmsprop"):
+      raise Exception("Optimizer not implemented")
+    self.train_op = Handle(model, "fetch", "train_op")
+
+  def step(self, sess, batch):
+    _, batch_data = batch
+    feed_dict = self.model.get_feed_dict(batch_data, is_train=True)
+    outputs = sess.run([self.loss, self.train_op, self.wd_loss, self.model.pred_grid_loss],
+                       feed_dict=feed_dict)
+    loss, train_op, wd_loss, pred_grid_loss = outputs
+    return loss, train_op, wd_loss, pred_grid_loss
+
+
+class Tester(object):
+  """code/pred_models.py:1745-1790."""
+
+  def __init__(self, model, config, sess=None):
+    self.config = config
+    self.model = model
+    self.sess = sess
+    self.grid_pred_decoded = self.model.grid_pred_decoded
+    self.grid_pred_reg_decoded = self.model.grid_pred_reg_decoded
+    self.beam_outputs = self.model.beam_outputs
+
+  def step(self, sess, batch):
+    config = self.config
+    _, batch_data = batch
+    feed_dict = self.model.get_feed_dict(batch_data, is_train=False)
+    inputs = list(self.grid_pred_decoded) + list(self.grid_pred_reg_decoded)
+    if config.use_beam_search:
+      inputs.append(self.beam_outputs)
+    outputs = sess.run(inputs, feed_dict=feed_dict)
+    ns = len(config.scene_grids)
+    grid_pred_class, grid_pred_reg = outputs[:ns], outputs[ns:2 * ns]
+    beam_outputs = outputs[-1] if config.use_beam_search else None
+    return grid_pred_class, grid_pred_reg, beam_outputs

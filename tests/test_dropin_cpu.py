@@ -1,0 +1,177 @@
+# coding=utf-8
+"""CPU tests of the drop-in boundary (host logic only - no kernel runs here).
+
+With multiverse_b200/dropin first on sys.path the reference's callers import OUR `pred_models`
+and the `tensorflow`-named shim.  When the reference tree is mounted (this container; it does not
+exist on the GPU box) its unchanged code/test.py flow and its own Model.get_feed_dict are run
+against ours."""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "multiverse_b200", "dropin")
+REF = "/root/reference/code"
+have_ref = os.path.exists(os.path.join(REF, "pred_utils.py"))
+
+
+@pytest.fixture()
+def dropin(monkeypatch):
+  monkeypatch.syspath_prepend(DROPIN)
+  for m in ("tensorflow", "tensorflow.compat", "tensorflow.compat.v1", "pred_models", "pred_utils",
+            "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  tf.reset_default_graph()
+  import pred_models
+  yield tf, pred_models
+  tf.reset_default_graph()
+
+
+def make_args(tmp_path, **kw):
+  from multiverse_b200 import synthetic
+  cfg = synthetic.make_config(batch_size=3, **kw)
+  a = dict(vars(cfg))
+  a.update(modelname="m", runId=0, gpuid=0, use_soft_grid_class=False, soft_grid=1, use_gt_grid=False,
+           mask_grid_regression=False, use_single_decoder=False, use_teacher_forcing=False,
+           train_w_onehot=True, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, optimizer="adadelta")
+  return types.SimpleNamespace(**a), cfg
+
+
+def test_model_surface_matches_reference_names(dropin, tmp_path):
+  tf, pm = dropin
+  args, _ = make_args(tmp_path)
+  model = pm.get_model(args, gpuid=0)
+  for attr in ("obs_length", "pred_length", "is_train", "obs_scene", "obs_scene_mask", "scene_feat",
+               "grid_obs_labels", "grid_obs_regress", "grid_pred_labels_T", "grid_pred_regress",
+               "grid_pred_decoded", "grid_pred_reg_decoded", "beam_outputs", "global_step", "N"):
+    assert hasattr(model, attr), attr
+  names = [v.name for v in tf.global_variables()]
+  assert "global_step:0" in names
+  assert "person_pred/encoder_grid_class_0/enc_grid_0/kernel:0" in names
+  assert "person_pred/decoder_grid_reg_1/decoder_rnn/grid_emb/W:0" in names
+  assert "person_pred/hidden2grid_decoder_grid_class_0/out_dec_grid/W:0" in names
+  shapes = {v.name: tuple(v.get_shape()) for v in tf.global_variables()}
+  assert shapes["person_pred/encoder_grid_reg_0/enc_grid_regress_0/kernel:0"] == (3, 3, 258, 1024)
+  assert shapes["person_pred/decoder_grid_class_0/decoder_rnn/dec_grid_0/kernel:0"] == (3, 3, 288, 1024)
+  n_params = sum(int(np.prod(s)) for n, s in shapes.items() if n != "global_step:0")
+  assert n_params == 21337728          # two scales, emb 32
+  # unused scales are fetched as [] (code/pred_models.py:170-171)
+  args2, _ = make_args(tmp_path, use_grids=[True, False])
+  tf.reset_default_graph()
+  m2 = pm.get_model(args2, gpuid=0)
+  assert m2.grid_pred_decoded[1] == [] and m2.grid_pred_reg_decoded[1] == []
+  with pytest.raises(AssertionError):
+    a3, _ = make_args(tmp_path, use_beam_search=True, beam_size=5)     # two scales + beam (:262)
+    pm.get_model(a3, gpuid=0)
+
+
+def test_saver_round_trip_and_initializer(dropin, tmp_path):
+  tf, pm = dropin
+  args, _ = make_args(tmp_path, use_grids=[False, True])
+  model = pm.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  w0 = {k: v.copy() for k, v in model.weights().items()}
+  assert any(np.abs(v).max() > 0 for k, v in w0.items() if k.endswith("kernel"))
+  assert all(np.abs(v).max() == 0 for k, v in w0.items() if k.endswith("biases"))   # TF zeros init
+  saver = tf.train.Saver(max_to_keep=2)
+  sess = tf.Session(config=tf.ConfigProto(allow_soft_placement=True))
+  path = saver.save(sess, str(tmp_path / "save" / "save"), global_step=model.global_step)
+  assert tf.train.get_checkpoint_state(str(tmp_path / "save")).model_checkpoint_path == path
+  for v in tf.global_variables():
+    if v.dtype == "float32":
+      v.assign(np.ones(v.get_shape(), dtype=np.float32))
+  restore_vars = [v for v in tf.global_variables() if "global_step" not in v.name]
+  tf.train.Saver(restore_vars).restore(sess, path)
+  for k, v in model.weights().items():
+    assert np.array_equal(v, w0[k])
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not mounted")
+def test_get_feed_dict_equals_the_references(dropin, tmp_path, monkeypatch):
+  """Our vectorised Model.get_feed_dict against the reference's own method
+  (code/pred_models.py:1042-1194) executed on our Model instance."""
+  tf, pm = dropin
+  from multiverse_b200 import synthetic
+  monkeypatch.syspath_prepend(REF)
+  spec = importlib.util.spec_from_file_location("ref_pred_models", os.path.join(REF, "pred_models.py"))
+  ref = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(ref)
+  import pred_utils
+  for kw in (dict(), dict(use_grids=[True, False])):
+    tf.reset_default_graph()
+    args, cfg = make_args(tmp_path, **kw)
+    args.prepropath = str(tmp_path)
+    synthetic.write_npz(str(tmp_path / "data_test.npz"), cfg, 5, seed=3)
+    data = pred_utils.read_data(args, "test")
+    model = pm.get_model(args, gpuid=0)
+    for is_train in (False, True):
+      for _, batch in data.get_batches(args.batch_size, full=True, shuffle=False):
+        ours = model.get_feed_dict(batch, is_train=is_train)
+        theirs = ref.Model.get_feed_dict(model, batch, is_train=is_train)
+        assert set(ours) == set(theirs)
+        for k in theirs:
+          a, b = np.asarray(ours[k]), np.asarray(theirs[k])
+          assert a.shape == b.shape, k
+          assert np.array_equal(a.astype(np.float64), b.astype(np.float64)), k
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not mounted")
+def test_reference_test_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, capsys):
+  """code/test.py (byte-identical) imported and driven end to end - argparse, process_args,
+  read_data, get_model, initialize(load) through our Saver, Tester, evaluate and the metric
+  print-out - with the device forward stubbed out (there is no GPU in this container)."""
+  tf, pm = dropin
+  from multiverse_b200 import synthetic
+  import multiverse_b200.pred_models as impl
+  monkeypatch.syspath_prepend(REF)
+  cfg = synthetic.make_config(batch_size=4, use_grids=[True, False])
+  prepro = tmp_path / "prepro"; prepro.mkdir()
+  synthetic.write_npz(str(prepro / "data_test.npz"), cfg, 6, seed=4)
+  argv = ["test.py", str(prepro), str(tmp_path / "out"), "modelname", "--runId", "0", "--load_best",
+          "--is_baseline" if False else "--use_scene_enc", "--use_gnn", "--scene_h", "72", "--scene_w", "36",
+          "--scene_grid_strides", "2,4", "--use_grids", "1,0", "--batch_size", "4", "--emb_size", "32",
+          "--scene_conv_dim", "64", "--scene_class", "11", "--activation_func", "tanh", "--obs_len", "8",
+          "--pred_len", "12", "--convlstm_kernel", "3", "--enc_hidden_size", "256", "--dec_hidden_size", "256"]
+  monkeypatch.setattr(sys, "argv", argv)
+  spec = importlib.util.spec_from_file_location("ref_test", os.path.join(REF, "test.py"))
+  ref_test = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(ref_test)
+  import pred_utils
+  args = ref_test.parser.parse_args()
+  args.is_train, args.is_test = False, True
+  args = pred_utils.process_args(args)
+  assert args.scene_grids == [(36, 18), (18, 9)]
+
+  # a "trained" checkpoint in the location test.py --load_best expects
+  model0 = pm.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  tf.train.Saver().save(tf.Session(), args.save_dir_best_model, global_step=model0.global_step)
+  tf.reset_default_graph()
+
+  calls = []
+
+  def fake_forward(self, feed):
+    import torch
+    n, tp = self.N, self.config.pred_len
+    calls.append(feed)
+    out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
+    for i, (h, w) in enumerate(self.config.scene_grids):
+      if not self.config.use_grids[i]:
+        out["grid_pred_decoded"].append([]); out["grid_pred_reg_decoded"].append([])
+      else:
+        out["grid_pred_decoded"].append(torch.zeros(n, tp, h, w, 1))
+        out["grid_pred_reg_decoded"].append(torch.zeros(n, tp, h, w, 2))
+    return out
+
+  monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
+  ref_test.main(args)
+  text = capsys.readouterr().out
+  assert "total test samples:6" in text and "grid0_traj_ade" in text
+  assert len(calls) == 2                                  # ceil(6 / 4) batches
+  assert calls[0][[k for k in calls[0] if getattr(k, "name", "") == "scene_feat"][0]].shape[1:] == (72, 36, 11)

@@ -1,0 +1,82 @@
+# coding=utf-8
+"""GPU test of the reference-facing surface: get_model -> Tester.step(sess, batch) through the
+`tensorflow` shim's Session, i.e. the call code/test.py and code/pred_utils.evaluate make
+(code/pred_models.py:1761-1790, code/pred_utils.py:415), checked against the oracle."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_batch(cfg, feeds, n):
+  ns = len(cfg.scene_grids)
+  data = dict(
+      obs_grid_class=[np.stack([feeds["grid_obs_labels"][j][i] for j in range(ns)]) for i in range(n)],
+      pred_grid_class=[np.stack([feeds["grid_pred_labels"][j][i] for j in range(ns)]) for i in range(n)],
+      batch_scene_feat=feeds["scene_feat"], batch_obs_scene=feeds["obs_scene"][:, :, None],
+      original_batch_size=n)
+  for j in range(ns):
+    data["obs_grid_target_all_%d" % j] = [feeds["grid_obs_regress"][j][i] for i in range(n)]
+  return (tuple(range(n)), types.SimpleNamespace(data=data))
+
+
+@pytest.mark.parametrize("beam", [False, True])
+def test_tester_step_through_session(beam, monkeypatch):
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  import pred_models
+  from multiverse_b200 import synthetic
+  from oracle import multiverse_ref as R
+  tf.reset_default_graph()
+  over = dict(batch_size=2)
+  if beam:
+    over.update(use_grids=[False, True], use_beam_search=True, beam_size=6, diverse_beam=True,
+                diverse_gamma=0.01, fix_num_timestep=1)
+  cfg = synthetic.make_config(**over)
+  args = types.SimpleNamespace(**vars(cfg))
+  args.modelname, args.use_soft_grid_class, args.use_gt_grid = "m", False, False
+  w = synthetic.make_weights(cfg, 77)
+  feeds = synthetic.make_feeds(cfg, 2, 77)
+  model = pred_models.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    key = v.name.split(":")[0]
+    if key in w:
+      v.assign(w[key])
+  with tf.Session(config=tf.ConfigProto(allow_soft_placement=True)) as sess:
+    tester = pred_models.Tester(model, args, sess)
+    cls, reg, beam_out = tester.step(sess, make_batch(cfg, feeds, 2))
+    assert int(sess.run(model.global_step)) == 0
+  ref = R.forward(R.default_config(**over), w, feeds, np.float64)
+  rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+  for i in range(2):
+    if not cfg.use_grids[i]:
+      assert cls[i] == [] and reg[i] == []
+      continue
+    assert isinstance(cls[i], np.ndarray) and cls[i].shape == ref["grid_pred_decoded"][i].shape
+    assert rel(cls[i], ref["grid_pred_decoded"][i]) < 1e-4
+    assert rel(reg[i], ref["grid_pred_reg_decoded"][i]) < 1e-4
+  if beam:
+    lg, ids, lp = beam_out
+    assert ids.dtype == np.int32 and np.array_equal(ids, ref["beam_outputs"][1])
+    assert lg.shape == (2, 6, 12, 18 * 9) and lp.shape == (2, 6)
+  else:
+    assert beam_out is None
+  # north_star's unit surface: Model.enc_cell / dec_cell on NHWC numpy tensors
+  i = 1 if beam else 0
+  h, ww = cfg.scene_grids[i]
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((2, h, ww, 32)).astype(np.float32)
+  c = rng.standard_normal((2, h, ww, 256)).astype(np.float32)
+  hh = np.tanh(rng.standard_normal((2, h, ww, 256))).astype(np.float32)
+  c1, h1 = model.dec_cell(x, (c, hh), scale=i, kind="class")
+  sw = R.scale_weights(R.cast_tree(w, np.float64), i)
+  c_ref, h_ref = R.convlstm_cell(x.astype(np.float64), c.astype(np.float64), hh.astype(np.float64), *sw.dec_class)
+  assert rel(c1, c_ref) < 3e-5 and rel(h1, h_ref) < 3e-5
