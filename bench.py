@@ -108,7 +108,7 @@ def cpu_reference_run(cfg_over, n_sample, seed, repeats=1):
   (trajectories/sec, seconds, threads)."""
   from multiverse_b200 import synthetic
   from oracle import multiverse_ref_torch as RT
-  threads = os.cpu_count() or 1
+  threads = int(os.environ.get("MVB_CPU_THREADS", "0")) or (os.cpu_count() or 1)
   torch.set_num_threads(threads)
   cfg = synthetic.make_config(batch_size=n_sample, **cfg_over)
   w = synthetic.make_weights(cfg, seed)
@@ -269,7 +269,7 @@ def main():
   dom_tag = "beam" if cfg.use_beam_search else "dec_class"
   h0, w0 = [g for g, u in zip(cfg.scene_grids, cfg.use_grids) if u][0]
   rows = n_local * (cfg.beam_size if cfg.use_beam_search else 1)
-  durs = [e0.elapsed_time(e1) for tag, cx, e0, e1 in events if tag == dom_tag]
+  durs = [e0.elapsed_time(e1) for tag, shp, e0, e1 in events if tag == dom_tag and shp[:2] == (h0, w0)]
   all_cell_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in events)
   avg_ms = float(np.mean(durs))
   fl = cell_flops(h0, w0, cfg.emb_size) * rows

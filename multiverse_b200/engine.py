@@ -116,7 +116,7 @@ class ConvRNNEngine(object):
     e0.record()
     ops.cell_fwd(*args, **kw)
     e1.record()
-    self.cell_events.append((tag, args[1].cx, e0, e1))
+    self.cell_events.append((tag, (args[6], args[7], args[8]), e0, e1))   # (h, w, ns)
 
   # ------------------------------------------------------------------ pieces
   def scene_cnn(self, scene_feat, obs_scene):
