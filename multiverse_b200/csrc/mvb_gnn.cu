@@ -7,16 +7,67 @@
 // of each row survive the softmax in fp32 (exp(-1e30) == 0), so this kernel evaluates exactly
 // that 3x3 band:  h'_p = h_p + sum_q softmax_q(F^_p . F^_q) h_q.
 //
-// One warp per cell: the 9 neighbour rows of h (256 fp32) and scene_mean (64 fp32) are held in
-// registers (8 + 2 values per lane each), 9 dot products + 9 squared norms are reduced with warp
-// shuffles, and the result is written straight as the bf16 operand planes of the next cell step.
-// HBM-bound: 4*HW*(256+64) bytes read, 2*P*HW*256 written per sample row.
+// One warp walks one image row of one sample row with a 3x3 register window (8 h + 2 scene values
+// per lane per cell): moving one cell to the right loads only the 3 new cells of the next column,
+// so every h row is fetched 3x (not 9x) through L1/L2, squared norms are computed once per loaded
+// cell, and the centre-left dot product is the previous step's centre-right one.  Per cell: 7 dot
+// products + 3 norms reduced by warp shuffles, a <=9-way softmax, 72 FMAs of weighted sum, and the
+// result is written straight as the bf16 operand planes of the next cell step.
+// HBM-bound by design: 4*HW*(256+64) bytes read, 2*P*HW*256 written per sample row.
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
 
 namespace mvb {
 
-constexpr int GNN_WARPS = 8;
+constexpr int GNN_WARPS = 4;
+
+struct GnnCol {         // one window column: rows y-1, y, y+1
+  float h[3][8];
+  float s[3][2];
+  float n[3];           // squared norm of [h ; s] (warp-reduced)
+};
+
+__device__ __forceinline__ void gnn_load_col(GnnCol& c, const float* __restrict__ h32,
+                                             const float* __restrict__ scene, long long hrow0,
+                                             long long srow0, int x, int W, int Wp, const bool (&rok)[3],
+                                             int lane, int y) {
+  const bool cok = (x >= 0) && (x < W);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float q = 0.f;
+    if (cok && rok[r]) {
+      const float4* p4 = reinterpret_cast<const float4*>(h32 + (hrow0 + (long long)(y + r - 1) * Wp + x) * kHidden + lane * 8);
+      const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+      c.h[r][0] = a.x; c.h[r][1] = a.y; c.h[r][2] = a.z; c.h[r][3] = a.w;
+      c.h[r][4] = b.x; c.h[r][5] = b.y; c.h[r][6] = b.z; c.h[r][7] = b.w;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q = fmaf(c.h[r][k], c.h[r][k], q);
+      if (scene) {
+        const float2 sv = __ldg(reinterpret_cast<const float2*>(scene + (srow0 + (long long)(y + r - 1) * W + x) * 64 + lane * 2));
+        c.s[r][0] = sv.x; c.s[r][1] = sv.y;
+        q = fmaf(sv.x, sv.x, q); q = fmaf(sv.y, sv.y, q);
+      } else {
+        c.s[r][0] = 0.f; c.s[r][1] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c.h[r][k] = 0.f;
+      c.s[r][0] = 0.f; c.s[r][1] = 0.f;
+    }
+    c.n[r] = q;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) c.n[r] = warp_sum(c.n[r]);
+}
+
+__device__ __forceinline__ float gnn_dot(const GnnCol& a, int ra, const GnnCol& b, int rb) {
+  float d = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d = fmaf(a.h[ra][k], b.h[rb][k], d);
+  d = fmaf(a.s[ra][0], b.s[rb][0], d);
+  d = fmaf(a.s[ra][1], b.s[rb][1], d);
+  return d;
+}
 
 template <int P>
 __global__ void __launch_bounds__(GNN_WARPS * 32)
@@ -25,87 +76,76 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
            long long plane_stride, int cpad_out, int ch_off, long long NS, Grid g) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * GNN_WARPS + (threadIdx.x >> 5);
-  const int hw = g.H * g.W;
-  if (wid >= NS * hw) return;
-  const long long s = wid / hw;
-  const int pix = (int)(wid - s * hw);
-  const int y = pix / g.W, x = pix - y * g.W;
+  if (wid >= NS * g.H) return;
+  const long long s = wid / g.H;
+  const int y = (int)(wid - s * g.H);
   const long long ss = row_map ? (long long)row_map[s] : s;
-  const long long n = s / beam;
+  const long long hrow0 = ss * g.S;
+  const long long srow0 = (s / beam) * (long long)g.H * g.W;
+  const bool rok[3] = {y > 0, true, y < g.H - 1};
 
-  float hq[9][8];
-  float dot[9], nrm[9];
-  bool ok[9];
-  float hp[8], sp[2] = {0.f, 0.f};
-  {
-    const float4* p4 = reinterpret_cast<const float4*>(h32 + (ss * g.S + (long long)y * g.Wp + x) * kHidden + lane * 8);
-    const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
-    if (scene_mean) {
-      const float2 c = __ldg(reinterpret_cast<const float2*>(scene_mean + ((n * g.H + y) * g.W + x) * 64 + lane * 2));
-      sp[0] = c.x; sp[1] = c.y;
+  GnnCol L, C, R;
+  gnn_load_col(L, h32, scene_mean, hrow0, srow0, -1, g.W, g.Wp, rok, lane, y);   // zeros
+  gnn_load_col(C, h32, scene_mean, hrow0, srow0, 0, g.W, g.Wp, rok, lane, y);
+  float d_cl = 0.f;   // dot(centre, left-centre), carried from the previous cell
+  for (int x = 0; x < g.W; ++x) {
+    gnn_load_col(R, h32, scene_mean, hrow0, srow0, x + 1, g.W, g.Wp, rok, lane, y);
+    // dots of the centre cell (C,1) with its 8 neighbours; self = squared norm
+    float d[9];
+    d[0] = gnn_dot(C, 1, L, 0); d[1] = gnn_dot(C, 1, C, 0); d[2] = gnn_dot(C, 1, R, 0);
+    d[5] = gnn_dot(C, 1, R, 1);
+    d[6] = gnn_dot(C, 1, L, 2); d[7] = gnn_dot(C, 1, C, 2); d[8] = gnn_dot(C, 1, R, 2);
+    d[0] = warp_sum(d[0]); d[1] = warp_sum(d[1]); d[2] = warp_sum(d[2]); d[5] = warp_sum(d[5]);
+    d[6] = warp_sum(d[6]); d[7] = warp_sum(d[7]); d[8] = warp_sum(d[8]);
+    d[3] = d_cl;
+    d[4] = C.n[1];
+    d_cl = d[5];
+    const bool cokL = x > 0, cokR = x < g.W - 1;
+    const bool ok[9] = {rok[0] && cokL, rok[0], rok[0] && cokR, cokL, true, cokR,
+                        rok[2] && cokL, rok[2], rok[2] && cokR};
+    const float nq[9] = {L.n[0], C.n[0], R.n[0], L.n[1], C.n[1], R.n[1], L.n[2], C.n[2], R.n[2]};
+    // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))
+    const float inv_p = rsqrtf(fmaxf(C.n[1], 1e-12f));
+    float e[9], m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      e[k] = d[k] * inv_p * rsqrtf(fmaxf(nq[k], 1e-12f));
+      if (ok[k]) m = fmaxf(m, e[k]);
     }
-  }
+    float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
-    ok[k] = (yy >= 0) && (yy < g.H) && (xx >= 0) && (xx < g.W);
-    float d = 0.f, q = 0.f;
-    if (ok[k]) {
-      const float4* p4 = reinterpret_cast<const float4*>(h32 + (ss * g.S + (long long)yy * g.Wp + xx) * kHidden + lane * 8);
-      const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-      hq[k][0] = a.x; hq[k][1] = a.y; hq[k][2] = a.z; hq[k][3] = a.w;
-      hq[k][4] = b.x; hq[k][5] = b.y; hq[k][6] = b.z; hq[k][7] = b.w;
+    for (int k = 0; k < 9; ++k) { e[k] = ok[k] ? __expf(e[k] - m) : 0.f; sum += e[k]; }
+    const float inv_sum = 1.0f / sum;
+    float o[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { d = fmaf(hp[c], hq[k][c], d); q = fmaf(hq[k][c], hq[k][c], q); }
-      if (scene_mean) {
-        const float2 sq = __ldg(reinterpret_cast<const float2*>(scene_mean + ((n * g.H + yy) * g.W + xx) * 64 + lane * 2));
-        d = fmaf(sp[0], sq.x, d); d = fmaf(sp[1], sq.y, d);
-        q = fmaf(sq.x, sq.x, q); q = fmaf(sq.y, sq.y, q);
+    for (int c = 0; c < 8; ++c) o[c] = C.h[1][c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float aL = e[r * 3 + 0] * inv_sum, aC = e[r * 3 + 1] * inv_sum, aR = e[r * 3 + 2] * inv_sum;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        o[c] = fmaf(aL, L.h[r][c], o[c]);
+        o[c] = fmaf(aC, C.h[r][c], o[c]);
+        o[c] = fmaf(aR, R.h[r][c], o[c]);
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) hq[k][c] = 0.f;
     }
-    dot[k] = d; nrm[k] = q;
-  }
+    uint32_t pk[P][4];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { dot[k] = warp_sum(dot[k]); nrm[k] = warp_sum(nrm[k]); }
-  // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))
-  const float inv_p = rsqrtf(fmaxf(nrm[4], 1e-12f));
-  float e[9], m = -INFINITY;
+    for (int v = 0; v < 4; ++v) {
+      __nv_bfloat16 a[P], b[P];
+      split_planes<P>(o[2 * v], a);
+      split_planes<P>(o[2 * v + 1], b);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    e[k] = dot[k] * inv_p * rsqrtf(fmaxf(nrm[k], 1e-12f));
-    if (ok[k]) m = fmaxf(m, e[k]);
-  }
-  float sum = 0.f;
+      for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
+    }
+    const long long orow = s * g.S + (long long)y * g.Wp + x;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { e[k] = ok[k] ? __expf(e[k] - m) : 0.f; sum += e[k]; }
-  const float inv_sum = 1.0f / sum;
-  float o[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) o[c] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float a = e[k] * inv_sum;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) o[c] = fmaf(a, hq[k][c], o[c]);
-  }
-  uint32_t pk[P][4];
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    __nv_bfloat16 a[P], b[P];
-    split_planes<P>(hp[2 * v] + o[2 * v], a);
-    split_planes<P>(hp[2 * v + 1] + o[2 * v + 1], b);
-#pragma unroll
-    for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
-  }
-  const long long orow = s * g.S + (long long)y * g.Wp + x;
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
-    *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+    for (int p = 0; p < P; ++p) {
+      uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
+      *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+    }
+    L = C;
+    C = R;
   }
 }
 
@@ -116,7 +156,7 @@ int gnn_attend_fwd(const float* h32, const int* row_map, const float* scene_mean
   MVB_REQUIRE(h32 && hp_out && NS > 0 && beam >= 1, "gnn_attend_fwd: bad args");
   MVB_REQUIRE(cpad_out % 8 == 0 && ch_off_out % 8 == 0, "gnn_attend_fwd: pitch/offset must be multiples of 8");
   const Grid g = make_grid(H, W);
-  const long long warps = NS * H * W;
+  const long long warps = NS * H;
   const unsigned blocks = (unsigned)((warps + GNN_WARPS - 1) / GNN_WARPS);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(hp_out);
   switch (P) {

@@ -88,10 +88,25 @@ head_kernel(const float* __restrict__ h32, const float* __restrict__ Wo, float* 
   const long long s = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < 9 * kHidden * POUT; i += blockDim.x) w_s[i] = Wo[i];
+  // weights transposed to [tap][po][256] so a lane's 8 channels are two 128-bit words
+  for (int i = threadIdx.x; i < 9 * kHidden * POUT; i += blockDim.x) {
+    const int po = i % POUT, ch = (i / POUT) % kHidden, t = i / (POUT * kHidden);
+    w_s[(t * POUT + po) * kHidden + ch] = Wo[i];
+  }
   __syncthreads();
 
-  // phase 1: per-pixel, per-tap partial dot products
+  // phase 1: per-pixel, per-tap partial dot products.  The class head (POUT == 1) keeps its 72
+  // weights in registers; the 2-output head reads them as 128-bit shared-memory words.
+  float wr[POUT == 1 ? 9 : 1][8];
+  if (POUT == 1) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 a = *reinterpret_cast<const float4*>(w_s + t * kHidden + lane * 8);
+      const float4 b = *reinterpret_cast<const float4*>(w_s + t * kHidden + lane * 8 + 4);
+      wr[t][0] = a.x; wr[t][1] = a.y; wr[t][2] = a.z; wr[t][3] = a.w;
+      wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
+    }
+  }
   for (int q = warp; q < hw; q += HEAD_THREADS / 32) {
     const int y = q / g.W, x = q % g.W;
     const float4* p4 = reinterpret_cast<const float4*>(h32 + (s * g.S + (long long)y * g.Wp + x) * kHidden + lane * 8);
@@ -103,8 +118,15 @@ head_kernel(const float* __restrict__ h32, const float* __restrict__ Wo, float* 
 #pragma unroll
       for (int po = 0; po < POUT; ++po) {
         float acc = 0.f;
+        if (POUT == 1) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc = fmaf(hv[c], w_s[(t * kHidden + lane * 8 + c) * POUT + po], acc);
+          for (int c = 0; c < 8; ++c) acc = fmaf(hv[c], wr[t][c], acc);
+        } else {
+          const float4 wa = *reinterpret_cast<const float4*>(w_s + (t * POUT + po) * kHidden + lane * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(w_s + (t * POUT + po) * kHidden + lane * 8 + 4);
+          acc = fmaf(hv[0], wa.x, acc); acc = fmaf(hv[1], wa.y, acc); acc = fmaf(hv[2], wa.z, acc); acc = fmaf(hv[3], wa.w, acc);
+          acc = fmaf(hv[4], wb.x, acc); acc = fmaf(hv[5], wb.y, acc); acc = fmaf(hv[6], wb.z, acc); acc = fmaf(hv[7], wb.w, acc);
+        }
         part[t * POUT + po] = acc;
       }
     }
