@@ -26,7 +26,7 @@ def conv2d_same(x, w, stride=1):
   _, pt, pb = R.same_pad(h, kh, stride)
   _, pl, pr = R.same_pad(wd, kw, stride)
   xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
-  y = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=stride)
+  y = F.conv2d(xn.contiguous(), w.permute(3, 2, 0, 1).contiguous(), stride=stride)
   return y.permute(0, 2, 3, 1)
 
 
@@ -38,9 +38,9 @@ def convlstm_cell(x, c, h, kernel, biases, forget_bias=1.0):
   return new_c, torch.tanh(new_c) * torch.sigmoid(go)
 
 
-def neighbour_mask(h, w):
-  eye = torch.eye(h * w).reshape(h * w, h, w, 1)
-  return conv2d_same(eye, torch.ones(3, 3, 1, 1)).reshape(h * w, h * w)
+def neighbour_mask(h, w, dtype=torch.float32):
+  eye = torch.eye(h * w, dtype=dtype).reshape(h * w, h, w, 1)
+  return conv2d_same(eye, torch.ones(3, 3, 1, 1, dtype=dtype)).reshape(h * w, h * w)
 
 
 def gnn_dense(hs, scene_mean, mask):
@@ -61,15 +61,15 @@ def grid_emb(x, W, b):
 
 def encoder(inputs, kernel, biases, ch):
   n, t, h, w, _ = inputs.shape
-  c = torch.zeros(n, h, w, ch)
-  hs = torch.zeros(n, h, w, ch)
+  c = torch.zeros(n, h, w, ch, dtype=inputs.dtype)
+  hs = torch.zeros(n, h, w, ch, dtype=inputs.dtype)
   for s in range(t):
     c, hs = convlstm_cell(inputs[:, s], c, hs, kernel, biases)
   return c, hs
 
 
-def one_hot_map(ids, h, w):
-  return F.one_hot(ids.long(), h * w).float().reshape(-1, h, w, 1)
+def one_hot_map(ids, h, w, dtype=torch.float32):
+  return F.one_hot(ids.long(), h * w).to(dtype).reshape(-1, h, w, 1)
 
 
 def decoder_greedy(first, state, tp, cell_w, emb_w, head_w, scene_mean, mask, use_gnn, onehot):
@@ -82,7 +82,7 @@ def decoder_greedy(first, state, tp, cell_w, emb_w, head_w, scene_mean, mask, us
     c, h = convlstm_cell(grid_emb(inp, *emb_w), c, h_in, *cell_w)
     o = conv2d_same(h, head_w)
     outs.append(o)
-    inp = one_hot_map(o.reshape(n, -1).argmax(1), hh, ww) if onehot else o
+    inp = one_hot_map(o.reshape(n, -1).argmax(1), hh, ww, o.dtype) if onehot else o
   return torch.stack(outs, 1)
 
 
@@ -95,7 +95,7 @@ def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, d
   v = hh * ww
   rep = lambda t: t.repeat_interleave(b, dim=0)
   c, h, inp, sm = rep(c0), rep(h0), rep(first), rep(scene_mean)
-  score = torch.zeros(n, b)
+  score = torch.zeros(n, b, dtype=h0.dtype)
   ids_l, par_l, log_l = [], [], []
 
   def step(inp, c, h):
@@ -109,7 +109,7 @@ def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, d
       order = torch.argsort(lp, dim=-1, descending=True, stable=True)
       rank = torch.empty_like(order)
       rank.scatter_(-1, order, torch.arange(v).expand_as(order))
-      lp = lp + math.log(gamma) * rank.float()
+      lp = lp + math.log(gamma) * rank.to(lp.dtype)
     cand = lp.reshape(n, b * v) if time > 1 else lp[:, 0]
     sc, idx = torch.topk(cand, b, dim=-1, sorted=True)
     if time <= fix_num_timestep:
@@ -119,14 +119,14 @@ def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, d
     score = sc
     flat = (par + (torch.arange(n) * b)[:, None]).reshape(-1)
     c, h = c[flat], h[flat]
-    inp = one_hot_map(ids.reshape(-1), hh, ww)
+    inp = one_hot_map(ids.reshape(-1), hh, ww, h0.dtype)
     if time == tp:
       break
     c, h = step(inp, c, h)
   parents = torch.arange(b)[None].repeat(n, 1)
   rows = torch.arange(n)[:, None]
   out_ids = torch.zeros(n, b, tp, dtype=torch.long)
-  out_logits = torch.zeros(n, b, tp, v)
+  out_logits = torch.zeros(n, b, tp, v, dtype=h0.dtype)
   for tau in range(tp - 1, -1, -1):
     out_ids[:, :, tau] = ids_l[tau][rows, parents]
     out_logits[:, :, tau] = log_l[tau][rows, parents]
@@ -138,8 +138,41 @@ def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, d
 def forward(cfg, weights, feeds):
   """Model.build_forward at inference (code/pred_models.py:123-308), fp32, torch CPU."""
   w = {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in weights.items()}
+  out = _forward(cfg, w, feeds, torch.float32)
+  return {k: ([t.numpy() if torch.is_tensor(t) else t for t in v] if isinstance(v, list) else v)
+          for k, v in out.items()}
+
+
+def loss_and_grads(cfg, weights, feeds, dtype=torch.float64):
+  """Training objective of Model.build_loss (code/pred_models.py:961-1040) on the greedy
+  train-mode forward (train_w_onehot: the class decoder is fed one_hot(argmax), :285) and its
+  gradients w.r.t. every trainable variable by torch autograd - the truth for the hand-written
+  backward kernels.  Returns (total, [cls_0, reg_0, cls_1, ...], wd_loss, {name: grad})."""
+  w = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype).requires_grad_(True)
+       for k, v in weights.items()}
+  out = _forward(cfg, w, feeds, dtype)
+  losses = []
   n = cfg.batch_size
-  scene_feat = torch.from_numpy(feeds["scene_feat"]).float()
+  for i, (h, ww) in enumerate(cfg.scene_grids):
+    if not cfg.use_grids[i]:
+      continue
+    logits = out["grid_pred_decoded"][i].reshape(-1, h * ww)
+    labels = torch.from_numpy(feeds["grid_pred_labels"][i]).long().reshape(-1)
+    cls = F.cross_entropy(logits, labels) * cfg.grid_loss_weight          # :991-995, :1024
+    tgt = torch.from_numpy(feeds["grid_pred_regress"][i]).to(dtype)
+    reg = F.huber_loss(out["grid_pred_reg_decoded"][i], tgt, delta=1.0) * cfg.grid_reg_loss_weight
+    losses += [cls, reg]
+  # wd_cost(".*/W", wd): wd * l2_loss(p) = wd * sum(p^2)/2 for variables whose name ends in /W
+  wd = sum(cfg.wd * 0.5 * (v * v).sum() for k, v in w.items() if k.endswith("/W"))
+  total = sum(losses) + wd
+  total.backward()
+  grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in w.items()}
+  return float(total), [float(l) for l in losses], float(wd), grads
+
+
+def _forward(cfg, w, feeds, dtype):
+  n = cfg.batch_size
+  scene_feat = torch.from_numpy(feeds["scene_feat"]).to(dtype)
   obs_scene = torch.from_numpy(feeds["obs_scene"]).long()
   x = scene_feat[obs_scene.reshape(-1)]              # embedding_lookup, :148-152
   convs = []
@@ -154,9 +187,9 @@ def forward(cfg, weights, feeds):
       continue
     sw = R.scale_weights(w, i)
     labels = torch.from_numpy(feeds["grid_obs_labels"][i]).long()
-    onehot = F.one_hot(labels, h * ww).float().reshape(n, -1, h, ww, 1)
-    obs_reg = torch.from_numpy(feeds["grid_obs_regress"][i]).float()
-    mask = neighbour_mask(h, ww)
+    onehot = F.one_hot(labels, h * ww).to(dtype).reshape(n, -1, h, ww, 1)
+    obs_reg = torch.from_numpy(feeds["grid_obs_regress"][i]).to(dtype)
+    mask = neighbour_mask(h, ww, dtype)
     enc = encoder(convs[i] * onehot, sw.enc_class[0], sw.enc_class[1], cfg.enc_hidden_size)
     enc_r = encoder(obs_reg, sw.enc_reg[0], sw.enc_reg[1], cfg.enc_hidden_size)
     scene_mean = convs[i].mean(1)
@@ -164,13 +197,13 @@ def forward(cfg, weights, feeds):
       lg, ids, sc = decoder_beam(onehot[:, -1], enc, cfg.pred_len, cfg.beam_size, sw.dec_class,
                                  sw.emb_class, sw.head_class, scene_mean, mask, cfg.diverse_beam,
                                  cfg.diverse_gamma, cfg.fix_num_timestep)
-      out["beam_outputs"] = [lg.numpy(), ids.numpy().astype(np.int32), sc.numpy()]
+      out["beam_outputs"] = [lg.numpy(), ids.numpy().astype(np.int32), sc.numpy()]   # no_grad only
       dec = lg[:, 0].reshape(n, cfg.pred_len, h, ww, 1)
     else:
       dec = decoder_greedy(onehot[:, -1], enc, cfg.pred_len, sw.dec_class, sw.emb_class,
                            sw.head_class, scene_mean, mask, cfg.use_gnn, True)
     reg = decoder_greedy(obs_reg[:, -1], enc_r, cfg.pred_len, sw.dec_reg, sw.emb_reg, sw.head_reg,
                          None, None, False, False)
-    out["grid_pred_decoded"].append(dec.numpy())
-    out["grid_pred_reg_decoded"].append(reg.numpy())
+    out["grid_pred_decoded"].append(dec)
+    out["grid_pred_reg_decoded"].append(reg)
   return out
