@@ -70,6 +70,40 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
                           int64_t NS, int H, int W, int cpad, int planes, float forget_bias,
                           void* stream);
 
+/* ---- a13: BPTT step of the cell (Trainer, pred_models.py:1636-1742; tf.gradients :1698 through
+ *      ConvLSTMCell) ------------------------------------------------------------------------ */
+
+/* Forward step that also stores the activated gates i,j,f,o as fp32 [NS*S,1024] in the packed
+ * column order (tile*256 + gate*64 + ch%64) for the backward pass. */
+int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
+                                const float* bias_packed, const float* c_in, float* c_out,
+                                float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out,
+                                int ch_off_out, float* gates_out, int64_t NS, int H, int W, int cpad,
+                                int planes, float forget_bias, void* stream);
+/* Pointwise LSTM backward: (dh_t, dc_t (or NULL = 0), gates_t, c_{t-1} (or NULL = 0), c_t) ->
+ * dg_planes bf16 [P][NS*S][1024] (pre-activation gate gradients; halo rows are never written and
+ * must be zero), dc_prev fp32, dbias_packed[1024] += column sums. */
+int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
+                       const float* dc_in, void* dg_planes, int64_t plane_stride, float* dc_prev,
+                       float* dbias_packed, int64_t NS, int H, int W, int planes, void* stream);
+/* bf16 planes [P][R][C] -> [P][C][Rp] (Rp >= R, multiple of 8): K-major operands of the wgrad GEMM. */
+int mvb_transpose_planes(const void* src, void* dst, int64_t R, int C, int64_t Rp, int planes,
+                         void* stream);
+/* TF kernel [3,3,cx+256,1024] -> dgrad operand planes bf16 [P][cpad][9*1024]. */
+int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int planes,
+                                void* stream);
+/* dxh fp32 [NS*S, cpad] = conv3x3^T(dG, W): gradient w.r.t. concat([x, h]) of the step. */
+int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int64_t NS, int H,
+                   int W, int cpad, int planes, void* stream);
+/* dw_packed fp32 [1024][9*cpad] += dG^T x im2col(xh): weight gradient of the step (transposed
+ * operands from mvb_transpose_planes, row pitch Rp). */
+int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
+                   int H, int W, int cpad, int64_t Rp, int planes, void* stream);
+/* packed accumulators -> gradients of the TF variables kernel [3,3,cx+256,1024], biases [1024]
+ * (accumulate != 0: +=). */
+int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
+                          float* dbiases, int cx, int comp, int accumulate, void* stream);
+
 /* ---- layout conversion at the API boundary (placeholders are NHWC, pred_models.py:62-115) */
 
 /* fp32 NHWC [NS,H,W,C] -> bf16 planes written at channel offset ch_off of halo rows (pitch cpad);

@@ -74,7 +74,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 2; }
+int mvb_abi_version(void) { return 3; }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 
@@ -92,7 +92,43 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
                           void* stream) {
   return cell_fwd(xh_planes, w_planes, bias_packed, c_in, row_map, c_out, h32_out, hp_out,
                   hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
-                  S(stream));
+                  nullptr, S(stream));
+}
+
+int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
+                                const float* bias_packed, const float* c_in, float* c_out,
+                                float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out,
+                                int ch_off_out, float* gates_out, int64_t NS, int H, int W, int cpad,
+                                int planes, float forget_bias, void* stream) {
+  return cell_fwd(xh_planes, w_planes, bias_packed, c_in, nullptr, c_out, h32_out, hp_out,
+                  hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
+                  gates_out, S(stream));
+}
+int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
+                       const float* dc_in, void* dg_planes, int64_t plane_stride, float* dc_prev,
+                       float* dbias_packed, int64_t NS, int H, int W, int planes, void* stream) {
+  return lstm_gates_bwd(gates, c_prev, c_new, dh, dc_in, dg_planes, plane_stride, dc_prev,
+                        dbias_packed, NS, H, W, planes, S(stream));
+}
+int mvb_transpose_planes(const void* src, void* dst, int64_t R, int C, int64_t Rp, int planes,
+                         void* stream) {
+  return transpose_planes(src, dst, R, C, Rp, planes, S(stream));
+}
+int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int planes,
+                                void* stream) {
+  return pack_cell_weights_dgrad(kernel, wd_planes, cx, planes, S(stream));
+}
+int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int64_t NS, int H,
+                   int W, int cpad, int planes, void* stream) {
+  return cell_dgrad(dg_planes, wd_planes, dxh, NS, H, W, cpad, planes, S(stream));
+}
+int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
+                   int H, int W, int cpad, int64_t Rp, int planes, void* stream) {
+  return cell_wgrad(dgT_planes, xhT_planes, dw_packed, NS, H, W, cpad, Rp, planes, S(stream));
+}
+int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
+                          float* dbiases, int cx, int comp, int accumulate, void* stream) {
+  return unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp, accumulate, S(stream));
 }
 
 int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,

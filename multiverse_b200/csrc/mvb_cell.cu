@@ -52,6 +52,7 @@ struct CellParams {
   const int* row_map;       // [NS] source sample-row of c_in, or nullptr (identity)
   float* c_out;             // [R, 256]
   float* h32_out;           // [R, 256] or nullptr
+  float* gates_out;         // [R, 1024] activated gates (packed column order) for training, or nullptr
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
   long long hp_plane_stride;  // elements between planes of hp_out
   int cpad_out;             // row pitch of hp_out (elements)
@@ -213,9 +214,25 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
             const float xj = __uint_as_float(gj[v]) + __ldg(bptr + 1 * TILE_CH + v);
             const float xf = __uint_as_float(gf[v]) + __ldg(bptr + 2 * TILE_CH + v);
             const float xo = __uint_as_float(go[v]) + __ldg(bptr + 3 * TILE_CH + v);
-            const float c1 = sigmoid_acc(xf + prm.forget_bias) * cprev[v] + sigmoid_acc(xi) * tanh_acc(xj);
+            const float ai = sigmoid_acc(xi), aj = tanh_acc(xj), af = sigmoid_acc(xf + prm.forget_bias),
+                        ao = sigmoid_acc(xo);
+            const float c1 = af * cprev[v] + ai * aj;
             cn[v] = c1;
-            hn[v] = tanh_acc(c1) * sigmoid_acc(xo);
+            hn[v] = tanh_acc(c1) * ao;
+            if (prm.gates_out) {   // reuse the accumulator registers as staging for the stores below
+              gi[v] = __float_as_uint(ai); gj[v] = __float_as_uint(aj);
+              gf[v] = __float_as_uint(af); go[v] = __float_as_uint(ao);
+            }
+          }
+          if (prm.gates_out) {
+            float* gp = prm.gates_out + row * kGates + nt * BLOCK_N + j0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              reinterpret_cast<uint4*>(gp + 0 * TILE_CH)[v] = make_uint4(gi[4 * v], gi[4 * v + 1], gi[4 * v + 2], gi[4 * v + 3]);
+              reinterpret_cast<uint4*>(gp + 1 * TILE_CH)[v] = make_uint4(gj[4 * v], gj[4 * v + 1], gj[4 * v + 2], gj[4 * v + 3]);
+              reinterpret_cast<uint4*>(gp + 2 * TILE_CH)[v] = make_uint4(gf[4 * v], gf[4 * v + 1], gf[4 * v + 2], gf[4 * v + 3]);
+              reinterpret_cast<uint4*>(gp + 3 * TILE_CH)[v] = make_uint4(go[4 * v], go[4 * v + 1], go[4 * v + 2], go[4 * v + 3]);
+            }
           }
           float4* co = reinterpret_cast<float4*>(prm.c_out + row * kHidden + ch0);
 #pragma unroll
@@ -321,7 +338,7 @@ static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const Cel
 int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, const float* c_in,
              const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
-             float forget_bias, cudaStream_t stream) {
+             float forget_bias, float* gates_out, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "cell_fwd: planes P=%d not in {1,2,3}", P);
   MVB_REQUIRE(cpad % BLOCK_K == 0 && cpad >= kHidden + BLOCK_K, "cell_fwd: cpad=%d must be a multiple of 32 and >= 288", cpad);
   MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
@@ -342,6 +359,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
 
   CellParams prm;
   prm.bias = bias; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
+  prm.gates_out = gates_out;
   prm.hp_out = reinterpret_cast<__nv_bfloat16*>(hp_out);
   prm.hp_plane_stride = hp_plane_stride; prm.cpad_out = cpad_out; prm.ch_off_out = ch_off_out;
   prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.forget_bias = forget_bias;

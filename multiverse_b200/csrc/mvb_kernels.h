@@ -11,7 +11,7 @@ void count_launch(int n);
 int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, const float* c_in,
              const int* row_map, float* c_out, float* h32_out, void* hp_out,
              long long hp_plane_stride, int cpad_out, int ch_off_out, long long NS, int H, int W,
-             int cpad, int P, float forget_bias, cudaStream_t stream);
+             int cpad, int P, float forget_bias, float* gates_out, cudaStream_t stream);
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
                       int cx, int P, int comp, cudaStream_t stream);
 
@@ -53,5 +53,19 @@ int beam_step(const float* logits, const float* score_in, float* score_out, int*
 int beam_backtrace(const int* step_ids, const int* step_parents, const float* step_logits,
                    int* out_ids, float* out_logits, long long N, int B, int Tp, int V,
                    cudaStream_t stream);
+
+// mvb_train.cu
+int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long long NS, int H, int W,
+               int cpad, int P, cudaStream_t stream);
+int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long long NS, int H, int W,
+               int cpad, long long Rp, int P, cudaStream_t stream);
+int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
+                   const float* dc_in, void* dg_planes, long long plane_stride, float* dc_prev,
+                   float* dbias_packed, long long NS, int H, int W, int P, cudaStream_t stream);
+int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P,
+                     cudaStream_t stream);
+int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P, cudaStream_t stream);
+int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases,
+                      int cx, int comp, int accumulate, cudaStream_t stream);
 
 }  // namespace mvb

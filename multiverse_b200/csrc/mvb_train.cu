@@ -1,0 +1,495 @@
+// Backward of the ConvLSTM cell (BPTT step), for Trainer (code/pred_models.py:1636-1742; the
+// reference gets these from tf.gradients :1698 through tf.contrib.rnn.ConvLSTMCell).
+//
+//   lstm_gates_bwd   pointwise: (dh_t, dc_t, gates_t, c_{t-1}, c_t) -> dG_t (pre-activation gate
+//                    gradients, bf16 planes, packed column order), dc_{t-1}, dbias
+//   cell dgrad       dxh[r, c]  = sum_tap sum_g dG[r - shift(tap), g] * W[tap, c, g]
+//                    = one tcgen05 implicit GEMM  [R, 9*1024] x [9*1024, cpad]   (same halo trick
+//                    as the forward: a tap is a constant row shift of the dG matrix)
+//   cell wgrad       dW[tap, c, g] = sum_r xh[r + shift(tap), c] * dG[r, g]
+//                    = tcgen05 GEMM  dG^T [1024, R] x xh^T [cpad, R]^T with the tap as a COLUMN
+//                    shift of the transposed activations; 8 x 18 output tiles = one wave of CTAs,
+//                    each looping over all R rows (K) and adding into the fp32 dW accumulator
+// Both GEMMs use the forward kernel's operand-plane scheme (P bf16 planes, products i+j<P) and
+// the same TMA / mbarrier / TMEM pipeline; the tile is 128 x (cpad/2) (144 or 160 columns).
+// Algorithmic FLOPs: dgrad = wgrad = forward (2*R*9*cpad*1024 each).
+#include "mvb_common.cuh"
+#include "mvb_kernels.h"
+
+namespace mvb {
+
+constexpr int G_BLOCK_M = 128;
+constexpr int G_BLOCK_K = 32;
+constexpr int G_UMMA_K = 16;
+constexpr int G_MAX_BN = 160;
+constexpr int G_EPI_WARPS = 4;
+constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;
+constexpr int G_A_PLANE = G_BLOCK_M * G_BLOCK_K * 2;   // 8 KB
+constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 10 KB (BN = 144 uses 9 KB of it)
+constexpr uint32_t G_SW64_LAYOUT = 4;
+constexpr uint32_t G_SW64_SBO = 512;
+
+enum { MODE_DGRAD = 0, MODE_WGRAD = 1 };
+
+template <int P> struct GemmCfg {
+  static constexpr int STAGE_BYTES = P * (G_A_PLANE + G_B_PLANE);
+  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 5 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct GemmParams {
+  float* out;          // dgrad: [R, cpad] fp32;  wgrad: [1024, 9*cpad] fp32 accumulator (+=)
+  long long R;         // halo rows
+  int H, W;
+  int cpad, bn;        // bn = cpad / 2
+  int num_kb;          // k-blocks per tile
+  long long num_m_tiles;
+  int num_n_tiles;
+};
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const GemmParams prm) {
+  using Cfg = GemmCfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Grid g = make_grid(prm.H, prm.W);
+  const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;
+  const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + prm.bn * G_BLOCK_K * 2);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(prm.bn >> 3) << 17) |
+                         ((uint32_t)(G_BLOCK_M >> 4) << 24);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], G_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const long long mt = t / prm.num_n_tiles;
+      const int ntile = (int)(t % prm.num_n_tiles);
+      for (int kb = 0; kb < prm.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + P * G_A_PLANE;
+        mbar_expect_tx(&full_bar[stage], stage_tx);
+        if (MODE == MODE_DGRAD) {
+          // A = dG[rows - shift(tap), 32 gate columns];  B = Wd[bn channels, tap*1024 + 32 gate columns]
+          const int q = kb / 9, tap = kb - q * 9;
+          const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+          tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
+          tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, ntile * prm.bn, 0);
+        } else {
+          // A = dG^T[128 gate rows, 32 halo rows];  B = xh^T[bn channels, 32 halo rows + shift(tap)]
+          const int tap = ntile >> 1, half = ntile & 1;
+          const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kb * G_BLOCK_K, (int)(mt * G_BLOCK_M), 0);
+          tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K + shift, half * prm.bn, 0);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256;
+      for (int kb = 0; kb < prm.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + P * G_A_PLANE;
+        const uint32_t b_plane = (uint32_t)prm.bn * G_BLOCK_K * 2;   // TMA packs planes back to back
+        uint32_t first = (kb == 0) ? 0u : 1u;
+#pragma unroll
+        for (int pa = 0; pa < P; ++pa) {
+#pragma unroll
+          for (int pb = 0; pb < P - pa; ++pb) {
+#pragma unroll
+            for (int k = 0; k < G_BLOCK_K / G_UMMA_K; ++k) {
+              const uint64_t ad = make_smem_desc(sa + pa * G_A_PLANE + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+              const uint64_t bd = make_smem_desc(sb + pb * b_plane + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+              umma_bf16(d_tmem, ad, bd, idesc, first);
+              first = 1u;
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[as]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> fp32 global =====================
+    const int wq = warp & 3;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const long long mt = t / prm.num_n_tiles;
+      const int ntile = (int)(t % prm.num_n_tiles);
+      const long long row = mt * G_BLOCK_M + wq * 32 + lane;
+      bool valid;
+      float* dst;
+      if (MODE == MODE_DGRAD) {
+        valid = row < prm.R;
+        if (valid) {
+          const int rem = (int)(row % g.S);
+          const int y = rem / g.Wp, x = rem - y * g.Wp;
+          valid = (x < g.W) && (y < g.H);
+        }
+        dst = prm.out + row * prm.cpad + ntile * prm.bn;
+      } else {
+        valid = row < kGates;
+        const int tap = ntile >> 1, half = ntile & 1;
+        dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + half * prm.bn;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256;
+      for (int c0 = 0; c0 < prm.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            if (MODE == MODE_WGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            d4[q] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ----------------------------------------------------------------------------------
+// pointwise LSTM backward
+//   gates [R,1024] (activated i,j,f,o; packed column order tile*256 + gate*64 + j), c_prev, c [R,256]
+//   dc_total = dc_in + dh*o*(1-tanh(c)^2);  dG = {di_pre, dj_pre, df_pre, do_pre};  dc_prev = dc_total*f
+// block = 32 channel groups (8 channels each) x 8 rows
+// ----------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256)
+lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                const float* __restrict__ c_new, const float* __restrict__ dh,
+                const float* __restrict__ dc_in, __nv_bfloat16* __restrict__ dg_planes,
+                long long plane_stride, float* __restrict__ dc_prev, float* __restrict__ dbias,
+                long long NS, Grid g) {
+  const int cg = threadIdx.x & 31;     // channel group: channels [8cg, 8cg+8)
+  const int rl = threadIdx.x >> 5;     // row lane 0..7
+  const int ch0 = cg * 8;
+  const int colbase = (ch0 / 64) * 256 + (ch0 % 64);
+  const int hw = g.H * g.W;
+  float bsum[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bsum[a][k] = 0.f;
+  for (long long pix = (long long)blockIdx.x * 8 + rl; pix < NS * hw; pix += (long long)gridDim.x * 8) {
+    const long long s = pix / hw;
+    const int p = (int)(pix - s * hw);
+    const long long row = s * g.S + (long long)(p / g.W) * g.Wp + (p % g.W);
+    float gt[4][8], cp[8], cn[8], dhv[8], dcv[8];
+    auto ld8 = [](const float* ptr, float (&o)[8]) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ptr)), b = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    };
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ld8(gates + row * kGates + colbase + a * 64, gt[a]);
+    if (c_prev) ld8(c_prev + row * kHidden + ch0, cp);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cp[k] = 0.f;
+    }
+    ld8(c_new + row * kHidden + ch0, cn);
+    ld8(dh + row * kHidden + ch0, dhv);
+    if (dc_in) ld8(dc_in + row * kHidden + ch0, dcv);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dcv[k] = 0.f;
+    }
+    float dgv[4][8], dcp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float ai = gt[0][k], aj = gt[1][k], af = gt[2][k], ao = gt[3][k];
+      const float th = tanh_acc(cn[k]);
+      const float dct = dcv[k] + dhv[k] * ao * (1.f - th * th);
+      dgv[0][k] = dct * aj * ai * (1.f - ai);
+      dgv[1][k] = dct * ai * (1.f - aj * aj);
+      dgv[2][k] = dct * cp[k] * af * (1.f - af);
+      dgv[3][k] = dhv[k] * th * ao * (1.f - ao);
+      dcp[k] = dct * af;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) bsum[a][k] += dgv[a][k];
+    }
+    float4* dc4 = reinterpret_cast<float4*>(dc_prev + row * kHidden + ch0);
+    dc4[0] = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    dc4[1] = make_float4(dcp[4], dcp[5], dcp[6], dcp[7]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      uint32_t pk[P][4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        __nv_bfloat16 x0[P], x1[P];
+        split_planes<P>(dgv[a][2 * v], x0);
+        split_planes<P>(dgv[a][2 * v + 1], x1);
+#pragma unroll
+        for (int q = 0; q < P; ++q) pk[q][v] = pack_bf16x2(x0[q], x1[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < P; ++q)
+        *reinterpret_cast<uint4*>(dg_planes + q * plane_stride + row * kGates + colbase + a * 64) =
+            make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+    }
+  }
+  // dbias: reduce the 8 row lanes through shared memory, one atomic per column per block
+  __shared__ float red[8][32][33];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[rl][cg][a * 8 + k] = bsum[a][k];
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sacc += red[r][cg][a * 8 + k];
+        atomicAdd(dbias + colbase + a * 64 + k, sacc);
+      }
+  }
+}
+
+// src [P][R][C] bf16 -> dst [P][C][Rp] bf16 (64x64 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+transpose_planes_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                        long long R, int C, long long Rp) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int p = blockIdx.z;
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const __nv_bfloat16* s = src + (long long)p * R * C;
+  __nv_bfloat16* d = dst + (long long)p * C * Rp;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int rr = i / 64, cc = i % 64;
+    tile[rr][cc] = (r0 + rr < R && c0 + cc < C) ? s[(r0 + rr) * C + c0 + cc] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int cc = i / 64, rr = i % 64;
+    if (c0 + cc < C && r0 + rr < Rp) d[(long long)(c0 + cc) * Rp + r0 + rr] = tile[rr][cc];
+  }
+}
+
+// dgrad weights: Wd planes [P][cpad][9*1024], Wd[kc][tap*1024 + n_packed] = W_tf[tap][cin(kc)][col(n_packed)]
+template <int P>
+__global__ void pack_dgrad_kernel(const float* __restrict__ kernel, __nv_bfloat16* __restrict__ wd,
+                                  int cx, int cxp, int cpad) {
+  const long long ktot = 9LL * kGates;
+  const long long total = (long long)cpad * ktot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i / ktot);
+    const int k = (int)(i - (long long)kc * ktot);
+    const int tap = k / kGates, n = k - tap * kGates;
+    const int tile = n / 256, gate = (n % 256) / 64, j = n % 64;
+    const int col = gate * kHidden + tile * 64 + j;
+    int cin = -1;
+    if (kc < cx) cin = kc;
+    else if (kc >= cxp) cin = cx + (kc - cxp);
+    const float v = (cin >= 0) ? kernel[((long long)tap * (cx + kHidden) + cin) * kGates + col] : 0.f;
+    __nv_bfloat16 pl[P];
+    split_planes<P>(v, pl);
+#pragma unroll
+    for (int p = 0; p < P; ++p) wd[(long long)p * total + i] = pl[p];
+  }
+}
+
+// dWp [1024][9*cpad] fp32 (packed) -> dkernel [3,3,cx+256,1024] (TF layout), dbias packed -> TF order
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const float* __restrict__ dbp,
+                                    float* __restrict__ dkernel, float* __restrict__ dbiases, int cx,
+                                    int cxp, int cpad, int comp, int accumulate) {
+  const int cin_tot = cx + kHidden;
+  const long long total = 9LL * cin_tot * kGates;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % kGates);
+    const int cin = (int)((i / kGates) % cin_tot);
+    const int tap = (int)(i / ((long long)kGates * cin_tot));
+    const int gate = col / kHidden, ch = col % kHidden;
+    const int n = (ch / 64) * 256 + gate * 64 + (ch % 64);
+    const int kc = cin < cx ? cin : cxp + (cin - cx);
+    float v = dwp[(long long)n * (9LL * cpad) + tap * cpad + kc];
+    if (comp && cin < cx) v += dwp[(long long)n * (9LL * cpad) + tap * cpad + cx + cin];   // + residual block
+    dkernel[i] = accumulate ? dkernel[i] + v : v;
+    if (tap == 0 && cin == 0) dbiases[col] = accumulate ? dbiases[col] + dbp[n] : dbp[n];
+  }
+}
+
+template <int P, int MODE>
+static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm,
+                        int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<P>;
+  static bool configured = false;
+  if (!configured) {
+    MVB_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const long long tiles = prm.num_m_tiles * prm.num_n_tiles;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  pgemm_kernel<P, MODE><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+static int num_sms_of_device(int* out) {
+  int dev = 0;
+  MVB_CHECK_CUDA(cudaGetDevice(&dev));
+  MVB_CHECK_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return MVB_OK;
+}
+
+int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long long NS, int H, int W,
+               int cpad, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "cell_dgrad: planes P=%d", P);
+  MVB_REQUIRE(dg_planes && wd_planes && dxh && NS > 0, "cell_dgrad: bad args");
+  MVB_REQUIRE(cpad % 32 == 0 && (cpad / 2) % 16 == 0 && cpad / 2 <= G_MAX_BN, "cell_dgrad: cpad=%d unsupported", cpad);
+  const Grid g = make_grid(H, W);
+  const long long R = NS * g.S;
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_3d_bf16(&tmA, dg_planes, kGates, (uint64_t)R, P, kGates * 2ull, (uint64_t)R * kGates * 2,
+                               G_BLOCK_K, G_BLOCK_M, P, 64);
+  if (rc) return rc;
+  const uint64_t ktot = 9ull * kGates;
+  rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K,
+                           cpad / 2, P, 64);
+  if (rc) return rc;
+  GemmParams prm;
+  prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = cpad / 2;
+  prm.num_kb = 9 * (kGates / G_BLOCK_K); prm.num_m_tiles = (R + G_BLOCK_M - 1) / G_BLOCK_M; prm.num_n_tiles = 2;
+  int sms = 0;
+  if ((rc = num_sms_of_device(&sms))) return rc;
+  switch (P) {
+    case 1: return launch_pgemm<1, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
+  }
+}
+
+int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long long NS, int H, int W,
+               int cpad, long long Rp, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "cell_wgrad: planes P=%d", P);
+  MVB_REQUIRE(dgT_planes && xhT_planes && dwp && NS > 0, "cell_wgrad: bad args");
+  MVB_REQUIRE(cpad % 32 == 0 && (cpad / 2) % 16 == 0 && cpad / 2 <= G_MAX_BN, "cell_wgrad: cpad=%d unsupported", cpad);
+  const Grid g = make_grid(H, W);
+  const long long R = NS * g.S;
+  MVB_REQUIRE(Rp >= R && Rp % 8 == 0, "cell_wgrad: Rp=%lld must be >= R and a multiple of 8", Rp);
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_3d_bf16(&tmA, dgT_planes, (uint64_t)R, kGates, P, (uint64_t)Rp * 2, (uint64_t)Rp * kGates * 2,
+                               G_BLOCK_K, G_BLOCK_M, P, 64);
+  if (rc) return rc;
+  rc = encode_tmap_3d_bf16(&tmB, xhT_planes, (uint64_t)R, (uint64_t)cpad, P, (uint64_t)Rp * 2, (uint64_t)Rp * cpad * 2,
+                           G_BLOCK_K, cpad / 2, P, 64);
+  if (rc) return rc;
+  GemmParams prm;
+  prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = cpad / 2;
+  prm.num_kb = (int)((R + G_BLOCK_K - 1) / G_BLOCK_K); prm.num_m_tiles = kGates / G_BLOCK_M; prm.num_n_tiles = 18;
+  int sms = 0;
+  if ((rc = num_sms_of_device(&sms))) return rc;
+  switch (P) {
+    case 1: return launch_pgemm<1, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
+  }
+}
+
+int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
+                   const float* dc_in, void* dg_planes, long long plane_stride, float* dc_prev,
+                   float* dbias_packed, long long NS, int H, int W, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "lstm_gates_bwd: planes P=%d", P);
+  MVB_REQUIRE(gates && c_new && dh && dg_planes && dc_prev && dbias_packed && NS > 0, "lstm_gates_bwd: bad args");
+  const Grid g = make_grid(H, W);
+  const long long pix = NS * H * W;
+  const int blocks = (int)((pix + 7) / 8 < 148 * 8 ? (pix + 7) / 8 : 148 * 8);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dg_planes);
+  switch (P) {
+    case 1: lstm_bwd_kernel<1><<<blocks, 256, 0, stream>>>(gates, c_prev, c_new, dh, dc_in, d, plane_stride, dc_prev, dbias_packed, NS, g); break;
+    case 2: lstm_bwd_kernel<2><<<blocks, 256, 0, stream>>>(gates, c_prev, c_new, dh, dc_in, d, plane_stride, dc_prev, dbias_packed, NS, g); break;
+    default: lstm_bwd_kernel<3><<<blocks, 256, 0, stream>>>(gates, c_prev, c_new, dh, dc_in, d, plane_stride, dc_prev, dbias_packed, NS, g); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P, cudaStream_t stream) {
+  MVB_REQUIRE(src && dst && R > 0 && C > 0 && Rp >= R && P >= 1, "transpose_planes: bad args");
+  dim3 grid((unsigned)((Rp + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)P);
+  transpose_planes_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                    reinterpret_cast<__nv_bfloat16*>(dst), R, C, Rp);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3 && kernel && wd_planes && cx >= 1, "pack_cell_weights_dgrad: bad args");
+  const int cxp = (cx + 31) / 32 * 32, cpad = cxp + kHidden;
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(wd_planes);
+  switch (P) {
+    case 1: pack_dgrad_kernel<1><<<1184, 256, 0, stream>>>(kernel, d, cx, cxp, cpad); break;
+    case 2: pack_dgrad_kernel<2><<<1184, 256, 0, stream>>>(kernel, d, cx, cxp, cpad); break;
+    default: pack_dgrad_kernel<3><<<1184, 256, 0, stream>>>(kernel, d, cx, cxp, cpad); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases, int cx,
+                      int comp, int accumulate, cudaStream_t stream) {
+  MVB_REQUIRE(dwp && dbias_packed && dkernel && dbiases && cx >= 1, "unpack_cell_wgrad: bad args");
+  const int cxp = (cx + 31) / 32 * 32, cpad = cxp + kHidden;
+  unpack_wgrad_kernel<<<1184, 256, 0, stream>>>(dwp, dbias_packed, dkernel, dbiases, cx, cxp, cpad, comp, accumulate);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+}  // namespace mvb

@@ -176,3 +176,51 @@ def beam_backtrace(step_ids, step_parents, step_logits, out_ids, out_logits):
   v = step_logits.shape[-1]
   _lib.call("mvb_beam_backtrace", _p(step_ids), _p(step_parents), _p(step_logits), _p(out_ids),
             _p(out_logits), n, b, tp, v, _stream())
+
+
+# --------------------------------------------------------------------------- training (BPTT) ops
+def cell_fwd_train(xh, packed, c_in, c_out, h32_out, xh_next, gates_out, h, w, ns, forget_bias=1.0):
+  """cell_fwd that also stores the activated gates [R,1024] for the backward pass."""
+  if xh_next is not None:
+    stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
+  else:
+    stride, cpad_out, off = 0, 0, 0
+  _lib.call("mvb_convlstm_cell_fwd_train", _p(xh), _p(packed.w), _p(packed.bias), _p(c_in),
+            _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, _p(gates_out), ns, h, w,
+            packed.cpad, packed.planes, float(forget_bias), _stream())
+
+
+def pack_dgrad(packed, kernel):
+  """Operand planes of the dgrad GEMM for a PackedCell (cached on it)."""
+  if getattr(packed, "wd", None) is None:
+    packed.wd = torch.empty((packed.planes, packed.cpad, 9 * 4 * HIDDEN), dtype=torch.bfloat16,
+                            device=kernel.device)
+  _lib.call("mvb_pack_cell_weights_dgrad", _p(kernel.detach().float().contiguous()), _p(packed.wd),
+            packed.cx, packed.planes, _stream())
+  return packed.wd
+
+
+def lstm_gates_bwd(gates, c_prev, c_new, dh, dc_in, dg_planes, dc_prev, dbias_packed, h, w, ns):
+  _lib.call("mvb_lstm_gates_bwd", _p(gates), _p(c_prev), _p(c_new), _p(dh), _p(dc_in),
+            _p(dg_planes), dg_planes.stride(0), _p(dc_prev), _p(dbias_packed), ns, h, w,
+            dg_planes.shape[0], _stream())
+
+
+def transpose_planes(src, dst):
+  p, r, c = src.shape
+  _lib.call("mvb_transpose_planes", _p(src), _p(dst), r, c, dst.shape[2], p, _stream())
+
+
+def cell_dgrad(dg_planes, wd, dxh, h, w, ns):
+  _lib.call("mvb_cell_dgrad", _p(dg_planes), _p(wd), _p(dxh), ns, h, w, dxh.shape[1],
+            dg_planes.shape[0], _stream())
+
+
+def cell_wgrad(dgT, xhT, dw_packed, h, w, ns):
+  _lib.call("mvb_cell_wgrad", _p(dgT), _p(xhT), _p(dw_packed), ns, h, w, xhT.shape[1],
+            xhT.shape[2], dgT.shape[0], _stream())
+
+
+def unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp=False, accumulate=False):
+  _lib.call("mvb_unpack_cell_wgrad", _p(dw_packed), _p(dbias_packed), _p(dkernel), _p(dbiases), cx,
+            int(comp), int(accumulate), _stream())
