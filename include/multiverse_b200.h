@@ -86,17 +86,20 @@ int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
 int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
                        const float* dc_in, void* dg_planes, int64_t plane_stride, float* dc_prev,
                        float* dbias_packed, int64_t NS, int H, int W, int planes, void* stream);
-/* bf16 planes [P][R][C] -> [P][C][Rp] (Rp >= R, multiple of 8): K-major operands of the wgrad GEMM. */
+/* bf16 planes [P][R][C] -> [P][taps][C][Rp] (Rp >= R, multiple of 8): K-major operands of the wgrad
+ * GEMM.  taps == 1: plain transpose (dG).  taps == 9: one copy per 3x3 tap with the tap's halo-row
+ * shift (dy-1)*(W+1)+(dx-1) applied (xh) - TMA inner coordinates must be 16-byte aligned, so the
+ * shift cannot be done by the GEMM along its contiguous K axis. */
 int mvb_transpose_planes(const void* src, void* dst, int64_t R, int C, int64_t Rp, int planes,
-                         void* stream);
+                         int taps, int W, void* stream);
 /* TF kernel [3,3,cx+256,1024] -> dgrad operand planes bf16 [P][cpad][9*1024]. */
 int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int planes,
                                 void* stream);
 /* dxh fp32 [NS*S, cpad] = conv3x3^T(dG, W): gradient w.r.t. concat([x, h]) of the step. */
 int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int64_t NS, int H,
                    int W, int cpad, int planes, void* stream);
-/* dw_packed fp32 [1024][9*cpad] += dG^T x im2col(xh): weight gradient of the step (transposed
- * operands from mvb_transpose_planes, row pitch Rp). */
+/* dw_packed fp32 [1024][9*cpad] += dG^T x im2col(xh): weight gradient of the step.  dgT_planes
+ * [P][1024][Rp] and xhT_planes [P][9][cpad][Rp] come from mvb_transpose_planes (taps 1 / 9). */
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
                    int H, int W, int cpad, int64_t Rp, int planes, void* stream);
 /* packed accumulators -> gradients of the TF variables kernel [3,3,cx+256,1024], biases [1024]

@@ -111,8 +111,8 @@ int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_n
                         dbias_packed, NS, H, W, planes, S(stream));
 }
 int mvb_transpose_planes(const void* src, void* dst, int64_t R, int C, int64_t Rp, int planes,
-                         void* stream) {
-  return transpose_planes(src, dst, R, C, Rp, planes, S(stream));
+                         int taps, int W, void* stream) {
+  return transpose_planes(src, dst, R, C, Rp, planes, taps, W + 1, S(stream));
 }
 int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int planes,
                                 void* stream) {

@@ -62,8 +62,8 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
 int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
                    const float* dc_in, void* dg_planes, long long plane_stride, float* dc_prev,
                    float* dbias_packed, long long NS, int H, int W, int P, cudaStream_t stream);
-int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P,
-                     cudaStream_t stream);
+int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P, int taps,
+                     int Wp, cudaStream_t stream);
 int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P, cudaStream_t stream);
 int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases,
                       int cx, int comp, int accumulate, cudaStream_t stream);

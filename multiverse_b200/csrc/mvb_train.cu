@@ -7,8 +7,8 @@
 //                    = one tcgen05 implicit GEMM  [R, 9*1024] x [9*1024, cpad]   (same halo trick
 //                    as the forward: a tap is a constant row shift of the dG matrix)
 //   cell wgrad       dW[tap, c, g] = sum_r xh[r + shift(tap), c] * dG[r, g]
-//                    = tcgen05 GEMM  dG^T [1024, R] x xh^T [cpad, R]^T with the tap as a COLUMN
-//                    shift of the transposed activations; 8 x 18 output tiles = one wave of CTAs,
+//                    = tcgen05 GEMM  dG^T [1024, R] x xh^T_tap [cpad, R]^T over 9 tap-shifted
+//                    transposes of the activations; 8 x 18 output tiles = one wave of CTAs,
 //                    each looping over all R rows (K) and adding into the fp32 dW accumulator
 // Both GEMMs use the forward kernel's operand-plane scheme (P bf16 planes, products i+j<P) and
 // the same TMA / mbarrier / TMEM pipeline; the tile is 128 x (cpad/2) (144 or 160 columns).
@@ -98,11 +98,10 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, ntile * prm.bn, 0);
         } else {
-          // A = dG^T[128 gate rows, 32 halo rows];  B = xh^T[bn channels, 32 halo rows + shift(tap)]
+          // A = dG^T[128 gate rows, 32 halo rows];  B = tap-shifted xh^T[tap][bn channels, 32 halo rows]
           const int tap = ntile >> 1, half = ntile & 1;
-          const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
           tma_load_3d(sa, &tmA, &full_bar[stage], kb * G_BLOCK_K, (int)(mt * G_BLOCK_M), 0);
-          tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K + shift, half * prm.bn, 0);
+          tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K, tap * prm.cpad + half * prm.bn, 0);
         }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
@@ -295,19 +294,24 @@ lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_pre
   }
 }
 
-// src [P][R][C] bf16 -> dst [P][C][Rp] bf16 (64x64 tiles through shared memory)
+// src [P][R][C] bf16 -> dst [P][T][C][Rp] bf16 (64x64 tiles through shared memory).
+// T == 1: plain transpose.  T == 9: one copy per 3x3 tap with the tap's row shift applied,
+// dst[p][tap][c][r] = src[p][r + shift(tap)][c] (zero outside) - TMA needs 16-byte aligned inner
+// coordinates, so the wgrad GEMM cannot shift along its contiguous K (= row) axis itself.
 __global__ void __launch_bounds__(256)
 transpose_planes_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                        long long R, int C, long long Rp) {
+                        long long R, int C, long long Rp, int taps, int Wp) {
   __shared__ __nv_bfloat16 tile[64][66];
-  const int p = blockIdx.z;
+  const int p = blockIdx.z / taps, tap = blockIdx.z % taps;
+  const long long shift = taps == 9 ? (long long)(tap / 3 - 1) * Wp + (tap % 3 - 1) : 0;
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
   const __nv_bfloat16* s = src + (long long)p * R * C;
-  __nv_bfloat16* d = dst + (long long)p * C * Rp;
+  __nv_bfloat16* d = dst + ((long long)p * taps + tap) * C * Rp;
   for (int i = threadIdx.x; i < 64 * 64; i += 256) {
     const int rr = i / 64, cc = i % 64;
-    tile[rr][cc] = (r0 + rr < R && c0 + cc < C) ? s[(r0 + rr) * C + c0 + cc] : __float2bfloat16_rn(0.f);
+    const long long sr = r0 + rr + shift;
+    tile[rr][cc] = (sr >= 0 && sr < R && c0 + cc < C) ? s[sr * C + c0 + cc] : __float2bfloat16_rn(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 64; i += 256) {
@@ -424,7 +428,7 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
   int rc = encode_tmap_3d_bf16(&tmA, dgT_planes, (uint64_t)R, kGates, P, (uint64_t)Rp * 2, (uint64_t)Rp * kGates * 2,
                                G_BLOCK_K, G_BLOCK_M, P, 64);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&tmB, xhT_planes, (uint64_t)R, (uint64_t)cpad, P, (uint64_t)Rp * 2, (uint64_t)Rp * cpad * 2,
+  rc = encode_tmap_3d_bf16(&tmB, xhT_planes, (uint64_t)R, 9ull * cpad, P, (uint64_t)Rp * 2, (uint64_t)Rp * cpad * 18,
                            G_BLOCK_K, cpad / 2, P, 64);
   if (rc) return rc;
   GemmParams prm;
@@ -458,11 +462,12 @@ int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, 
   return MVB_OK;
 }
 
-int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P, cudaStream_t stream) {
-  MVB_REQUIRE(src && dst && R > 0 && C > 0 && Rp >= R && P >= 1, "transpose_planes: bad args");
-  dim3 grid((unsigned)((Rp + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)P);
+int transpose_planes(const void* src, void* dst, long long R, int C, long long Rp, int P, int taps,
+                     int Wp, cudaStream_t stream) {
+  MVB_REQUIRE(src && dst && R > 0 && C > 0 && Rp >= R && P >= 1 && (taps == 1 || taps == 9), "transpose_planes: bad args");
+  dim3 grid((unsigned)((Rp + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)(P * taps));
   transpose_planes_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
-                                                    reinterpret_cast<__nv_bfloat16*>(dst), R, C, Rp);
+                                                    reinterpret_cast<__nv_bfloat16*>(dst), R, C, Rp, taps, Wp);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;

@@ -206,9 +206,10 @@ def lstm_gates_bwd(gates, c_prev, c_new, dh, dc_in, dg_planes, dc_prev, dbias_pa
             dg_planes.shape[0], _stream())
 
 
-def transpose_planes(src, dst):
+def transpose_planes(src, dst, taps=1, w=0):
+  """src [P,R,C] -> dst [P,C,Rp] (taps=1) or [P,9,C,Rp] (taps=9, tap-shifted copies)."""
   p, r, c = src.shape
-  _lib.call("mvb_transpose_planes", _p(src), _p(dst), r, c, dst.shape[2], p, _stream())
+  _lib.call("mvb_transpose_planes", _p(src), _p(dst), r, c, dst.shape[-1], p, taps, w, _stream())
 
 
 def cell_dgrad(dg_planes, wd, dxh, h, w, ns):
@@ -217,8 +218,8 @@ def cell_dgrad(dg_planes, wd, dxh, h, w, ns):
 
 
 def cell_wgrad(dgT, xhT, dw_packed, h, w, ns):
-  _lib.call("mvb_cell_wgrad", _p(dgT), _p(xhT), _p(dw_packed), ns, h, w, xhT.shape[1],
-            xhT.shape[2], dgT.shape[0], _stream())
+  _lib.call("mvb_cell_wgrad", _p(dgT), _p(xhT), _p(dw_packed), ns, h, w, xhT.shape[2],
+            xhT.shape[3], dgT.shape[0], _stream())
 
 
 def unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp=False, accumulate=False):

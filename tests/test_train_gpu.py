@@ -71,8 +71,9 @@ def test_cell_backward_matches_autograd(dev, name):
   # wgrad
   Rp = (R + 7) // 8 * 8
   dgT = torch.zeros((planes, 1024, Rp), dtype=torch.bfloat16, device=dev)
-  xhT = torch.zeros((planes, pk.cpad, Rp), dtype=torch.bfloat16, device=dev)
-  ops.transpose_planes(dg, dgT); ops.transpose_planes(xh, xhT)
+  xhT = torch.zeros((planes, 9, pk.cpad, Rp), dtype=torch.bfloat16, device=dev)
+  ops.transpose_planes(dg, dgT); ops.transpose_planes(xh, xhT, taps=9, w=w)
+  assert torch.equal(xhT[:, 4, :, :R].transpose(1, 2).contiguous(), xh)
   assert torch.equal(dgT[:, :, :R].transpose(1, 2).contiguous(), dg)
   dwp = torch.zeros((1024, 9 * pk.cpad), device=dev)
   ops.cell_wgrad(dgT, xhT, dwp, h, w, ns)
