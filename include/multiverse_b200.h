@@ -107,6 +107,39 @@ int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_pac
 int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
                           float* dbiases, int cx, int comp, int accumulate, void* stream);
 
+/* ---- a12: loss (Model.build_loss, pred_models.py:961-1040) --------------------------------
+ * loss_out[0] += cls_weight * mean_rows CE(logits[rows,V], labels);  dlogits = its gradient.
+ * loss_out[1] += reg_weight * mean Huber_delta1(reg - target) over nreg elements; dreg = gradient.
+ * Either half may be skipped by passing NULL for logits / reg. */
+int mvb_loss_fwd_bwd(const float* logits, const int32_t* labels, float* dlogits, int64_t rows, int V,
+                     float cls_weight, const float* reg, const float* target, float* dreg,
+                     int64_t nreg, float reg_weight, float* loss_out, void* stream);
+/* ---- a13: backward of the heads / embedding / attention / scene CNN (tf.gradients :1698) ----
+ * hidden2grid: dWo[3,3,256,Pout] += ..., dh[NS*S,256] (=|+=) conv3x3^T(dout[NS,HW,Pout], Wo). */
+int mvb_head_bwd(const float* h32, const float* dout, const float* Wo, int Pout, float* dWo,
+                 float* dh, int accumulate_dh, int64_t NS, int H, int W, void* stream);
+/* grid_emb: dxh = gradient w.r.t. concat([x,h]) rows (x block = columns [0,E)); input is
+ * one_hot(ids) (Pout=1) or the dense map in_map[NS,HW,2] (Pout=2, also yields d_in). */
+int mvb_emb_bwd(const float* dxh, int cpad, const int32_t* ids, const float* in_map, const float* We,
+                const float* be, int E, int Pout, float* dWe, float* dbe, float* d_in,
+                int accumulate_din, int64_t NS, int H, int W, void* stream);
+/* graph attention: gout = gradient w.r.t. its output; work = fp32 scratch of 19*NS*H*W floats. */
+int mvb_gnn_attend_bwd(const float* h32, const float* scene_mean, const float* gout, float* work,
+                       float* dh, int accumulate_dh, float* dscene_mean, int64_t NS, int H, int W,
+                       void* stream);
+int mvb_scene_conv_bwd(const float* in, const float* W, const float* out, const float* dout,
+                       float* dW, float* db, float* din, int64_t F, int IH, int IW, int Cin, int Cout,
+                       void* stream);
+int mvb_enc_class_input_bwd(const float* dxh, int cpad, const int32_t* frame_idx,
+                            const int32_t* label, float* dscene, int64_t NS, int H, int W,
+                            void* stream);
+int mvb_scene_time_mean_bwd(const float* dmean, const int32_t* frame_idx, float* dscene, int64_t N,
+                            int T, int64_t HWC, void* stream);
+/* Trainer (:1698-1716): g = clip(grad*grad_scale + wd*w, +-clip) (clip <= 0: off), then
+ * tf.train.AdadeltaOptimizer(lr, rho, eps) on (w, acc, acc_upd), all fp32 [n]. */
+int mvb_clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, int64_t n, float lr,
+                      float rho, float eps, float clip, float wd, float grad_scale, void* stream);
+
 /* ---- layout conversion at the API boundary (placeholders are NHWC, pred_models.py:62-115) */
 
 /* fp32 NHWC [NS,H,W,C] -> bf16 planes written at channel offset ch_off of halo rows (pitch cpad);

@@ -31,6 +31,14 @@ SIGNATURES = {
     "mvb_cell_dgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_cell_wgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i64, _i, _vp],
     "mvb_unpack_cell_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mvb_loss_fwd_bwd": [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _i64, _f, _vp, _vp],
+    "mvb_head_bwd": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "mvb_emb_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "mvb_gnn_attend_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _i, _i, _vp],
+    "mvb_scene_conv_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "mvb_enc_class_input_bwd": [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "mvb_scene_time_mean_bwd": [_vp, _vp, _vp, _i64, _i, _i64, _vp],
+    "mvb_clip_adadelta": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp],
     "mvb_nhwc_to_planes": [_vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _i, _vp],
     "mvb_nhwc_to_halo": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_halo_to_nhwc": [_vp, _vp, _i64, _i, _i, _i, _vp],

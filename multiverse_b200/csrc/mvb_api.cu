@@ -131,6 +131,46 @@ int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, flo
   return unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp, accumulate, S(stream));
 }
 
+int mvb_loss_fwd_bwd(const float* logits, const int32_t* labels, float* dlogits, int64_t rows, int V,
+                     float cls_weight, const float* reg, const float* target, float* dreg,
+                     int64_t nreg, float reg_weight, float* loss_out, void* stream) {
+  return loss_fwd_bwd(logits, labels, dlogits, rows, V, cls_weight, reg, target, dreg, nreg,
+                      reg_weight, loss_out, S(stream));
+}
+int mvb_head_bwd(const float* h32, const float* dout, const float* Wo, int Pout, float* dWo,
+                 float* dh, int accumulate_dh, int64_t NS, int H, int W, void* stream) {
+  return head_bwd(h32, dout, Wo, Pout, dWo, dh, accumulate_dh, NS, H, W, S(stream));
+}
+int mvb_emb_bwd(const float* dxh, int cpad, const int32_t* ids, const float* in_map, const float* We,
+                const float* be, int E, int Pout, float* dWe, float* dbe, float* d_in,
+                int accumulate_din, int64_t NS, int H, int W, void* stream) {
+  return emb_bwd(dxh, cpad, ids, in_map, We, be, E, Pout, dWe, dbe, d_in, accumulate_din, NS, H, W,
+                 S(stream));
+}
+int mvb_gnn_attend_bwd(const float* h32, const float* scene_mean, const float* gout, float* work,
+                       float* dh, int accumulate_dh, float* dscene_mean, int64_t NS, int H, int W,
+                       void* stream) {
+  return gnn_bwd(h32, scene_mean, gout, work, dh, accumulate_dh, dscene_mean, NS, H, W, S(stream));
+}
+int mvb_scene_conv_bwd(const float* in, const float* W, const float* out, const float* dout,
+                       float* dW, float* db, float* din, int64_t F, int IH, int IW, int Cin, int Cout,
+                       void* stream) {
+  return scene_conv_bwd(in, W, out, dout, dW, db, din, F, IH, IW, Cin, Cout, S(stream));
+}
+int mvb_enc_class_input_bwd(const float* dxh, int cpad, const int32_t* frame_idx,
+                            const int32_t* label, float* dscene, int64_t NS, int H, int W,
+                            void* stream) {
+  return enc_class_input_bwd(dxh, cpad, frame_idx, label, dscene, NS, H, W, S(stream));
+}
+int mvb_scene_time_mean_bwd(const float* dmean, const int32_t* frame_idx, float* dscene, int64_t N,
+                            int T, int64_t HWC, void* stream) {
+  return scene_mean_bwd(dmean, frame_idx, dscene, N, T, HWC, S(stream));
+}
+int mvb_clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, int64_t n, float lr,
+                      float rho, float eps, float clip, float wd, float grad_scale, void* stream) {
+  return clip_adadelta(w, grad, acc, acc_upd, n, lr, rho, eps, clip, wd, grad_scale, S(stream));
+}
+
 int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride, int cpad,
                        int ch_off, int64_t NS, int H, int W, int C, int planes, int comp,
                        void* stream) {

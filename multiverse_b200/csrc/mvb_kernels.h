@@ -68,4 +68,25 @@ int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P,
 int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases,
                       int cx, int comp, int accumulate, cudaStream_t stream);
 
+// mvb_train2.cu
+int loss_fwd_bwd(const float* logits, const int* labels, float* dlogits, long long rows, int V,
+                 float cls_scale, const float* reg, const float* target, float* dreg, long long nreg,
+                 float reg_scale, float* loss_out, cudaStream_t stream);
+int head_bwd(const float* h32, const float* dout, const float* Wo, int Pout, float* dWo, float* dh,
+             int accumulate_dh, long long NS, int H, int W, cudaStream_t stream);
+int emb_bwd(const float* dxh, int cpad, const int* ids, const float* in_map, const float* We,
+            const float* be, int E, int Pout, float* dWe, float* dbe, float* d_in, int accumulate_din,
+            long long NS, int H, int W, cudaStream_t stream);
+int gnn_bwd(const float* h32, const float* scene_mean, const float* gout, float* work, float* dh,
+            int accumulate_dh, float* dscene_mean, long long NS, int H, int W, cudaStream_t stream);
+int scene_conv_bwd(const float* in, const float* W, const float* out, const float* dout, float* dW,
+                   float* db, float* din, long long F, int IH, int IW, int Cin, int Cout,
+                   cudaStream_t stream);
+int enc_class_input_bwd(const float* dxh, int cpad, const int* frame_idx, const int* label,
+                        float* dscene, long long NS, int H, int W, cudaStream_t stream);
+int scene_mean_bwd(const float* dmean, const int* frame_idx, float* dscene, long long N, int T,
+                   long long HWC, cudaStream_t stream);
+int clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, long long n, float lr,
+                  float rho, float eps, float clip, float wd, float gscale, cudaStream_t stream);
+
 }  // namespace mvb

@@ -225,3 +225,48 @@ def cell_wgrad(dgT, xhT, dw_packed, h, w, ns):
 def unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp=False, accumulate=False):
   _lib.call("mvb_unpack_cell_wgrad", _p(dw_packed), _p(dbias_packed), _p(dkernel), _p(dbiases), cx,
             int(comp), int(accumulate), _stream())
+
+
+def loss_fwd_bwd(logits, labels, dlogits, cls_weight, reg, target, dreg, reg_weight, loss_out):
+  """loss_out[0] += weighted mean CE, loss_out[1] += weighted mean Huber; gradients written."""
+  rows, v = (logits.numel() // logits.shape[-1], logits.shape[-1]) if logits is not None else (0, 0)
+  nreg = reg.numel() if reg is not None else 0
+  _lib.call("mvb_loss_fwd_bwd", _p(logits), _p(labels), _p(dlogits), rows, v, float(cls_weight),
+            _p(reg), _p(target), _p(dreg), nreg, float(reg_weight), _p(loss_out), _stream())
+
+
+def head_bwd(h32, dout, Wo, dWo, dh, accumulate_dh, h, w, ns):
+  _lib.call("mvb_head_bwd", _p(h32), _p(dout), _p(Wo), Wo.shape[3], _p(dWo), _p(dh),
+            int(accumulate_dh), ns, h, w, _stream())
+
+
+def emb_bwd(dxh, ids, in_map, We, be, dWe, dbe, d_in, accumulate_din, h, w, ns):
+  _lib.call("mvb_emb_bwd", _p(dxh), dxh.shape[1], _p(ids), _p(in_map), _p(We), _p(be), We.shape[3],
+            We.shape[2], _p(dWe), _p(dbe), _p(d_in), int(accumulate_din), ns, h, w, _stream())
+
+
+def gnn_bwd(h32, scene_mean, gout, work, dh, accumulate_dh, dscene_mean, h, w, ns):
+  _lib.call("mvb_gnn_attend_bwd", _p(h32), _p(scene_mean), _p(gout), _p(work), _p(dh),
+            int(accumulate_dh), _p(dscene_mean), ns, h, w, _stream())
+
+
+def scene_conv_bwd(x, W, out, dout, dW, db, din):
+  f, ih, iw, cin = x.shape
+  _lib.call("mvb_scene_conv_bwd", _p(x), _p(W), _p(out), _p(dout), _p(dW), _p(db), _p(din), f, ih, iw,
+            cin, W.shape[3], _stream())
+
+
+def enc_class_input_bwd(dxh, frame_idx, label, dscene, h, w):
+  _lib.call("mvb_enc_class_input_bwd", _p(dxh), dxh.shape[1], _p(frame_idx), _p(label), _p(dscene),
+            label.shape[0], h, w, _stream())
+
+
+def scene_time_mean_bwd(dmean, frame_idx, dscene):
+  n, t = frame_idx.shape
+  _lib.call("mvb_scene_time_mean_bwd", _p(dmean), _p(frame_idx), _p(dscene), n, t, dmean[0].numel(),
+            _stream())
+
+
+def clip_adadelta(w, grad, acc, acc_upd, lr, clip, wd, grad_scale=1.0, rho=0.95, eps=1e-8):
+  _lib.call("mvb_clip_adadelta", _p(w), _p(grad), _p(acc), _p(acc_upd), w.numel(), float(lr),
+            float(rho), float(eps), float(clip or 0.0), float(wd), float(grad_scale), _stream())

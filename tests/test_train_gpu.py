@@ -82,3 +82,171 @@ def test_cell_backward_matches_autograd(dev, name):
   ops.unpack_cell_wgrad(dwp, dbp, dk, db, cx, comp=pk.comp)
   assert rel(0.5 * dk.cpu().numpy(), t["kernel"].grad.numpy()) < GTOL
   assert rel(db.cpu().numpy(), t["biases"].grad.numpy()) < GTOL
+
+
+def test_loss_kernel(dev):
+  from multiverse_b200 import ops
+  import torch.nn.functional as F
+  rng = np.random.default_rng(1)
+  lg = (rng.standard_normal((7, 3, 50)) * 3).astype(np.float32)
+  lab = rng.integers(0, 50, size=(7, 3)).astype(np.int32)
+  pr = (rng.standard_normal((7, 3, 50, 2)) * 2).astype(np.float32)
+  tg = (rng.standard_normal((7, 3, 50, 2)) * 2).astype(np.float32)
+  tl = torch.from_numpy(lg).double().requires_grad_(True); tp = torch.from_numpy(pr).double().requires_grad_(True)
+  l1 = F.cross_entropy(tl.reshape(-1, 50), torch.from_numpy(lab).long().reshape(-1)) * 1.5
+  l2 = F.huber_loss(tp, torch.from_numpy(tg).double(), delta=1.0) * 0.2
+  (l1 + l2).backward()
+  dl = torch.empty(7, 3, 50, device=dev); dp = torch.empty(7, 3, 50, 2, device=dev)
+  out = torch.zeros(2, device=dev)
+  ops.loss_fwd_bwd(T(lg, dev), T(lab, dev), dl, 1.5, T(pr, dev), T(tg, dev), dp, 0.2, out)
+  assert abs(out[0].item() - l1.item()) < 1e-5 * abs(l1.item()) and abs(out[1].item() - l2.item()) < 1e-5 * abs(l2.item())
+  assert rel(dl.cpu().numpy(), tl.grad.numpy()) < 1e-5 and rel(dp.cpu().numpy(), tp.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("pout", [1, 2])
+def test_head_and_emb_backward(dev, pout):
+  from multiverse_b200 import ops
+  d = cases.head_case()
+  ns, h, w, _ = d["h"].shape
+  rng = np.random.default_rng(2)
+  Wo = d["Wo1"] if pout == 1 else d["Wo2"]
+  dout = rng.standard_normal((ns, h * w, pout)).astype(np.float32)
+  th = torch.from_numpy(d["h"]).double().requires_grad_(True); tW = torch.from_numpy(Wo).double().requires_grad_(True)
+  o = RT.conv2d_same(th, tW)
+  (o.reshape(ns, h * w, pout) * torch.from_numpy(dout).double()).sum().backward()
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(d["h"], dev), h32, h, w)
+  dWo = torch.zeros(3, 3, 256, pout, device=dev); dh = ops.alloc_state(ns, h, w, dev)
+  ops.head_bwd(h32, T(dout, dev), T(Wo, dev), dWo, dh, False, h, w, ns)
+  ops.head_bwd(h32, T(dout, dev), T(Wo, dev), dWo, dh, True, h, w, ns)      # accumulate: 2x
+  dhn = torch.empty(ns, h, w, 256, device=dev); ops.halo_to_nhwc(dh, dhn, h, w)
+  assert rel(0.5 * dhn.cpu().numpy(), th.grad.numpy()) < 1e-5
+  assert rel(0.5 * dWo.cpu().numpy(), tW.grad.numpy()) < 1e-5
+  # embedding backward
+  e = 32
+  We = d["We1"] if pout == 1 else d["We2"]
+  dx = rng.standard_normal((ns, h, w, e)).astype(np.float32)
+  tWe = torch.from_numpy(We).double().requires_grad_(True); tbe = torch.from_numpy(d["be"]).double().requires_grad_(True)
+  if pout == 1:
+    ids = rng.integers(0, h * w, size=ns).astype(np.int32); ids[0] = 0
+    tin = RT.one_hot_map(torch.from_numpy(ids), h, w, torch.float64)
+  else:
+    inm = rng.standard_normal((ns, h, w, 2)).astype(np.float32)
+    tin = torch.from_numpy(inm).double().requires_grad_(True)
+  (RT.grid_emb(tin, tWe, tbe) * torch.from_numpy(dx).double()).sum().backward()
+  dxh = torch.zeros(ops.halo_rows(ns, h, w), 288, device=dev)
+  dxh.view(ns, h + 1, w + 1, 288)[:, :h, :w, :e] = T(dx, dev)
+  dWe = torch.zeros_like(T(We, dev)); dbe = torch.zeros(e, device=dev)
+  if pout == 1:
+    ops.emb_bwd(dxh, T(ids, dev), None, T(We, dev), T(d["be"], dev), dWe, dbe, None, False, h, w, ns)
+  else:
+    din = torch.ones(ns, h * w, 2, device=dev)
+    ops.emb_bwd(dxh, None, T(inm.reshape(ns, h * w, 2), dev), T(We, dev), T(d["be"], dev), dWe, dbe, din, True, h, w, ns)
+    assert rel(din.cpu().numpy() - 1.0, tin.grad.numpy().reshape(ns, h * w, 2)) < 1e-5
+  assert rel(dWe.cpu().numpy(), tWe.grad.numpy()) < 1e-5 and rel(dbe.cpu().numpy(), tbe.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("with_scene", [True, False])
+def test_gnn_backward(dev, with_scene):
+  from multiverse_b200 import ops
+  d = cases.gnn_case()
+  ns, h, w, _ = d["h"].shape
+  rng = np.random.default_rng(3)
+  g = rng.standard_normal((ns, h, w, 256)).astype(np.float32)
+  hh = d["h"].copy(); hh[0, 0, 0] = 0.0                                  # a zero-norm cell (eps clamp)
+  th = torch.from_numpy(hh).double().requires_grad_(True)
+  ts = torch.from_numpy(d["scene"] * (0.0 if not with_scene else 1.0)).double().requires_grad_(True)
+  out = RT.gnn_dense(th, ts if with_scene else None, RT.neighbour_mask(h, w, torch.float64))
+  (out * torch.from_numpy(g).double()).sum().backward()
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(hh, dev), h32, h, w)
+  gh = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(g, dev), gh, h, w)
+  work = torch.empty(19 * ns * h * w, device=dev)
+  dh = ops.alloc_state(ns, h, w, dev); ds = torch.zeros(ns, h, w, 64, device=dev)
+  ops.gnn_bwd(h32, T(d["scene"], dev) if with_scene else None, gh, work, dh, False, ds if with_scene else None, h, w, ns)
+  dhn = torch.empty(ns, h, w, 256, device=dev); ops.halo_to_nhwc(dh, dhn, h, w)
+  if with_scene:
+    assert rel(dhn.cpu().numpy(), th.grad.numpy()) < 2e-5
+    assert rel(ds.cpu().numpy(), ts.grad.numpy()) < 2e-5
+  else:
+    ref = th.grad.numpy().copy()
+    # the zero-norm cell: autograd of rsqrt(clamp(...)) passes the gradient straight through
+    assert rel(dhn.cpu().numpy(), ref) < 2e-5
+
+
+def test_scene_backward(dev):
+  from multiverse_b200 import ops
+  d = cases.scene_case()
+  rng = np.random.default_rng(4)
+  x = torch.from_numpy(d["scene_feat"]).double()
+  W1 = torch.from_numpy(d["W1"]).double().requires_grad_(True); b1 = torch.from_numpy(d["b1"]).double().requires_grad_(True)
+  W2 = torch.from_numpy(d["W2"]).double().requires_grad_(True); b2 = torch.from_numpy(d["b2"]).double().requires_grad_(True)
+  c1 = torch.tanh(RT.conv2d_same(x, W1, 2) + b1); c2 = torch.tanh(RT.conv2d_same(c1, W2, 2) + b2)
+  g1 = rng.standard_normal(tuple(c1.shape)).astype(np.float32); g2 = rng.standard_normal(tuple(c2.shape)).astype(np.float32)
+  ((c1 * torch.from_numpy(g1).double()).sum() + (c2 * torch.from_numpy(g2).double()).sum()).backward()
+  xd = T(d["scene_feat"], dev)
+  o1 = ops.scene_conv_fwd(xd, T(d["W1"], dev), T(d["b1"], dev)); o2 = ops.scene_conv_fwd(o1, T(d["W2"], dev), T(d["b2"], dev))
+  d1 = T(g1, dev).clone(); d2 = T(g2, dev)
+  dW1 = torch.zeros(3, 3, 11, 64, device=dev); db1 = torch.zeros(64, device=dev)
+  dW2 = torch.zeros(3, 3, 64, 64, device=dev); db2 = torch.zeros(64, device=dev)
+  ops.scene_conv_bwd(o1, T(d["W2"], dev), o2, d2, dW2, db2, d1)
+  ops.scene_conv_bwd(xd, T(d["W1"], dev), o1, d1, dW1, db1, None)
+  for a, b in ((dW2, W2), (db2, b2), (dW1, W1), (db1, b1)):
+    assert rel(a.cpu().numpy(), b.grad.numpy()) < 2e-5
+  # time-mean and one-hot-mask backward are scatters
+  idx = T(d["obs_scene"], dev)
+  dmean = torch.randn(4, 6, 5, 64, device=dev); ds = torch.zeros_like(o1)
+  ops.scene_time_mean_bwd(dmean, idx, ds)
+  ref = torch.zeros_like(o1)
+  for n in range(4):
+    for t in range(8):
+      ref[int(idx[n, t])] += dmean[n] / 8
+  assert float((ds - ref).abs().max()) < 1e-5
+
+
+def test_clip_adadelta_matches_tf_formula(dev):
+  from multiverse_b200 import ops
+  rng = np.random.default_rng(6)
+  w = rng.standard_normal(1000); g = rng.standard_normal(1000) * 8
+  acc = np.abs(rng.standard_normal(1000)); au = np.abs(rng.standard_normal(1000)) * 1e-3
+  lr, rho, eps, clip, wd = 0.3, 0.95, 1e-8, 10.0, 0.001
+  gg = np.clip(g * 0.5 + wd * w, -clip, clip)
+  a2 = rho * acc + (1 - rho) * gg * gg
+  u = np.sqrt(au + eps) / np.sqrt(a2 + eps) * gg
+  au2 = rho * au + (1 - rho) * u * u
+  w2 = w - lr * u
+  tw, tg, ta, tu = [T(v.astype(np.float32), dev) for v in (w, g, acc, au)]
+  ops.clip_adadelta(tw, tg, ta, tu, lr, clip, wd, grad_scale=0.5)
+  assert rel(tw.cpu().numpy(), w2) < 1e-5 and rel(ta.cpu().numpy(), a2) < 1e-5 and rel(tu.cpu().numpy(), au2) < 1e-4
+
+
+@pytest.mark.parametrize("use_grids", [[False, True], [True, True]])
+def test_whole_model_loss_and_gradients(dev, use_grids):
+  """TrainEngine.loss_and_grads (train-mode forward + loss + hand-written BPTT) against torch
+  autograd through the oracle's torch restatement, every trainable variable."""
+  from multiverse_b200 import synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  from oracle import multiverse_ref as R
+  over = dict(batch_size=2, use_grids=use_grids)
+  cfg = synthetic.make_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+                              clip_gradient_norm=10.0, **over)
+  w = synthetic.make_weights(cfg, 31)
+  f = synthetic.make_feeds(cfg, 2, 31, with_pred=True)
+  rcfg = R.default_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, **over)
+  tot, losses, wd, grads = RT.loss_and_grads(rcfg, w, f)
+  eng = TrainEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  feeds = dict(scene_feat=T(f["scene_feat"], dev), obs_scene=T(f["obs_scene"], dev),
+               grid_obs_labels=[T(a, dev) for a in f["grid_obs_labels"]],
+               grid_obs_regress=[T(a, dev) for a in f["grid_obs_regress"]],
+               grid_pred_labels=[T(a, dev) for a in f["grid_pred_labels"]],
+               grid_pred_regress=[T(a, dev) for a in f["grid_pred_regress"]])
+  got_losses, got_wd = eng.loss_and_grads(feeds)
+  got_losses = got_losses.cpu().numpy()
+  assert np.abs(got_losses - np.array(losses)).max() < 1e-4 * max(np.abs(losses))
+  assert abs(float(got_wd) - wd) < 1e-5 * wd
+  worst = {}
+  for k in sorted(grads):
+    ref = grads[k] - (cfg.wd * w[k] if k.endswith("/W") else 0.0)     # engine grads exclude the wd term
+    e = rel(eng.grads[k].cpu().numpy(), ref)
+    worst[k] = e
+  bad = {k: v for k, v in worst.items() if v > 1e-3}
+  print("worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+  assert not bad, bad
