@@ -35,6 +35,11 @@ WORKLOADS = {
                desc="multifuture K=20 diverse beam, 36x18 grid, + greedy offset decoder"),
     "c3": dict(global_batch=256, cfg=dict(use_grids=[True, True]),
                desc="greedy two-scale 36x18+18x9, graph attention, class+offset heads"),
+    "c5": dict(global_batch=1024, train=True, micro_batch=128,
+               cfg=dict(use_grids=[True, True], is_train=True, grid_loss_weight=1.0, grid_reg_loss_weight=0.1,
+                        wd=0.001, clip_gradient_norm=10.0),
+               desc="train.py step: fwd + CE/Huber/wd loss + BPTT + clip + Adadelta, two scales, "
+                    "data-parallel (one NCCL all-reduce of the 85 MB gradient bucket)"),
 }
 
 
@@ -108,7 +113,9 @@ def cpu_reference_run(cfg_over, n_sample, seed, repeats=1):
   (trajectories/sec, seconds, threads)."""
   from multiverse_b200 import synthetic
   from oracle import multiverse_ref_torch as RT
-  threads = int(os.environ.get("MVB_CPU_THREADS", "0")) or (os.cpu_count() or 1)
+  # all host threads up to 32: on the 128-thread GPU boxes more threads make the oneDNN convolutions of
+  # this small-batch recurrent model SLOWER (profiles/r01_bench.json: 16-32 threads are the optimum)
+  threads = int(os.environ.get("MVB_CPU_THREADS", "0")) or min(32, os.cpu_count() or 1)
   torch.set_num_threads(threads)
   cfg = synthetic.make_config(batch_size=n_sample, **cfg_over)
   w = synthetic.make_weights(cfg, seed)
@@ -145,6 +152,113 @@ def run_reference(args, wl):
   print(json.dumps(line), flush=True)
 
 
+def run_train(args, wl):
+  """Workload c5: one Trainer.step (code/pred_models.py:1719-1742) per timed step."""
+  from multiverse_b200 import build, ops, synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  build.build()
+  world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+  gb = args.global_batch or wl["global_batch"]
+  n_local = gb // world
+  mb = min(wl["micro_batch"], n_local)
+  cfg = synthetic.make_config(batch_size=n_local, **wl["cfg"])
+  weights = synthetic.make_weights(cfg)
+  f = synthetic.make_feeds(cfg, gb, with_pred=True)
+  sl = slice(rank * n_local, (rank + 1) * n_local)
+  pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+  host = dict(scene_feat=pin(f["scene_feat"][sl]), obs_scene=pin(f["obs_scene"][sl] - rank * n_local))
+  for k in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
+    host[k] = [pin(a[sl]) for a in f[k]]
+  up = lambda t: t.to(dev, non_blocking=True)
+  h2d = lambda: {k: ([up(a) for a in v] if isinstance(v, list) else up(v)) for k, v in host.items()}
+  h2d_bytes = sum(t.numel() * t.element_size() for v in host.values() for t in (v if isinstance(v, list) else [v]))
+  eng = TrainEngine(cfg, {k: torch.from_numpy(v) for k, v in weights.items()}, dev, args.planes)
+  feeds = h2d()
+  lr = 0.2
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  for _ in range(args.warmup):
+    eng.train_step(feeds, lr, dist, mb)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  ops.reset_launch_count()
+  ms_total = timed(lambda: eng.train_step(feeds, lr, dist, mb), args.steps)
+  launches = ops.launch_count()
+  clocks = sampler.stop() if rank == 0 else None
+  host_loss = torch.empty(2 * sum(cfg.use_grids), dtype=torch.float32).pin_memory()
+
+  def e2e_step():
+    losses, _ = eng.train_step(h2d(), lr, dist, mb)
+    host_loss.copy_(losses, non_blocking=True)
+
+  e2e_step()
+  ms_e2e = timed(e2e_step, args.steps)
+  if rank != 0:
+    if dist is not None:
+      dist.destroy_process_group()
+    return
+  peaks = load_peaks()
+  fl = 3.0 * sum(cfg.obs_len * (cell_flops(h, w, 64) + cell_flops(h, w, 2)) + 2 * cfg.pred_len * cell_flops(h, w, 32)
+                 for h, w in cfg.scene_grids) * gb / world
+  achieved = fl / (ms_total / args.steps * 1e-3) / 1e12
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    from oracle import multiverse_ref_torch as RT
+    torch.set_num_threads(int(os.environ.get("MVB_CPU_THREADS", "0")) or min(32, os.cpu_count() or 1))
+    c2 = synthetic.make_config(batch_size=2, **wl["cfg"])
+    f2 = synthetic.make_feeds(c2, 2, with_pred=True)
+    t0 = time.perf_counter()
+    RT.loss_and_grads(c2, synthetic.make_weights(c2), f2, dtype=torch.float32)
+    dt = time.perf_counter() - t0
+    cpu = dict(value=2 / dt, unit="trajectories/s", cores=torch.get_num_threads(), kind="port",
+               sample="2 trajectories, one fwd+bwd (%.1f s) of the torch-CPU restatement (autograd); TF 1.15 is not installable" % dt)
+  line = dict(metric="training trajectories/sec (obs8->pred12, fwd+bwd+update)", value=gb * args.steps / (ms_total * 1e-3),
+              unit="trajectories/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+              ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+              dtype="bf16x%d planes -> f32 accumulate" % args.planes, data="synthetic",
+              config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
+                          micro_batch=mb, parallelism="data-parallel x%d, NCCL all-reduce of %.1f MB fp32 grads"
+                          % (world, eng.flat_grad.numel() * 4 / 1e6),
+                          l2="activation store >> 126 MB L2, no flush needed"),
+              clocks=clocks,
+              e2e=dict(value=gb * args.steps / (ms_e2e * 1e-3), unit="trajectories/s", ms_per_step=ms_e2e / args.steps,
+                       h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=host_loss.numel() * 4),
+              gpu_launches=int(launches),
+              roofline=dict(bound="tensor", kernel="whole train step (cell fwd + dgrad + wgrad GEMMs dominate)",
+                            achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                            frac=achieved / peaks["bf16_sustained"], traffic=None,
+                            note="algorithmic FLOPs = 3 x forward cell FLOPs; ceiling 0.333 (3 bf16 passes)"),
+              cpu_baseline=cpu)
+  print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +274,8 @@ def main():
   if args.impl == "reference":
     return run_reference(args, wl)
   args.warmup = max(args.warmup, 3)
+  if wl.get("train"):
+    return run_train(args, wl)
 
   from multiverse_b200 import build, ops, synthetic
   from multiverse_b200.engine import ConvRNNEngine

@@ -78,6 +78,7 @@ class Model(object):
     self.gpuid = 0
     self._engine = None
     self._stale = True
+    self._device_newer = False
     self._rng = np.random.default_rng(getattr(config, "seed", 0) or 0)
     self._own_vars = []
 
@@ -122,7 +123,14 @@ class Model(object):
     self._stale = True
 
   def _sync_to_host(self):
-    pass  # inference never modifies variables on the device
+    """Pull trained parameters back into the host copies (Saver.save, Variable.eval)."""
+    eng = self._engine
+    if eng is not None and getattr(eng, "params", None) is not None and self._device_newer:
+      for v in self._own_vars:
+        key = v.name.split(":")[0]
+        if key in eng.params:
+          v.value = eng.params[key].cpu().numpy()
+      self._device_newer = False
 
   def weights(self):
     return {v.name.split(":")[0]: v.value for v in self._own_vars if v.dtype == "float32"}
@@ -233,12 +241,20 @@ class Model(object):
       dev = torch.device("cuda", self.gpuid)
       torch.cuda.set_device(dev)
       w = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.weights().items()}
-      self._engine = engine.ConvRNNEngine(_engine_config(self.config), w, dev)
+      if self.config.is_train:
+        from . import train_engine
+        self._engine = train_engine.TrainEngine(_engine_config(self.config), w, dev)
+      else:
+        self._engine = engine.ConvRNNEngine(_engine_config(self.config), w, dev)
       self._stale = False
     elif self._stale:
-      import torch as _t
-      self._engine.set_weights({k: _t.from_numpy(np.ascontiguousarray(v))
-                                for k, v in self.weights().items()})
+      w = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.weights().items()}
+      if getattr(self._engine, "params", None) is not None:      # restored checkpoint while training
+        for k, v in w.items():
+          self._engine.params[k].copy_(v)
+        self._engine._repack()
+      else:
+        self._engine.set_weights(w)
       self._stale = False
     return self._engine
 
@@ -264,15 +280,17 @@ class Model(object):
     need_fwd = any(isinstance(h, Handle) and h.kind == "fetch" and
                    h.name in ("grid_pred_decoded", "grid_pred_reg_decoded", "beam_outputs")
                    for h in handles)
-    if any(isinstance(h, Handle) and h.name in ("loss", "wd_loss", "classification_loss",
-                                                "regression_loss", "train_op") for h in handles):
-      raise NotImplementedError("the training fetches (loss / train_op) are not implemented yet: "
-                                "forward inference only in this round (SURVEY.md §8 rows a12-a13)")
+    train_names = ("loss", "wd_loss", "classification_loss", "regression_loss", "train_op")
+    tr = None
+    if any(isinstance(h, Handle) and h.name in train_names for h in handles):
+      tr = self._train_step(feed, apply=any(isinstance(h, Handle) and h.name == "train_op" for h in handles))
     res = self._engine_forward(feed) if need_fwd else None
     out = []
     for h in handles:
       if isinstance(h, tf.Variable):
         out.append(h.eval())
+      elif h.name in train_names:
+        out.append(tr[h.name] if h.index is None else tr[h.name][h.index])
       elif h.name == "beam_outputs":
         out.append(res["beam_outputs"][h.index].cpu().numpy())
       elif h.kind == "fetch":
@@ -284,6 +302,58 @@ class Model(object):
   def _engine_forward(self, feed):
     eng = self._ensure_engine()
     return eng.forward(self._device_feeds(feed))
+
+  def learning_rate(self, step):
+    """Trainer's schedule (code/pred_models.py:1645-1665): init_lr, optionally cosine or staircase
+    exponential decay every num_epoch_per_decay epochs; times emb_lr (:1672)."""
+    import math
+    cfg = self.config
+    lr = cfg.init_lr
+    if getattr(cfg, "use_cosine_lr", False):
+      max_steps = int(cfg.train_num_examples / cfg.batch_size * cfg.num_epochs)
+      lr = cfg.init_lr * 0.5 * (1 + math.cos(math.pi * min(step, max_steps) / max(max_steps, 1)))
+    elif getattr(cfg, "learning_rate_decay", None) is not None:
+      decay_steps = int(cfg.train_num_examples / cfg.batch_size * cfg.num_epoch_per_decay)
+      lr = cfg.init_lr * cfg.learning_rate_decay ** (step // max(decay_steps, 1))
+    return lr * getattr(cfg, "emb_lr", 1.0)
+
+  def _train_step(self, feed, apply=True):
+    """What sess.run([loss, train_op, wd_loss, pred_grid_loss]) does (Trainer.step, :1719-1742)."""
+    import torch
+    cfg = self.config
+    if getattr(cfg, "optimizer", "adadelta") != "adadelta":
+      raise NotImplementedError("only the default Adadelta optimizer has a CUDA update kernel")
+    if getattr(cfg, "use_soft_grid_class", False) or getattr(cfg, "mask_grid_regression", False):
+      raise NotImplementedError("soft grid labels / masked regression loss are not implemented")
+    if not getattr(cfg, "train_w_onehot", False):
+      raise NotImplementedError("training feeds one_hot(argmax) to the decoder (--train_w_onehot, "
+                                "every published command); the soft-feedback variant is not built")
+    eng = self._ensure_engine()
+    dev = eng.device
+    feeds = self._device_feeds(feed)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=True)
+    feeds["grid_pred_labels"] = [None] * len(cfg.scene_grids)
+    feeds["grid_pred_regress"] = [None] * len(cfg.scene_grids)
+    for i in range(len(cfg.scene_grids)):
+      if cfg.use_grids[i]:
+        feeds["grid_pred_labels"][i] = up(feed[self.grid_pred_labels_T[i]], np.int32)
+        feeds["grid_pred_regress"][i] = up(feed[self.grid_pred_regress[i]], np.float32)
+    step = int(self.global_step.value)
+    if apply:
+      losses, wd = eng.train_step(feeds, self.learning_rate(step))
+      self.global_step.value = np.asarray(step + 1, dtype="int32")
+      self._device_newer = True
+    else:
+      losses, wd = eng.loss_and_grads(feeds)
+    losses = losses.cpu().numpy()
+    wd = float(wd)
+    cls = {}
+    reg = {}
+    used = [i for i in range(len(cfg.scene_grids)) if cfg.use_grids[i]]
+    for j, i in enumerate(used):
+      cls[i], reg[i] = losses[2 * j], losses[2 * j + 1]
+    return dict(loss=np.float32(losses.sum() + wd), wd_loss=np.float32(wd), train_op=None,
+                classification_loss=cls, regression_loss=reg)
 
   # ---------------------------------------------------------------- unit-test surface
   def enc_cell(self, x, state, scale=0, kind="class"):
@@ -339,6 +409,9 @@ def _engine_config(config):
           "pred_len").split()
   d = {k: getattr(config, k) for k in keys}
   d["activation_func"] = "tanh"
+  for k, default in (("grid_loss_weight", 1.0), ("grid_reg_loss_weight", 0.1), ("wd", 0.0),
+                     ("clip_gradient_norm", None), ("is_train", False)):
+    d[k] = getattr(config, k, default)
   for flag in ("use_single_decoder", "use_teacher_forcing"):
     if getattr(config, flag, False):
       raise NotImplementedError("--%s is not implemented (no published config uses it)" % flag)

@@ -237,16 +237,20 @@ class TrainEngine(ConvRNNEngine):
     # ---- packed accumulators -> gradients of the TF variables
     for key in ("enc_class", "enc_reg", "dec_class", "dec_reg"):
       pk = getattr(sw, key)
-      ops.unpack_cell_wgrad(cgr[key].dwp, cgr[key].dbp, G[nm[key][0]], G[nm[key][1]], pk.cx, comp=pk.comp)
+      ops.unpack_cell_wgrad(cgr[key].dwp, cgr[key].dbp, G[nm[key][0]], G[nm[key][1]], pk.cx, comp=pk.comp,
+                            accumulate=True)
 
   # ------------------------------------------------------------------ public
-  def loss_and_grads(self, feeds):
+  def loss_and_grads(self, feeds, loss_scale=1.0, zero=True):
     """Forward + loss + backward.  feeds additionally needs grid_pred_labels[i] int32 [N,Tp] and
     grid_pred_regress[i] fp32 [N,Tp,h,w,2].  Returns (losses fp32 tensor [2*scales] on device in
-    the reference's order cls_0, reg_0, cls_1, ..., wd_loss tensor); gradients are left in
-    self.grads (TF variable names), WITHOUT the weight-decay term (added by the optimizer)."""
+    the reference's order cls_0, reg_0, cls_1, ..., wd_loss tensor); gradients are ADDED into
+    self.grads (TF variable names; zeroed first unless zero=False), WITHOUT the weight-decay term
+    (added by the optimizer).  loss_scale weights this call's batch inside a larger one
+    (micro-batching: n_chunk / N, every loss being a batch mean)."""
     cfg, dev = self.cfg, self.device
-    self.flat_grad.zero_()
+    if zero:
+      self.flat_grad.zero_()
     obs_scene = feeds["obs_scene"].to(torch.int32).contiguous()
     scene_feat = feeds["scene_feat"].float().contiguous()
     convs, means = self.scene_cnn(scene_feat, obs_scene)
@@ -255,8 +259,8 @@ class TrainEngine(ConvRNNEngine):
     dconv = [torch.zeros_like(c) for c in convs]
     for i in used:
       S = self._forward_scale(i, feeds, convs, means)
-      self._backward_scale(i, S, feeds, convs, means, dconv, loss_out[i], cfg.grid_loss_weight,
-                           cfg.grid_reg_loss_weight)
+      self._backward_scale(i, S, feeds, convs, means, dconv, loss_out[i],
+                           cfg.grid_loss_weight * loss_scale, cfg.grid_reg_loss_weight * loss_scale)
     # scene CNN backward: conv_k -> conv_{k-1} chain (code/pred_models.py:155-165)
     ins = [scene_feat] + convs[:-1]
     for k in range(len(convs) - 1, -1, -1):
@@ -276,8 +280,26 @@ class TrainEngine(ConvRNNEngine):
                         cfg.wd if k.endswith("/W") else 0.0, 1.0 / world)
     self._repack()
 
-  def train_step(self, feeds, lr, dist=None):
-    losses, wd = self.loss_and_grads(feeds)
+  def loss_and_grads_chunked(self, feeds, micro_batch):
+    """loss_and_grads over a batch larger than the activation store allows: gradient
+    accumulation over contiguous chunks (identical result - every loss is a batch mean)."""
+    n = feeds["obs_scene"].shape[0]
+    if not micro_batch or n <= micro_batch:
+      return self.loss_and_grads(feeds)
+    assert n % micro_batch == 0, "batch must be a multiple of the micro batch"
+    total, wd = None, None
+    for lo in range(0, n, micro_batch):
+      sl = slice(lo, lo + micro_batch)
+      uniq, inv = torch.unique(feeds["obs_scene"][sl], return_inverse=True)
+      part = dict(scene_feat=feeds["scene_feat"][uniq.long()].contiguous(), obs_scene=inv.to(torch.int32))
+      for key in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
+        part[key] = [None if a is None else a[sl] for a in feeds[key]]
+      losses, wd = self.loss_and_grads(part, loss_scale=micro_batch / float(n), zero=(lo == 0))
+      total = losses if total is None else total + losses
+    return total, wd
+
+  def train_step(self, feeds, lr, dist=None, micro_batch=0):
+    losses, wd = self.loss_and_grads_chunked(feeds, micro_batch)
     world = 1
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
       world = dist.get_world_size()

@@ -250,3 +250,62 @@ def test_whole_model_loss_and_gradients(dev, use_grids):
   bad = {k: v for k, v in worst.items() if v > 1e-3}
   print("worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
   assert not bad, bad
+
+
+def test_trainer_step_through_session_and_micro_batching(dev, monkeypatch):
+  """Trainer.step via the shim Session (what code/train.py calls, :253): loss values equal the
+  oracle's, parameters move, global_step advances, micro-batched gradients equal full-batch ones."""
+  import os, sys, types
+  from multiverse_b200 import synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  from oracle import multiverse_ref as R
+  ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  import pred_models
+  tf.reset_default_graph()
+  over = dict(batch_size=4, use_grids=[False, True])
+  cfg = synthetic.make_config(is_train=True, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+                              clip_gradient_norm=10.0, **over)
+  args = types.SimpleNamespace(**vars(cfg))
+  args.modelname = "m"; args.use_soft_grid_class = False; args.use_gt_grid = False; args.train_w_onehot = True
+  args.optimizer = "adadelta"; args.init_lr = 0.2; args.emb_lr = 1.0; args.learning_rate_decay = 0.95
+  args.num_epoch_per_decay = 2.0; args.train_num_examples = 100; args.use_cosine_lr = False
+  args.mask_grid_regression = False
+  w = synthetic.make_weights(cfg, 5); f = synthetic.make_feeds(cfg, 4, 5, with_pred=True)
+  model = pred_models.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    if v.name.split(":")[0] in w:
+      v.assign(w[v.name.split(":")[0]])
+  ns = 2
+  data = dict(obs_grid_class=[np.stack([f["grid_obs_labels"][j][i] for j in range(ns)]) for i in range(4)],
+              pred_grid_class=[np.stack([f["grid_pred_labels"][j][i] for j in range(ns)]) for i in range(4)],
+              batch_scene_feat=f["scene_feat"], batch_obs_scene=f["obs_scene"][:, :, None])
+  for j in range(ns):
+    data["obs_grid_target_all_%d" % j] = list(f["grid_obs_regress"][j])
+    data["pred_grid_target_all_%d" % j] = list(f["grid_pred_regress"][j])
+  batch = (tuple(range(4)), types.SimpleNamespace(data=data))
+  rcfg = R.default_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, **over)
+  tot, losses, wd, grads = RT.loss_and_grads(rcfg, w, f)
+  with tf.Session() as sess:
+    trainer = pred_models.Trainer(model, args)
+    loss, _, wd_loss, pgl = trainer.step(sess, batch)
+    assert abs(loss - tot) < 1e-4 * abs(tot) and abs(wd_loss - wd) < 1e-5 * wd
+    assert np.abs(np.array(pgl) - np.array(losses)).max() < 1e-4 * max(losses)
+    assert int(sess.run(model.global_step)) == 1
+    # one Adadelta step moved every trained variable, and Saver sees the new values
+    moved = model.global_step.owner
+    k = "person_pred/decoder_grid_class_1/decoder_rnn/dec_grid_1/kernel"
+    new = [v for v in tf.global_variables() if v.name == k + ":0"][0].eval()
+    assert np.abs(new - w[k]).max() > 0
+  # micro-batched gradients == full-batch gradients
+  eng = TrainEngine(cfg, {kk: torch.from_numpy(v) for kk, v in w.items()}, dev, 2)
+  feeds = {kk: ([T(a, dev) for a in v] if isinstance(v, list) else T(v, dev)) for kk, v in f.items() if kk != "traj"}
+  l_full, _ = eng.loss_and_grads(feeds)
+  g_full = eng.flat_grad.clone()
+  l_mb, _ = eng.loss_and_grads_chunked(feeds, 2)
+  assert float((l_full - l_mb).abs().max()) < 1e-4 * float(l_full.abs().max())
+  assert float((g_full - eng.flat_grad).abs().max()) < 2e-4 * float(g_full.abs().max())
