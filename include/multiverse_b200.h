@@ -102,6 +102,10 @@ int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int
  * [P][1024][Rp] and xhT_planes [P][9][cpad][Rp] come from mvb_transpose_planes (taps 1 / 9). */
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
                    int H, int W, int cpad, int64_t Rp, int planes, void* stream);
+/* Same result without the transposed copies: both operands are read MN-major straight from the
+ * row-major planes (dG [P][NS*S][1024], xh [P][NS*S][cpad]); the tap is a row shift of the TMA box. */
+int mvb_cell_wgrad_direct(const void* dg_planes, const void* xh_planes, float* dw_packed, int64_t NS,
+                          int H, int W, int cpad, int planes, void* stream);
 /* packed accumulators -> gradients of the TF variables kernel [3,3,cx+256,1024], biases [1024]
  * (accumulate != 0: +=). */
 int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,

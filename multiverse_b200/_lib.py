@@ -30,6 +30,7 @@ SIGNATURES = {
     "mvb_pack_cell_weights_dgrad": [_vp, _vp, _i, _i, _vp],
     "mvb_cell_dgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_cell_wgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i64, _i, _vp],
+    "mvb_cell_wgrad_direct": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_unpack_cell_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvb_loss_fwd_bwd": [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _i64, _f, _vp, _vp],
     "mvb_head_bwd": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i64, _i, _i, _vp],

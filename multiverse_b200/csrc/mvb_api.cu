@@ -65,6 +65,31 @@ int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_
   return MVB_OK;
 }
 
+int encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t (&dims)[4],
+                        const uint64_t (&strides_bytes)[3], const uint32_t (&box)[4],
+                        int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MVB_ERR_DRIVER;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d (dims %llu,%llu,%llu,%llu)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3]);
+    return MVB_ERR_DRIVER;
+  }
+  return MVB_OK;
+}
+
 }  // namespace mvb
 
 using namespace mvb;
@@ -125,6 +150,10 @@ int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
                    int H, int W, int cpad, int64_t Rp, int planes, void* stream) {
   return cell_wgrad(dgT_planes, xhT_planes, dw_packed, NS, H, W, cpad, Rp, planes, S(stream));
+}
+int mvb_cell_wgrad_direct(const void* dg_planes, const void* xh_planes, float* dw_packed, int64_t NS,
+                          int H, int W, int cpad, int planes, void* stream) {
+  return cell_wgrad_mn(dg_planes, xh_planes, dw_packed, NS, H, W, cpad, planes, S(stream));
 }
 int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
                           float* dbiases, int cx, int comp, int accumulate, void* stream) {

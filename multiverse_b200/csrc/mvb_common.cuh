@@ -156,6 +156,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 4-D tiled TMA load.
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -215,9 +225,10 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // K-major shared-memory matrix descriptor (SM100 "version 1"), swizzle given by
 // layout_type (2 = 128B, 4 = 64B, 6 = 32B); sbo = byte stride between 8-row groups.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
+                                                   uint32_t layout_type, uint32_t lbo_bytes = 0) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
   d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout_type << 61;
@@ -230,5 +241,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
                         uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                         uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+int encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t (&dims)[4],
+                        const uint64_t (&strides_bytes)[3], const uint32_t (&box)[4],
+                        int swizzle_bytes);
 
 }  // namespace mvb

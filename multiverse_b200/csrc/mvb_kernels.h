@@ -59,6 +59,8 @@ int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long lo
                int cpad, int P, cudaStream_t stream);
 int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long long NS, int H, int W,
                int cpad, long long Rp, int P, cudaStream_t stream);
+int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long long NS, int H, int W,
+                  int cpad, int P, cudaStream_t stream);
 int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
                    const float* dc_in, void* dg_planes, long long plane_stride, float* dc_prev,
                    float* dbias_packed, long long NS, int H, int W, int P, cudaStream_t stream);

@@ -15,6 +15,7 @@
 // Algorithmic FLOPs: dgrad = wgrad = forward (2*R*9*cpad*1024 each).
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
+#include <stdlib.h>
 
 namespace mvb {
 
@@ -29,7 +30,7 @@ constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 10 KB (BN = 144 uses 9
 constexpr uint32_t G_SW64_LAYOUT = 4;
 constexpr uint32_t G_SW64_SBO = 512;
 
-enum { MODE_DGRAD = 0, MODE_WGRAD = 1 };
+enum { MODE_DGRAD = 0, MODE_WGRAD = 1, MODE_WGRAD_MN = 2 };
 
 template <int P> struct GemmCfg {
   static constexpr int STAGE_BYTES = P * (G_A_PLANE + G_B_PLANE);
@@ -45,6 +46,11 @@ struct GemmParams {
   int num_kb;          // k-blocks per tile
   long long num_m_tiles;
   int num_n_tiles;
+  // MODE_WGRAD_MN: operands are read MN-major straight from the row-major activations
+  int nb;              // 32-channel blocks per N tile (bn = 32*nb)
+  int n_per_tap;       // N tiles per tap (cpad / bn)
+  int ksplit;          // K (= halo rows) is split over this many work items
+  uint32_t lbo, sbo;   // UMMA descriptor strides of the MN-major SWIZZLE_64B tiles
 };
 
 template <int P, int MODE>
@@ -66,7 +72,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;
   const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + prm.bn * G_BLOCK_K * 2);
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(prm.bn >> 3) << 17) |
-                         ((uint32_t)(G_BLOCK_M >> 4) << 24);
+                         ((uint32_t)(G_BLOCK_M >> 4) << 24) |
+                         (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
   if (warp == 1 && lane == 0) {
@@ -97,11 +104,19 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
           tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, ntile * prm.bn, 0);
-        } else {
+        } else if (MODE == MODE_WGRAD) {
           // A = dG^T[128 gate rows, 32 halo rows];  B = tap-shifted xh^T[tap][bn channels, 32 halo rows]
           const int tap = ntile >> 1, half = ntile & 1;
           tma_load_3d(sa, &tmA, &full_bar[stage], kb * G_BLOCK_K, (int)(mt * G_BLOCK_M), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K, tap * prm.cpad + half * prm.bn, 0);
+        } else {
+          // MN-major: A = dG[32 halo rows (K), 4 blocks of 32 gate columns], B = xh[32 halo rows + shift(tap),
+          // nb blocks of 32 channels]; ntile = (tap, n-in-tap, k-split)
+          const int ks = ntile % prm.ksplit, nn = (ntile / prm.ksplit) % prm.n_per_tap, tap = ntile / (prm.ksplit * prm.n_per_tap);
+          const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+          const int k0 = (ks * prm.num_kb + kb) * G_BLOCK_K;
+          tma_load_4d(sa, &tmA, &full_bar[stage], 0, k0, (int)mt * 4, 0);
+          tma_load_4d(sb, &tmB, &full_bar[stage], 0, k0 + shift, nn * prm.nb, 0);
         }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
@@ -129,8 +144,15 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int pb = 0; pb < P - pa; ++pb) {
 #pragma unroll
             for (int k = 0; k < G_BLOCK_K / G_UMMA_K; ++k) {
-              const uint64_t ad = make_smem_desc(sa + pa * G_A_PLANE + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
-              const uint64_t bd = make_smem_desc(sb + pb * b_plane + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+              uint64_t ad, bd;
+              if (MODE == MODE_WGRAD_MN) {
+                // one UMMA consumes 16 K rows = two 8-row groups (sbo apart) of every 32-wide MN block
+                ad = make_smem_desc(sa + pa * G_A_PLANE + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
+                bd = make_smem_desc(sb + pb * b_plane + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
+              } else {
+                ad = make_smem_desc(sa + pa * G_A_PLANE + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+                bd = make_smem_desc(sb + pb * b_plane + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+              }
               umma_bf16(d_tmem, ad, bd, idesc, first);
               first = 1u;
             }
@@ -161,10 +183,14 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           valid = (x < g.W) && (y < g.H);
         }
         dst = prm.out + row * prm.cpad + ntile * prm.bn;
-      } else {
+      } else if (MODE == MODE_WGRAD) {
         valid = row < kGates;
         const int tap = ntile >> 1, half = ntile & 1;
         dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + half * prm.bn;
+      } else {
+        valid = row < kGates;
+        const int nn = (ntile / prm.ksplit) % prm.n_per_tap, tap = ntile / (prm.ksplit * prm.n_per_tap);
+        dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + nn * prm.bn;
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -179,6 +205,11 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int q = 0; q < 4; ++q) {
             float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            if (MODE == MODE_WGRAD_MN) {   // several K splits add into the same tile
+              float* da = reinterpret_cast<float*>(d4 + q);
+              atomicAdd(da, o.x); atomicAdd(da + 1, o.y); atomicAdd(da + 2, o.z); atomicAdd(da + 3, o.w);
+              continue;
+            }
             if (MODE == MODE_WGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
             d4[q] = o;
           }
@@ -440,6 +471,49 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
     case 1: return launch_pgemm<1, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
     case 2: return launch_pgemm<2, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
     default: return launch_pgemm<3, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
+  }
+}
+
+int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long long NS, int H, int W,
+                  int cpad, int P, cudaStream_t stream) {
+  MVB_REQUIRE(P >= 1 && P <= 3, "cell_wgrad_mn: planes P=%d", P);
+  MVB_REQUIRE(dg_planes && xh_planes && dwp && NS > 0, "cell_wgrad_mn: bad args");
+  MVB_REQUIRE(cpad == 288 || cpad == 320, "cell_wgrad_mn: cpad=%d unsupported", cpad);
+  const Grid g = make_grid(H, W);
+  const long long R = NS * g.S;
+  const int bn = cpad == 288 ? 96 : 160;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {32, (uint64_t)R, kGates / 32, (uint64_t)P};
+    const uint64_t st[3] = {kGates * 2ull, 64, (uint64_t)R * kGates * 2};
+    const uint32_t box[4] = {32, G_BLOCK_K, 4, (uint32_t)P};
+    int rc = encode_tmap_4d_bf16(&tmA, dg_planes, dims, st, box, 64);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {32, (uint64_t)R, (uint64_t)cpad / 32, (uint64_t)P};
+    const uint64_t st[3] = {(uint64_t)cpad * 2, 64, (uint64_t)R * cpad * 2};
+    const uint32_t box[4] = {32, G_BLOCK_K, (uint32_t)(bn / 32), (uint32_t)P};
+    int rc = encode_tmap_4d_bf16(&tmB, xh_planes, dims, st, box, 64);
+    if (rc) return rc;
+  }
+  GemmParams prm;
+  prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = bn;
+  prm.nb = bn / 32; prm.n_per_tap = cpad / bn;
+  const long long kb_total = (R + G_BLOCK_K - 1) / G_BLOCK_K;
+  prm.ksplit = kb_total >= 64 ? 2 : 1;
+  prm.num_kb = (int)((kb_total + prm.ksplit - 1) / prm.ksplit);
+  prm.num_m_tiles = kGates / G_BLOCK_M;
+  prm.num_n_tiles = 9 * prm.n_per_tap * prm.ksplit;
+  prm.lbo = 32 * 64;   // bytes between 32-wide MN blocks ([32 K rows][64 B] each)
+  prm.sbo = 8 * 64;    // bytes between groups of 8 K rows
+  int sms = 0;
+  int rc = num_sms_of_device(&sms);
+  if (rc) return rc;
+  switch (P) {
+    case 1: return launch_pgemm<1, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
   }
 }
 

@@ -222,6 +222,12 @@ def cell_wgrad(dgT, xhT, dw_packed, h, w, ns):
             xhT.shape[3], dgT.shape[0], _stream())
 
 
+def cell_wgrad_direct(dg_planes, xh, dw_packed, h, w, ns):
+  """wgrad straight from the row-major planes (MN-major tcgen05 operands, no transposes)."""
+  _lib.call("mvb_cell_wgrad_direct", _p(dg_planes), _p(xh), _p(dw_packed), ns, h, w, xh.shape[2],
+            xh.shape[0], _stream())
+
+
 def unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp=False, accumulate=False):
   _lib.call("mvb_unpack_cell_wgrad", _p(dw_packed), _p(dbias_packed), _p(dkernel), _p(dbiases), cx,
             int(comp), int(accumulate), _stream())

@@ -7,8 +7,8 @@ all-reduce of the flat fp32 gradient buffer: sum, scale by 1/G 
 optimizer kernel, then clip, which reproduces the single-GPU batch semantics because every loss
 is a mean over equal shards.
 
-Per cell step the backward is  lstm_gates_bwd -> cell_dgrad (tcgen05) -> transposes -> cell_wgrad
-(tcgen05);  around it: head_bwd, emb_bwd, gnn_bwd, enc_class_input_bwd, scene_*_bwd.
+Per cell step the backward is  lstm_gates_bwd -> cell_dgrad (tcgen05) -> cell_wgrad_direct (tcgen05,
+MN-major operands read straight from the stored planes);  around it: head_bwd, emb_bwd, gnn_bwd, enc_class_input_bwd, scene_*_bwd.
 """
 from __future__ import annotations
 
@@ -154,7 +154,6 @@ class TrainEngine(ConvRNNEngine):
     n, h, w = S["n"], S["h"], S["w"]
     dev, P = self.device, self.planes
     R = ops.halo_rows(n, h, w)
-    Rp = (R + 7) // 8 * 8
     dg = self._one(("dg", i, n), lambda: torch.zeros((P, R, 4 * HID), dtype=torch.bfloat16, device=dev))
     dc_prev = self._steps(("dc_pp", i, n), 2, lambda: ops.alloc_state(n, h, w, dev))
     out_dc = dc_prev[0] if dc is not dc_prev[0] else dc_prev[1]
@@ -163,12 +162,7 @@ class TrainEngine(ConvRNNEngine):
     if need_dxh:
       dxh = self._one(("dxh", i, n, packed.cpad), lambda: torch.zeros((R, packed.cpad), device=dev))
       ops.cell_dgrad(dg, packed.wd, dxh, h, w, n)
-    dgT = self._one(("dgT", i, n), lambda: torch.zeros((P, 4 * HID, Rp), dtype=torch.bfloat16, device=dev))
-    xhT = self._one(("xhT", i, n, packed.cpad),
-                    lambda: torch.zeros((P, 9, packed.cpad, Rp), dtype=torch.bfloat16, device=dev))
-    ops.transpose_planes(dg, dgT)
-    ops.transpose_planes(xh, xhT, taps=9, w=w)
-    ops.cell_wgrad(dgT, xhT, cg.dwp, h, w, n)
+    ops.cell_wgrad_direct(dg, xh, cg.dwp, h, w, n)     # MN-major operands: no transposed copies
     return dxh, out_dc
 
   def _backward_scale(self, i, S, feeds, convs, means, dconv, loss_out, cw, rw):

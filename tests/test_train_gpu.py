@@ -82,6 +82,10 @@ def test_cell_backward_matches_autograd(dev, name):
   ops.unpack_cell_wgrad(dwp, dbp, dk, db, cx, comp=pk.comp)
   assert rel(0.5 * dk.cpu().numpy(), t["kernel"].grad.numpy()) < GTOL
   assert rel(db.cpu().numpy(), t["biases"].grad.numpy()) < GTOL
+  # the production path: MN-major operands straight from the row-major planes (no transposes)
+  dwp2 = torch.zeros_like(dwp)
+  ops.cell_wgrad_direct(dg, xh, dwp2, h, w, ns)
+  assert rel(dwp2.cpu().numpy(), 0.5 * dwp.cpu().numpy()) < 1e-6
 
 
 def test_loss_kernel(dev):
