@@ -70,6 +70,20 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
                           int64_t NS, int H, int W, int cpad, int planes, float forget_bias,
                           void* stream);
 
+/* Class-decoder cell step whose input is grid_emb(one_hot(ids)) (pred_models.py:411-446, :602-666).
+ * That input is tanh(b) everywhere except the 3x3 cells around ids[s], so its contribution to the
+ * gate pre-activations is exactly two table rows per cell (mvb_cell_xfold_tables): the x chunks of
+ * the K loop are skipped (1/9 of the MMAs) and the x block of xh_planes is never read.
+ *   table_B  fp32 [9][1024]      (border class of the cell; biases folded in)
+ *   table_T2 fp32 [9][25][1024]  (border class of ids[s]; 5x5 offset of the cell to ids[s]) */
+int mvb_cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be,
+                          int E, float* table_B, float* table_T2, void* stream);
+int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, const float* table_B,
+                                 const float* table_T2, const int32_t* ids, const float* c_in,
+                                 const int32_t* row_map, float* c_out, float* h32_out, void* hp_out,
+                                 int64_t hp_plane_stride, int cpad_out, int ch_off_out, int64_t NS, int H,
+                                 int W, int cpad, int planes, float forget_bias, void* stream);
+
 /* ---- a13: BPTT step of the cell (Trainer, pred_models.py:1636-1742; tf.gradients :1698 through
  *      ConvLSTMCell) ------------------------------------------------------------------------ */
 

@@ -117,7 +117,20 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
                           void* stream) {
   return cell_fwd(xh_planes, w_planes, bias_packed, c_in, row_map, c_out, h32_out, hp_out,
                   hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
-                  nullptr, S(stream));
+                  nullptr, nullptr, nullptr, nullptr, S(stream));
+}
+int mvb_cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be,
+                          int E, float* table_B, float* table_T2, void* stream) {
+  return cell_xfold_tables(kernel, biases, We, be, E, table_B, table_T2, S(stream));
+}
+int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, const float* table_B,
+                                 const float* table_T2, const int32_t* ids, const float* c_in,
+                                 const int32_t* row_map, float* c_out, float* h32_out, void* hp_out,
+                                 int64_t hp_plane_stride, int cpad_out, int ch_off_out, int64_t NS, int H,
+                                 int W, int cpad, int planes, float forget_bias, void* stream) {
+  return cell_fwd(xh_planes, w_planes, table_B, c_in, row_map, c_out, h32_out, hp_out, hp_plane_stride,
+                  cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias, nullptr, table_B, table_T2, ids,
+                  S(stream));
 }
 
 int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
@@ -127,7 +140,7 @@ int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
                                 int planes, float forget_bias, void* stream) {
   return cell_fwd(xh_planes, w_planes, bias_packed, c_in, nullptr, c_out, h32_out, hp_out,
                   hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
-                  gates_out, S(stream));
+                  gates_out, nullptr, nullptr, nullptr, S(stream));
 }
 int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
                        const float* dc_in, void* dg_planes, int64_t plane_stride, float* dc_prev,

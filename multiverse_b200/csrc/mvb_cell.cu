@@ -53,6 +53,14 @@ struct CellParams {
   float* c_out;             // [R, 256]
   float* h32_out;           // [R, 256] or nullptr
   float* gates_out;         // [R, 1024] activated gates (packed column order) for training, or nullptr
+  // "x-fold" (class decoder only): the input is grid_emb(one_hot(id)), i.e. tanh(b) everywhere except
+  // the 3x3 cells around id, so its whole contribution to the pre-activations is a table look-up:
+  // xf_B[border class of the cell][1024] (bias folded in) + xf_T2[border class of id][5x5 offset][1024]
+  // for the <=25 cells around id.  The x chunks are then skipped in the K loop (kb_begin).
+  const float* xf_B;        // [9][1024] packed column order, or nullptr
+  const float* xf_T2;       // [9][25][1024]
+  const int* xf_ids;        // [NS] arg-max cell of every sample row
+  int kb_begin;             // first k-block of the K loop (9 * number of skipped 32-channel chunks)
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
   long long hp_plane_stride;  // elements between planes of hp_out
   int cpad_out;             // row pitch of hp_out (elements)
@@ -110,7 +118,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const long long m0 = (t / N_TILES) * BLOCK_M;
       const int n0 = (int)(t % N_TILES) * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = prm.kb_begin; kb < num_kb; ++kb) {
         // chunk-major K order: the 9 taps of one 32-channel chunk are consecutive (their A boxes
         // overlap in L2), and the x block - whose terms can be orders of magnitude larger than the
         // h terms (raw pixel offsets in the regression encoder) - is accumulated first, so the
@@ -136,12 +144,12 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = prm.kb_begin; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + P * A_PLANE_BYTES;
-        uint32_t first = (kb == 0) ? 0u : 1u;
+        uint32_t first = (kb == prm.kb_begin) ? 0u : 1u;
 #pragma unroll
         for (int pa = 0; pa < P; ++pa) {
 #pragma unroll
@@ -173,12 +181,25 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
       const long long row = m0 + wq * 32 + lane;
       bool valid = row < prm.R;
       long long src_row = row;
+      const float* xfb = nullptr;      // x-fold: table row of this cell's border class (bias included)
+      const float* xft = nullptr;      // x-fold: table row of the offset to the arg-max cell, if within 5x5
       if (valid) {
         const long long smp = row / g.S;
         const int rem = (int)(row - smp * g.S);
         const int y = rem / g.Wp, x = rem - y * g.Wp;
         valid = (x < g.W) && (y < g.H);
         if (valid && prm.row_map) src_row = (long long)prm.row_map[smp] * g.S + rem;
+        if (valid && prm.xf_B) {
+          const int cy = y == 0 ? 0 : (y == g.H - 1 ? 2 : 1), cx = x == 0 ? 0 : (x == g.W - 1 ? 2 : 1);
+          xfb = prm.xf_B + (cy * 3 + cx) * kGates;
+          const int a = prm.xf_ids[smp];
+          const int ay = a / g.W, ax = a - ay * g.W;
+          const int ry = y - ay, rx = x - ax;
+          if (ry >= -2 && ry <= 2 && rx >= -2 && rx <= 2) {
+            const int acy = ay == 0 ? 0 : (ay == g.H - 1 ? 2 : 1), acx = ax == 0 ? 0 : (ax == g.W - 1 ? 2 : 1);
+            xft = prm.xf_T2 + ((long long)(acy * 3 + acx) * 25 + (ry + 2) * 5 + (rx + 2)) * kGates;
+          }
+        }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -206,14 +227,19 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         tmem_ld_wait();
         if (valid) {
-          const float* bptr = prm.bias + nt * BLOCK_N + j0;
+          const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
+          const float* tptr = xft ? xft + nt * BLOCK_N + j0 : nullptr;
           float cn[16], hn[16];
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
-            const float xi = __uint_as_float(gi[v]) + __ldg(bptr + 0 * TILE_CH + v);
-            const float xj = __uint_as_float(gj[v]) + __ldg(bptr + 1 * TILE_CH + v);
-            const float xf = __uint_as_float(gf[v]) + __ldg(bptr + 2 * TILE_CH + v);
-            const float xo = __uint_as_float(go[v]) + __ldg(bptr + 3 * TILE_CH + v);
+            float xi = __uint_as_float(gi[v]) + __ldg(bptr + 0 * TILE_CH + v);
+            float xj = __uint_as_float(gj[v]) + __ldg(bptr + 1 * TILE_CH + v);
+            float xf = __uint_as_float(gf[v]) + __ldg(bptr + 2 * TILE_CH + v);
+            float xo = __uint_as_float(go[v]) + __ldg(bptr + 3 * TILE_CH + v);
+            if (tptr) {
+              xi += __ldg(tptr + 0 * TILE_CH + v); xj += __ldg(tptr + 1 * TILE_CH + v);
+              xf += __ldg(tptr + 2 * TILE_CH + v); xo += __ldg(tptr + 3 * TILE_CH + v);
+            }
             const float ai = sigmoid_acc(xi), aj = tanh_acc(xj), af = sigmoid_acc(xf + prm.forget_bias),
                         ao = sigmoid_acc(xo);
             const float c1 = af * cprev[v] + ai * aj;
@@ -317,6 +343,58 @@ __global__ void pack_weights_kernel(const float* __restrict__ kernel, const floa
   }
 }
 
+// x-fold tables of a class-decoder cell (packed column order n = tile*256 + gate*64 + j):
+//   X0[e] = tanh(be[e]);  delta[k][e] = tanh(be[e] + We[8-k][e]) - X0[e]   (k = 3x3 position around the arg-max;
+//   the one-hot at a reaches cell q = a + k through tap a - q, i.e. tap index 8 - k)
+//   B[cls][n]        = bias[n] + sum_{tap valid at a cell of border class cls} X0 . W[tap][:E][n]
+//   T2[acls][r][n]   = sum_{tap: q = p + off(tap) in 3x3(a), q inside the grid} delta[k(q)] . W[tap][:E][n],  r = p - a
+__global__ void xfold_tables_kernel(const float* __restrict__ kernel, const float* __restrict__ biases,
+                                    const float* __restrict__ We, const float* __restrict__ be, int E,
+                                    float* __restrict__ Bt, float* __restrict__ T2) {
+  const int total = (9 + 9 * 25) * kGates;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % kGates, item = i / kGates;
+    const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+    const int col = gate * kHidden + tile * TILE_CH + j;
+    const int cin_tot = E + kHidden;
+    float acc = 0.f;
+    if (item < 9) {
+      const int cy = item / 3, cx = item % 3;
+      acc = biases[col];
+      for (int t = 0; t < 9; ++t) {
+        const int oy = t / 3 - 1, ox = t % 3 - 1;
+        if ((cy == 0 && oy < 0) || (cy == 2 && oy > 0) || (cx == 0 && ox < 0) || (cx == 2 && ox > 0)) continue;
+        for (int e = 0; e < E; ++e) acc = fmaf(tanhf(be[e]), kernel[((long long)t * cin_tot + e) * kGates + col], acc);
+      }
+      Bt[item * kGates + n] = acc;
+    } else {
+      const int it2 = item - 9, acls = it2 / 25, rr = it2 % 25;
+      const int acy = acls / 3, acx = acls % 3;
+      const int ry = rr / 5 - 2, rx = rr % 5 - 2;
+      for (int t = 0; t < 9; ++t) {
+        const int ky = ry + t / 3 - 1, kx = rx + t % 3 - 1;      // q - a
+        if (ky < -1 || ky > 1 || kx < -1 || kx > 1) continue;
+        if ((acy == 0 && ky < 0) || (acy == 2 && ky > 0) || (acx == 0 && kx < 0) || (acx == 2 && kx > 0)) continue;
+        const int k = (ky + 1) * 3 + (kx + 1);
+        for (int e = 0; e < E; ++e) {
+          const float d = tanhf(be[e] + We[(8 - k) * E + e]) - tanhf(be[e]);
+          acc = fmaf(d, kernel[((long long)t * cin_tot + e) * kGates + col], acc);
+        }
+      }
+      T2[(long long)it2 * kGates + n] = acc;
+    }
+  }
+}
+
+int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,
+                      float* Bt, float* T2, cudaStream_t stream) {
+  MVB_REQUIRE(kernel && biases && We && be && Bt && T2 && E > 0, "cell_xfold_tables: bad args");
+  xfold_tables_kernel<<<234, 256, 0, stream>>>(kernel, biases, We, be, E, Bt, T2);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 template <int P>
 static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CellParams& prm,
                        int num_sms, cudaStream_t stream) {
@@ -338,7 +416,8 @@ static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const Cel
 int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, const float* c_in,
              const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
-             float forget_bias, float* gates_out, cudaStream_t stream) {
+             float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
+             cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "cell_fwd: planes P=%d not in {1,2,3}", P);
   MVB_REQUIRE(cpad % BLOCK_K == 0 && cpad >= kHidden + BLOCK_K, "cell_fwd: cpad=%d must be a multiple of 32 and >= 288", cpad);
   MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
@@ -360,6 +439,12 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   CellParams prm;
   prm.bias = bias; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
   prm.gates_out = gates_out;
+  prm.xf_B = xf_B; prm.xf_T2 = xf_T2; prm.xf_ids = xf_ids;
+  prm.kb_begin = 0;
+  if (xf_B) {
+    MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
+    prm.kb_begin = 9 * ((cpad - kHidden) / BLOCK_K);
+  }
   prm.hp_out = reinterpret_cast<__nv_bfloat16*>(hp_out);
   prm.hp_plane_stride = hp_plane_stride; prm.cpad_out = cpad_out; prm.ch_off_out = ch_off_out;
   prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.forget_bias = forget_bias;

@@ -8,12 +8,12 @@ arithmetic step is a kernel of the C-ABI library:
   scene CNN (:146-165)                      -> mvb_scene_conv_fwd x2, mvb_scene_time_mean
   class encoder (:210-215, dynamic_rnn)      -> T x [mvb_enc_class_input, mvb_convlstm_cell_fwd]
   regression encoder (:232-234)              -> T x [mvb_nhwc_to_planes, mvb_convlstm_cell_fwd]
-  greedy class decoder (:311-471, raw_rnn)   -> Tp x [mvb_gnn_attend_fwd, mvb_convlstm_cell_fwd,
-                                                     mvb_head_class_fwd (logits+argmax+emb)]
+  greedy class decoder (:311-471, raw_rnn)   -> Tp x [mvb_gnn_attend_fwd, mvb_convlstm_cell_fwd_onehot,
+                                                     mvb_head_class_fwd (logits+argmax)]
   regression decoder (:298-305)              -> Tp x [mvb_convlstm_cell_fwd, mvb_head_reg_fwd]
   beam decoder (:474-806)                    -> Tp x [mvb_head_class_fwd, mvb_beam_step,
-                                                     mvb_emb_onehot_fwd, mvb_gnn_attend_fwd,
-                                                     mvb_convlstm_cell_fwd] + mvb_beam_backtrace
+                                                     mvb_gnn_attend_fwd,
+                                                     mvb_convlstm_cell_fwd_onehot] + mvb_beam_backtrace
 
 The (c,h) gather by parent beam (:611-623) is never a copy: mvb_beam_step emits a row map that
 the next GNN / cell launch reads its state through.
@@ -61,6 +61,8 @@ class ScaleWeights(object):
     self.emb_reg = (f(nm["emb_reg"][0]), f(nm["emb_reg"][1]))
     self.head_class = f(nm["head_class"])
     self.head_reg = f(nm["head_reg"])
+    # inference: the class decoder's embedded one-hot input folded into table look-ups
+    self.dec_class_xf = ops.XFold(f(nm["dec_class"][0]), f(nm["dec_class"][1]), *self.emb_class)
 
 
 class ConvRNNEngine(object):
@@ -117,6 +119,16 @@ class ConvRNNEngine(object):
     ops.cell_fwd(*args, **kw)
     e1.record()
     self.cell_events.append((tag, (args[6], args[7], args[8]), e0, e1))   # (h, w, ns)
+
+  def _cell_onehot(self, tag, *args, **kw):
+    """ops.cell_fwd_onehot with the same optional event bracket."""
+    if self.cell_events is None:
+      return ops.cell_fwd_onehot(*args, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.cell_fwd_onehot(*args, **kw)
+    e1.record()
+    self.cell_events.append((tag, (args[8], args[9], args[10]), e0, e1))   # (h, w, ns)
 
   # ------------------------------------------------------------------ pieces
   def scene_cnn(self, scene_feat, obs_scene):
@@ -181,23 +193,19 @@ class ConvRNNEngine(object):
     h32 = self._state("dec_h32", n, h, w)
     logits = torch.empty((pred_len, n, h * w), dtype=torch.float32, device=self.device)
     ids = torch.empty((pred_len, n), dtype=torch.int32, device=self.device)
-    We, be = sw.emb_class
-    ops.emb_onehot_fwd(first_ids, We, be, xh[0], h, w)
-    h_src, c_src = h32_enc, c_enc
+    h_src, c_src, ids_prev = h32_enc, c_enc, first_ids
     for t in range(pred_len):
       cur, nxt = xh[t % 2], xh[(t + 1) % 2]
       if cfg.use_gnn:
         ops.gnn_attend_fwd(h_src, scene_mean, cur, h, w, n)
-      elif t == 0:
-        # no attention: the planes of the encoder state must already sit in cur's h block
-        pass
-      self._cell("dec_class", cur, sw.dec_class, c_src, c[(t + 1) % 2], h32,
-                   None if cfg.use_gnn else nxt, h, w, n)
+      # (no attention: the planes of the previous h already sit in cur's h block)
+      # the embedded one_hot(ids_prev) input is folded into table look-ups: nobody writes the x block
+      self._cell_onehot("dec_class", cur, sw.dec_class, sw.dec_class_xf, ids_prev, c_src, c[(t + 1) % 2],
+                        h32, None if cfg.use_gnn else nxt, h, w, n)
       c_src, h_src = c[(t + 1) % 2], h32
-      last = t == pred_len - 1
-      ops.head_class_fwd(h32, sw.head_class, logits[t], ids[t], None if last else We,
-                         None if last else be, None if last else nxt, h, w, n,
+      ops.head_class_fwd(h32, sw.head_class, logits[t], ids[t], None, None, None, h, w, n,
                          planes=self.planes)
+      ids_prev = ids[t]
     return logits, ids
 
   def decode_reg(self, i, c_enc, first_input, pred_len, xh):
@@ -239,14 +247,15 @@ class ConvRNNEngine(object):
     scores = [torch.zeros((n, b), dtype=torch.float32, device=dev) for _ in range(2)]
     row_map = torch.empty((ns,), dtype=torch.int32, device=dev)
     tile_map = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(b).contiguous()
-    We, be = sw.emb_class
-    # time = 0: tiled encoder state and last observed cell (:497-502, :527-531)
-    ops.emb_onehot_fwd(first_ids.repeat_interleave(b).contiguous(), We, be, xh[0], h, w)
+    xf = sw.dec_class_xf
+    # time = 0: tiled encoder state and last observed cell (:497-502, :527-531); the embedded one-hot
+    # input of every step is folded into table look-ups (ops.cell_fwd_onehot)
+    ids0 = first_ids.repeat_interleave(b).contiguous()
     if cfg.use_gnn:
       ops.gnn_attend_fwd(h32_enc, scene_mean, xh[0], h, w, ns, beam=b, row_map=tile_map)
     else:
       raise NotImplementedError("beam search without use_gnn is not wired (no published config)")
-    self._cell("beam", xh[0], sw.dec_class, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
+    self._cell_onehot("beam", xh[0], sw.dec_class, xf, ids0, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
     cur_c = 1
     for time in range(1, pred_len + 1):
       ops.head_class_fwd(h32, sw.head_class, step_logits[time - 1], None, None, None, None, h, w,
@@ -259,9 +268,9 @@ class ConvRNNEngine(object):
       if time == pred_len:
         break
       nxt = xh[time % 2]
-      ops.emb_onehot_fwd(step_ids[time - 1].view(-1), We, be, nxt, h, w)
       ops.gnn_attend_fwd(h32, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
-      self._cell("beam", nxt, sw.dec_class, c[cur_c], c[1 - cur_c], h32, None, h, w, ns, row_map=row_map)
+      self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c[cur_c], c[1 - cur_c], h32,
+                        None, h, w, ns, row_map=row_map)
       cur_c = 1 - cur_c
     out_ids = torch.empty((n, b, pred_len), dtype=torch.int32, device=dev)
     out_logits = torch.empty((n, b, pred_len, v), dtype=torch.float32, device=dev)

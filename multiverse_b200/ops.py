@@ -91,6 +91,30 @@ def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
             packed.cpad, packed.planes, float(forget_bias), _stream())
 
 
+class XFold(object):
+  """Look-up tables that replace the embedded one-hot input of a class-decoder cell."""
+
+  def __init__(self, kernel, biases, We, be):
+    dev = kernel.device
+    self.B = torch.empty((9, 4 * HIDDEN), dtype=torch.float32, device=dev)
+    self.T2 = torch.empty((9, 25, 4 * HIDDEN), dtype=torch.float32, device=dev)
+    _lib.call("mvb_cell_xfold_tables", _p(kernel.detach().float().contiguous()),
+              _p(biases.detach().float().contiguous()), _p(We), _p(be), We.shape[3], _p(self.B),
+              _p(self.T2), _stream())
+
+
+def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
+                    forget_bias=1.0):
+  """Class-decoder step with the embedded one-hot input folded into table look-ups."""
+  if xh_next is not None:
+    stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
+  else:
+    stride, cpad_out, off = 0, 0, 0
+  _lib.call("mvb_convlstm_cell_fwd_onehot", _p(xh), _p(packed.w), _p(xf.B), _p(xf.T2), _p(ids), _p(c_in),
+            _p(row_map), _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w,
+            packed.cpad, packed.planes, float(forget_bias), _stream())
+
+
 def nhwc_to_planes(src, xh, ch_off, h, w, comp=False):
   ns, c = src.shape[0], src.shape[-1]
   _lib.call("mvb_nhwc_to_planes", _p(src), _p(xh), xh.stride(0), xh.shape[2], ch_off, ns, h, w,

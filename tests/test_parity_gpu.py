@@ -326,3 +326,33 @@ def test_full_size_properties(dev):
   for i in range(2):
     assert bool(torch.isfinite(full["grid_pred_decoded"][i]).all())
     assert bool(torch.isfinite(full["grid_pred_reg_decoded"][i]).all())
+
+
+def test_cell_onehot_fold_equals_explicit_embedding(dev):
+  """mvb_convlstm_cell_fwd_onehot (embedded one-hot input folded into table look-ups, x chunks
+  skipped) against the oracle cell fed the explicit grid_emb(one_hot(ids)) - corner, edge and
+  interior arg-max cells."""
+  from multiverse_b200 import ops
+  d = cases.cell_case("dec_cx32"); hd = cases.head_case()
+  ns, h, w, cx = 5, 6, 5, 32
+  rng = np.random.default_rng(9)
+  hh = np.tanh(rng.standard_normal((ns, h, w, 256))).astype(np.float32)
+  c = rng.standard_normal((ns, h, w, 256)).astype(np.float32)
+  ids = np.array([0, w - 1, (h - 1) * w, h * w - 1, 2 * w + 2], dtype=np.int32)
+  We, be = hd["We1"], hd["be"]
+  oh = R.one_hot(ids, h * w, np.float64).reshape(ns, h, w, 1)
+  x = R.grid_emb(oh, We.astype(np.float64), be.astype(np.float64))
+  c_ref, h_ref = R.convlstm_cell(x, c.astype(np.float64), hh.astype(np.float64), d["kernel"].astype(np.float64),
+                                 d["biases"].astype(np.float64))
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), 2)
+  xf = ops.XFold(T(d["kernel"], dev), T(d["biases"], dev), T(We, dev), T(be, dev))
+  xh = ops.alloc_xh(ns, h, w, pk.cpad, 2, dev)
+  xh[:, :, :32] = 7.0                                   # the x block must never be read
+  xh.view(2, ns, h + 1, w + 1, -1)[:, :, h] = 0; xh.view(2, ns, h + 1, w + 1, -1)[:, :, :, w] = 0
+  ops.nhwc_to_planes(T(hh, dev), xh, pk.cxp, h, w)
+  c_in = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(c, dev), c_in, h, w)
+  c_out = ops.alloc_state(ns, h, w, dev); h_out = ops.alloc_state(ns, h, w, dev)
+  ops.cell_fwd_onehot(xh, pk, xf, T(ids, dev), c_in, c_out, h_out, None, h, w, ns)
+  co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
+  ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
+  assert rel(co.cpu().numpy(), c_ref) < TIGHT and rel(ho.cpu().numpy(), h_ref) < TIGHT
