@@ -117,13 +117,18 @@ int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
                    int H, int W, int cpad, int64_t Rp, int planes, void* stream);
 /* Same result without the transposed copies: both operands are read MN-major straight from the
- * row-major planes (dG [P][NS*S][1024], xh [P][NS*S][cpad]); the tap is a row shift of the TMA box. */
+ * row-major planes (dG [P][NS*S][1024], xh [P][NS*S][cpad]); the tap is a row shift of the TMA box.
+ * dw_packed: fp32 [mvb_cell_wgrad_slabs(cpad)][1024][9*cpad], accumulated (+=). */
 int mvb_cell_wgrad_direct(const void* dg_planes, const void* xh_planes, float* dw_packed, int64_t NS,
                           int H, int W, int cpad, int planes, void* stream);
 /* packed accumulators -> gradients of the TF variables kernel [3,3,cx+256,1024], biases [1024]
  * (accumulate != 0: +=). */
 int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
-                          float* dbiases, int cx, int comp, int accumulate, void* stream);
+                          float* dbiases, int cx, int comp, int accumulate, int slabs, void* stream);
+/* Number of fp32 slabs [1024][9*cpad] mvb_cell_wgrad_direct accumulates into (its K split: every
+ * (tile, k-split) work item owns one slab region, so no atomics); dw_packed must hold that many,
+ * zero-initialised, and mvb_unpack_cell_wgrad sums them (slabs = 1 for mvb_cell_wgrad). */
+int mvb_cell_wgrad_slabs(int cpad);
 
 /* ---- a12: loss (Model.build_loss, pred_models.py:961-1040) --------------------------------
  * loss_out[0] += cls_weight * mean_rows CE(logits[rows,V], labels);  dlogits = its gradient.

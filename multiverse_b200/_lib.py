@@ -34,7 +34,8 @@ SIGNATURES = {
     "mvb_cell_dgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_cell_wgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i64, _i, _vp],
     "mvb_cell_wgrad_direct": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
-    "mvb_unpack_cell_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mvb_unpack_cell_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mvb_cell_wgrad_slabs": [_i],
     "mvb_loss_fwd_bwd": [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _i64, _f, _vp, _vp],
     "mvb_head_bwd": [_vp, _vp, _vp, _i, _vp, _vp, _i, _i64, _i, _i, _vp],
     "mvb_emb_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp],

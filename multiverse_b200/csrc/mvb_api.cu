@@ -169,9 +169,11 @@ int mvb_cell_wgrad_direct(const void* dg_planes, const void* xh_planes, float* d
   return cell_wgrad_mn(dg_planes, xh_planes, dw_packed, NS, H, W, cpad, planes, S(stream));
 }
 int mvb_unpack_cell_wgrad(const float* dw_packed, const float* dbias_packed, float* dkernel,
-                          float* dbiases, int cx, int comp, int accumulate, void* stream) {
-  return unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp, accumulate, S(stream));
+                          float* dbiases, int cx, int comp, int accumulate, int slabs, void* stream) {
+  return unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp, accumulate, slabs,
+                           S(stream));
 }
+int mvb_cell_wgrad_slabs(int cpad) { return cell_wgrad_mn_slabs(cpad); }
 
 int mvb_loss_fwd_bwd(const float* logits, const int32_t* labels, float* dlogits, int64_t rows, int V,
                      float cls_weight, const float* reg, const float* target, float* dreg,

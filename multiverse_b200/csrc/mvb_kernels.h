@@ -71,7 +71,8 @@ int transpose_planes(const void* src, void* dst, long long R, int C, long long R
                      int Wp, cudaStream_t stream);
 int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P, cudaStream_t stream);
 int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases,
-                      int cx, int comp, int accumulate, cudaStream_t stream);
+                      int cx, int comp, int accumulate, int slabs, cudaStream_t stream);
+int cell_wgrad_mn_slabs(int cpad);
 
 // mvb_train2.cu
 int loss_fwd_bwd(const float* logits, const int* labels, float* dlogits, long long rows, int V,

@@ -22,11 +22,11 @@ namespace mvb {
 constexpr int G_BLOCK_M = 128;
 constexpr int G_BLOCK_K = 32;
 constexpr int G_UMMA_K = 16;
-constexpr int G_MAX_BN = 160;
+constexpr int G_MAX_BN = 192;
 constexpr int G_EPI_WARPS = 4;
 constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;
 constexpr int G_A_PLANE = G_BLOCK_M * G_BLOCK_K * 2;   // 8 KB
-constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 10 KB (BN = 144 uses 9 KB of it)
+constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 12 KB (smaller N tiles use part of it)
 constexpr uint32_t G_SW64_LAYOUT = 4;
 constexpr uint32_t G_SW64_SBO = 512;
 
@@ -47,9 +47,11 @@ struct GemmParams {
   long long num_m_tiles;
   int num_n_tiles;
   // MODE_WGRAD_MN: operands are read MN-major straight from the row-major activations
-  int nb;              // 32-channel blocks per N tile (bn = 32*nb)
-  int n_per_tap;       // N tiles per tap (cpad / bn)
-  int ksplit;          // K (= halo rows) is split over this many work items
+  int ubn, nb;         // channels / 32-channel blocks of one (tap, chunk) unit
+  int n_per_tap;       // units per tap (cpad / ubn)
+  int upt;             // units per N tile (bn = upt * ubn): two 96-wide units are paired into N = 192
+  int n_units;         // 9 * n_per_tap
+  int ksplit;          // K (= halo rows) is split over this many work items, each with its own fp32 slab
   uint32_t lbo, sbo;   // UMMA descriptor strides of the MN-major SWIZZLE_64B tiles
 };
 
@@ -110,13 +112,20 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_3d(sa, &tmA, &full_bar[stage], kb * G_BLOCK_K, (int)(mt * G_BLOCK_M), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K, tap * prm.cpad + half * prm.bn, 0);
         } else {
-          // MN-major: A = dG[32 halo rows (K), 4 blocks of 32 gate columns], B = xh[32 halo rows + shift(tap),
-          // nb blocks of 32 channels]; ntile = (tap, n-in-tap, k-split)
-          const int ks = ntile % prm.ksplit, nn = (ntile / prm.ksplit) % prm.n_per_tap, tap = ntile / (prm.ksplit * prm.n_per_tap);
-          const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+          // MN-major: A = dG[32 halo rows (K), 4 blocks of 32 gate columns]; B = `upt` units, each
+          // xh[32 halo rows + shift(tap), nb blocks of 32 channels]; ntile = (unit group, k-split)
+          const int ks = ntile % prm.ksplit, grp = ntile / prm.ksplit;
           const int k0 = (ks * prm.num_kb + kb) * G_BLOCK_K;
           tma_load_4d(sa, &tmA, &full_bar[stage], 0, k0, (int)mt * 4, 0);
-          tma_load_4d(sb, &tmB, &full_bar[stage], 0, k0 + shift, nn * prm.nb, 0);
+          for (int j = 0; j < prm.upt; ++j) {
+            int u = grp * prm.upt + j;
+            if (u >= prm.n_units) u = prm.n_units - 1;     // odd tail: duplicate, discarded by the epilogue
+            const int tap = u / prm.n_per_tap, chunk = u - tap * prm.n_per_tap;
+            const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
+            for (int p = 0; p < P; ++p)
+              tma_load_4d(sb + p * (prm.bn * 64) + j * (prm.ubn * 64), &tmB, &full_bar[stage], 0, k0 + shift,
+                          chunk * prm.nb, p);
+          }
         }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
@@ -189,8 +198,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + half * prm.bn;
       } else {
         valid = row < kGates;
-        const int nn = (ntile / prm.ksplit) % prm.n_per_tap, tap = ntile / (prm.ksplit * prm.n_per_tap);
-        dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + nn * prm.bn;
+        dst = prm.out + (long long)(ntile % prm.ksplit) * kGates * 9LL * prm.cpad + row * (9LL * prm.cpad);
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -199,18 +207,22 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+        bool ok = valid;
+        float4* d4 = reinterpret_cast<float4*>(dst + c0);
+        if (MODE == MODE_WGRAD_MN) {
+          // column c0 of the tile -> (unit, channel): dW[tap][chunk*ubn + c]; this (tile, k-split) owns its slab
+          const int j = c0 / prm.ubn;
+          const int u = (ntile / prm.ksplit) * prm.upt + j;
+          ok = valid && u < prm.n_units;
+          const int tap = u / prm.n_per_tap, chunk = u - tap * prm.n_per_tap;
+          d4 = reinterpret_cast<float4*>(dst + tap * prm.cpad + chunk * prm.ubn + (c0 - j * prm.ubn));
+        }
+        if (ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-            if (MODE == MODE_WGRAD_MN) {   // several K splits add into the same tile
-              float* da = reinterpret_cast<float*>(d4 + q);
-              atomicAdd(da, o.x); atomicAdd(da + 1, o.y); atomicAdd(da + 2, o.z); atomicAdd(da + 3, o.w);
-              continue;
-            }
-            if (MODE == MODE_WGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            if (MODE != MODE_DGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
             d4[q] = o;
           }
         }
@@ -378,7 +390,7 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ kernel, __nv_bfloat1
 // dWp [1024][9*cpad] fp32 (packed) -> dkernel [3,3,cx+256,1024] (TF layout), dbias packed -> TF order
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const float* __restrict__ dbp,
                                     float* __restrict__ dkernel, float* __restrict__ dbiases, int cx,
-                                    int cxp, int cpad, int comp, int accumulate) {
+                                    int cxp, int cpad, int comp, int accumulate, int slabs) {
   const int cin_tot = cx + kHidden;
   const long long total = 9LL * cin_tot * kGates;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -389,8 +401,12 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const float* 
     const int gate = col / kHidden, ch = col % kHidden;
     const int n = (ch / 64) * 256 + gate * 64 + (ch % 64);
     const int kc = cin < cx ? cin : cxp + (cin - cx);
-    float v = dwp[(long long)n * (9LL * cpad) + tap * cpad + kc];
-    if (comp && cin < cx) v += dwp[(long long)n * (9LL * cpad) + tap * cpad + cx + cin];   // + residual block
+    float v = 0.f;
+    for (int sl = 0; sl < slabs; ++sl) {
+      const float* d = dwp + (long long)sl * kGates * 9LL * cpad + (long long)n * (9LL * cpad) + tap * cpad;
+      v += d[kc];
+      if (comp && cin < cx) v += d[cx + cin];   // + residual block of the compensated x block
+    }
     dkernel[i] = accumulate ? dkernel[i] + v : v;
     if (tap == 0 && cin == 0) dbiases[col] = accumulate ? dbiases[col] + dbp[n] : dbp[n];
   }
@@ -474,6 +490,8 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
   }
 }
 
+int cell_wgrad_mn_slabs(int cpad) { return cpad == 288 ? 5 : 1; }
+
 int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long long NS, int H, int W,
                   int cpad, int P, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "cell_wgrad_mn: planes P=%d", P);
@@ -481,7 +499,11 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   MVB_REQUIRE(cpad == 288 || cpad == 320, "cell_wgrad_mn: cpad=%d unsupported", cpad);
   const Grid g = make_grid(H, W);
   const long long R = NS * g.S;
-  const int bn = cpad == 288 ? 96 : 160;
+  GemmParams prm;
+  prm.ubn = cpad == 288 ? 96 : 160;
+  prm.upt = cpad == 288 ? 2 : 1;          // pair two 96-wide units: N = 192 keeps the MMA off the smem-bandwidth limit
+  prm.bn = prm.ubn * prm.upt;
+  prm.nb = prm.ubn / 32; prm.n_per_tap = cpad / prm.ubn; prm.n_units = 9 * prm.n_per_tap;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {32, (uint64_t)R, kGates / 32, (uint64_t)P};
@@ -493,18 +515,18 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   {
     const uint64_t dims[4] = {32, (uint64_t)R, (uint64_t)cpad / 32, (uint64_t)P};
     const uint64_t st[3] = {(uint64_t)cpad * 2, 64, (uint64_t)R * cpad * 2};
-    const uint32_t box[4] = {32, G_BLOCK_K, (uint32_t)(bn / 32), (uint32_t)P};
+    const uint32_t box[4] = {32, G_BLOCK_K, (uint32_t)prm.nb, 1};
     int rc = encode_tmap_4d_bf16(&tmB, xh_planes, dims, st, box, 64);
     if (rc) return rc;
   }
-  GemmParams prm;
-  prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = bn;
-  prm.nb = bn / 32; prm.n_per_tap = cpad / bn;
+  prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad;
   const long long kb_total = (R + G_BLOCK_K - 1) / G_BLOCK_K;
-  prm.ksplit = kb_total >= 64 ? 2 : 1;
+  // work items = 8 M tiles x unit groups x k-splits, sized to fill whole waves of 148 CTAs:
+  // cpad 288: 8 x 14 x 5 = 560 (3.8 waves); cpad 320: 8 x 18 x 1 = 144
+  prm.ksplit = cell_wgrad_mn_slabs(cpad);
   prm.num_kb = (int)((kb_total + prm.ksplit - 1) / prm.ksplit);
   prm.num_m_tiles = kGates / G_BLOCK_M;
-  prm.num_n_tiles = 9 * prm.n_per_tap * prm.ksplit;
+  prm.num_n_tiles = ((prm.n_units + prm.upt - 1) / prm.upt) * prm.ksplit;
   prm.lbo = 32 * 64;   // bytes between 32-wide MN blocks ([32 K rows][64 B] each)
   prm.sbo = 8 * 64;    // bytes between groups of 8 K rows
   int sms = 0;
@@ -562,10 +584,11 @@ int pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int P,
 }
 
 int unpack_cell_wgrad(const float* dwp, const float* dbias_packed, float* dkernel, float* dbiases, int cx,
-                      int comp, int accumulate, cudaStream_t stream) {
+                      int comp, int accumulate, int slabs, cudaStream_t stream) {
   MVB_REQUIRE(dwp && dbias_packed && dkernel && dbiases && cx >= 1, "unpack_cell_wgrad: bad args");
   const int cxp = (cx + 31) / 32 * 32, cpad = cxp + kHidden;
-  unpack_wgrad_kernel<<<1184, 256, 0, stream>>>(dwp, dbias_packed, dkernel, dbiases, cx, cxp, cpad, comp, accumulate);
+  MVB_REQUIRE(slabs >= 1, "unpack_cell_wgrad: slabs=%d", slabs);
+  unpack_wgrad_kernel<<<1184, 256, 0, stream>>>(dwp, dbias_packed, dkernel, dbiases, cx, cxp, cpad, comp, accumulate, slabs);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;

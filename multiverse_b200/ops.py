@@ -252,9 +252,14 @@ def cell_wgrad_direct(dg_planes, xh, dw_packed, h, w, ns):
             xh.shape[0], _stream())
 
 
+def wgrad_slabs(cpad):
+  return int(_lib.load().mvb_cell_wgrad_slabs(cpad))
+
+
 def unpack_cell_wgrad(dw_packed, dbias_packed, dkernel, dbiases, cx, comp=False, accumulate=False):
+  slabs = dw_packed.shape[0] if dw_packed.dim() == 3 else 1
   _lib.call("mvb_unpack_cell_wgrad", _p(dw_packed), _p(dbias_packed), _p(dkernel), _p(dbiases), cx,
-            int(comp), int(accumulate), _stream())
+            int(comp), int(accumulate), slabs, _stream())
 
 
 def loss_fwd_bwd(logits, labels, dlogits, cls_weight, reg, target, dreg, reg_weight, loss_out):

@@ -24,7 +24,8 @@ class _CellGrad(object):
   """Packed fp32 accumulators of one ConvLSTM cell's weight gradient."""
 
   def __init__(self, packed, dev):
-    self.dwp = torch.zeros((4 * HID, 9 * packed.cpad), dtype=torch.float32, device=dev)
+    self.dwp = torch.zeros((ops.wgrad_slabs(packed.cpad), 4 * HID, 9 * packed.cpad), dtype=torch.float32,
+                           device=dev)
     self.dbp = torch.zeros((4 * HID,), dtype=torch.float32, device=dev)
 
   def zero(self):

@@ -175,3 +175,62 @@ def test_reference_test_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, ca
   assert "total test samples:6" in text and "grid0_traj_ade" in text
   assert len(calls) == 2                                  # ceil(6 / 4) batches
   assert calls[0][[k for k in calls[0] if getattr(k, "name", "") == "scene_feat"][0]].shape[1:] == (72, 36, 11)
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not mounted")
+def test_reference_train_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, capsys):
+  """code/train.py (byte-identical): argparse -> process_args -> read_data -> get_model -> Trainer /
+  Tester -> the training loop with periodic save + evaluate, on our surface; the device work
+  (Model._train_step / _engine_forward) is stubbed because this container has no GPU."""
+  tf, pm = dropin
+  from multiverse_b200 import synthetic
+  import multiverse_b200.pred_models as impl
+  monkeypatch.syspath_prepend(REF)
+  cfg = synthetic.make_config(batch_size=4, use_grids=[True, False])
+  prepro = tmp_path / "prepro"; prepro.mkdir()
+  synthetic.write_npz(str(prepro / "data_train.npz"), cfg, 10, seed=5)
+  synthetic.write_npz(str(prepro / "data_val.npz"), cfg, 6, seed=6)
+  argv = ["train.py", str(prepro), str(tmp_path / "out"), "modelname", "--runId", "0", "--use_scene_enc", "--use_gnn",
+          "--scene_h", "72", "--scene_w", "36", "--scene_grid_strides", "2,4", "--use_grids", "1,0",
+          "--batch_size", "4", "--emb_size", "32", "--scene_conv_dim", "64", "--scene_class", "11",
+          "--activation_func", "tanh", "--obs_len", "8", "--pred_len", "12", "--train_w_onehot", "--wd", "0.001",
+          "--num_epochs", "2", "--save_period", "3", "--init_lr", "0.3", "--grid_reg_loss_weight", "0.2",
+          "--val_grid_num", "0"]
+  monkeypatch.setattr(sys, "argv", argv)
+  spec = importlib.util.spec_from_file_location("ref_train", os.path.join(REF, "train.py"))
+  ref_train = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(ref_train)
+  import pred_utils
+  args = ref_train.parser.parse_args()
+  args.is_train = True
+  args.is_test = False
+  args = pred_utils.process_args(args)
+  steps = []
+
+  def fake_train_step(self, feed, apply=True):
+    steps.append(int(self.global_step.value))
+    self.global_step.value = np.asarray(int(self.global_step.value) + 1, dtype="int32")
+    lr = self.learning_rate(steps[-1])
+    assert abs(lr - 0.3 * 0.95 ** (steps[-1] // int(10 / 4 * 2.0))) < 1e-12      # staircase decay, :1656-1665
+    return dict(loss=np.float32(1.0 / (1 + len(steps))), wd_loss=np.float32(0.1), train_op=None,
+                classification_loss={0: np.float32(0.5)}, regression_loss={0: np.float32(0.4)})
+
+  def fake_forward(self, feed):
+    import torch
+    n, tp = self.N, self.config.pred_len
+    out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
+    for i, (h, w) in enumerate(self.config.scene_grids):
+      ok = self.config.use_grids[i]
+      out["grid_pred_decoded"].append(torch.zeros(n, tp, h, w, 1) if ok else [])
+      out["grid_pred_reg_decoded"].append(torch.zeros(n, tp, h, w, 2) if ok else [])
+    return out
+
+  monkeypatch.setattr(impl.Model, "_train_step", fake_train_step)
+  monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
+  ref_train.main(args)
+  text = capsys.readouterr().out
+  assert steps == list(range(6))                       # ceil(10/4) * 2 epochs
+  assert "best eval on val grid0_traj_ade" in text
+  ck = tf.train.get_checkpoint_state(args.save_dir)
+  assert ck is not None and os.path.exists(ck.model_checkpoint_path + ".npz")
+  assert tf.train.get_checkpoint_state(args.save_dir_best) is not None

@@ -83,9 +83,12 @@ def test_cell_backward_matches_autograd(dev, name):
   assert rel(0.5 * dk.cpu().numpy(), t["kernel"].grad.numpy()) < GTOL
   assert rel(db.cpu().numpy(), t["biases"].grad.numpy()) < GTOL
   # the production path: MN-major operands straight from the row-major planes (no transposes)
-  dwp2 = torch.zeros_like(dwp)
+  dwp2 = torch.zeros((ops.wgrad_slabs(pk.cpad), 1024, 9 * pk.cpad), device=dev)
   ops.cell_wgrad_direct(dg, xh, dwp2, h, w, ns)
-  assert rel(dwp2.cpu().numpy(), 0.5 * dwp.cpu().numpy()) < 1e-6
+  assert rel(dwp2.sum(0).cpu().numpy(), 0.5 * dwp.cpu().numpy()) < 1e-5
+  dk2 = torch.empty_like(dk); db2 = torch.empty_like(db)
+  ops.unpack_cell_wgrad(dwp2, dbp, dk2, db2, cx, comp=pk.comp)
+  assert rel(dk2.cpu().numpy(), t["kernel"].grad.numpy()) < GTOL
 
 
 def test_loss_kernel(dev):
