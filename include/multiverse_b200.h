@@ -109,9 +109,10 @@ int mvb_transpose_planes(const void* src, void* dst, int64_t R, int C, int64_t R
 /* TF kernel [3,3,cx+256,1024] -> dgrad operand planes bf16 [P][cpad][9*1024]. */
 int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, int planes,
                                 void* stream);
-/* dxh fp32 [NS*S, cpad] = conv3x3^T(dG, W): gradient w.r.t. concat([x, h]) of the step. */
+/* dxh fp32 [NS*S, cpad] = conv3x3^T(dG, W): gradient w.r.t. concat([x, h]) of the step; the h block
+ * (columns [cpad-256, cpad)) always, the x block only if need_dx (the regression encoder's input is data). */
 int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int64_t NS, int H,
-                   int W, int cpad, int planes, void* stream);
+                   int W, int cpad, int planes, int need_dx, void* stream);
 /* dw_packed fp32 [1024][9*cpad] += dG^T x im2col(xh): weight gradient of the step.  dgT_planes
  * [P][1024][Rp] and xhT_planes [P][9][cpad][Rp] come from mvb_transpose_planes (taps 1 / 9). */
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,

@@ -31,7 +31,7 @@ SIGNATURES = {
     "mvb_lstm_gates_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_transpose_planes": [_vp, _vp, _i64, _i, _i64, _i, _i, _i, _vp],
     "mvb_pack_cell_weights_dgrad": [_vp, _vp, _i, _i, _vp],
-    "mvb_cell_dgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "mvb_cell_dgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "mvb_cell_wgrad": [_vp, _vp, _vp, _i64, _i, _i, _i, _i64, _i, _vp],
     "mvb_cell_wgrad_direct": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_unpack_cell_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -157,8 +157,8 @@ int mvb_pack_cell_weights_dgrad(const float* kernel, void* wd_planes, int cx, in
   return pack_cell_weights_dgrad(kernel, wd_planes, cx, planes, S(stream));
 }
 int mvb_cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, int64_t NS, int H,
-                   int W, int cpad, int planes, void* stream) {
-  return cell_dgrad(dg_planes, wd_planes, dxh, NS, H, W, cpad, planes, S(stream));
+                   int W, int cpad, int planes, int need_dx, void* stream) {
+  return cell_dgrad(dg_planes, wd_planes, dxh, NS, H, W, cpad, planes, need_dx, S(stream));
 }
 int mvb_cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dw_packed, int64_t NS,
                    int H, int W, int cpad, int64_t Rp, int planes, void* stream) {

@@ -59,7 +59,7 @@ int beam_backtrace(const int* step_ids, const int* step_parents, const float* st
 
 // mvb_train.cu
 int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long long NS, int H, int W,
-               int cpad, int P, cudaStream_t stream);
+               int cpad, int P, int need_x, cudaStream_t stream);
 int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long long NS, int H, int W,
                int cpad, long long Rp, int P, cudaStream_t stream);
 int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long long NS, int H, int W,

@@ -11,7 +11,10 @@
 //                    transposes of the activations; 8 x 18 output tiles = one wave of CTAs,
 //                    each looping over all R rows (K) and adding into the fp32 dW accumulator
 // Both GEMMs use the forward kernel's operand-plane scheme (P bf16 planes, products i+j<P) and
-// the same TMA / mbarrier / TMEM pipeline; the tile is 128 x (cpad/2) (144 or 160 columns).
+// the same TMA / mbarrier / TMEM pipeline.  Measured on B200: the tensor pipe processes N in
+// granules of 64 (N = 144 and N = 160 both cost what N = 192 costs), so dgrad tiles are the h block
+// (N = 256) plus, only where the caller needs it, the x block (N = 32 / 64); a cta_group::2 variant
+// was built and measured too and gave no gain (the 1-CTA kernel is not smem-bandwidth bound).
 // Algorithmic FLOPs: dgrad = wgrad = forward (2*R*9*cpad*1024 each).
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
@@ -22,11 +25,11 @@ namespace mvb {
 constexpr int G_BLOCK_M = 128;
 constexpr int G_BLOCK_K = 32;
 constexpr int G_UMMA_K = 16;
-constexpr int G_MAX_BN = 192;
+constexpr int G_MAX_BN = 256;
 constexpr int G_EPI_WARPS = 4;
 constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;
 constexpr int G_A_PLANE = G_BLOCK_M * G_BLOCK_K * 2;   // 8 KB
-constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 12 KB (smaller N tiles use part of it)
+constexpr int G_B_PLANE = G_MAX_BN * G_BLOCK_K * 2;    // 16 KB (smaller N tiles use part of it)
 constexpr uint32_t G_SW64_LAYOUT = 4;
 constexpr uint32_t G_SW64_SBO = 512;
 
@@ -34,7 +37,7 @@ enum { MODE_DGRAD = 0, MODE_WGRAD = 1, MODE_WGRAD_MN = 2 };
 
 template <int P> struct GemmCfg {
   static constexpr int STAGE_BYTES = P * (G_A_PLANE + G_B_PLANE);
-  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 5 : 3;
+  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 4 : 3;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -42,7 +45,9 @@ struct GemmParams {
   float* out;          // dgrad: [R, cpad] fp32;  wgrad: [1024, 9*cpad] fp32 accumulator (+=)
   long long R;         // halo rows
   int H, W;
-  int cpad, bn;        // bn = cpad / 2
+  int cpad, bn;        // N tile of the wgrad modes
+  int cxp;             // dgrad: width of the x block; its N tiles are [cxp, cxp+256) (h) and [0, cxp) (x)
+  int need_x;          // dgrad: also produce the x block columns
   int num_kb;          // k-blocks per tile
   long long num_m_tiles;
   int num_n_tiles;
@@ -58,7 +63,7 @@ struct GemmParams {
 template <int P, int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const GemmParams prm) {
+             const __grid_constant__ CUtensorMap tmBx, const GemmParams prm) {
   using Cfg = GemmCfg<P>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -72,10 +77,13 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Grid g = make_grid(prm.H, prm.W);
   const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;
-  const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + prm.bn * G_BLOCK_K * 2);
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(prm.bn >> 3) << 17) |
-                         ((uint32_t)(G_BLOCK_M >> 4) << 24) |
-                         (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
+  // dgrad: tiles [0, num_m_tiles) are the h part (N = 256 - the tensor pipe works in N granules of 64,
+  // so 256 + cxp costs less than two tiles of cpad/2 = 144), tiles beyond are the x part (N = cxp)
+  auto tile_bn = [&](long long t) -> int { return MODE == MODE_DGRAD ? (t < prm.num_m_tiles ? 256 : prm.cxp) : prm.bn; };
+  auto make_idesc = [&](int bn) -> uint32_t {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(G_BLOCK_M >> 4) << 24) |
+           (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
+  };
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
   if (warp == 1 && lane == 0) {
@@ -93,19 +101,22 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const long long mt = t / prm.num_n_tiles;
-      const int ntile = (int)(t % prm.num_n_tiles);
+      const bool xpart = MODE == MODE_DGRAD && t >= prm.num_m_tiles;
+      const long long mt = MODE == MODE_DGRAD ? (xpart ? t - prm.num_m_tiles : t) : t / prm.num_n_tiles;
+      const int ntile = MODE == MODE_DGRAD ? 0 : (int)(t % prm.num_n_tiles);
+      const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + tile_bn(t) * G_BLOCK_K * 2);
       for (int kb = 0; kb < prm.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + P * G_A_PLANE;
         mbar_expect_tx(&full_bar[stage], stage_tx);
         if (MODE == MODE_DGRAD) {
-          // A = dG[rows - shift(tap), 32 gate columns];  B = Wd[bn channels, tap*1024 + 32 gate columns]
+          // A = dG[rows - shift(tap), 32 gate columns];  B = Wd[N channels, tap*1024 + 32 gate columns]
           const int q = kb / 9, tap = kb - q * 9;
           const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
           tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
-          tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, ntile * prm.bn, 0);
+          if (xpart) tma_load_3d(sb, &tmBx, &full_bar[stage], tap * kGates + q * G_BLOCK_K, 0, 0);
+          else tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, prm.cxp, 0);
         } else if (MODE == MODE_WGRAD) {
           // A = dG^T[128 gate rows, 32 halo rows];  B = tap-shifted xh^T[tap][bn channels, 32 halo rows]
           const int tap = ntile >> 1, half = ntile & 1;
@@ -140,12 +151,14 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * 256;
+      const int bn_t = tile_bn(t);
+      const uint32_t idesc = make_idesc(bn_t);
       for (int kb = 0; kb < prm.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + P * G_A_PLANE;
-        const uint32_t b_plane = (uint32_t)prm.bn * G_BLOCK_K * 2;   // TMA packs planes back to back
+        const uint32_t b_plane = (uint32_t)bn_t * G_BLOCK_K * 2;   // TMA packs planes back to back
         uint32_t first = (kb == 0) ? 0u : 1u;
 #pragma unroll
         for (int pa = 0; pa < P; ++pa) {
@@ -179,8 +192,10 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      const long long mt = t / prm.num_n_tiles;
-      const int ntile = (int)(t % prm.num_n_tiles);
+      const bool xpart = MODE == MODE_DGRAD && t >= prm.num_m_tiles;
+      const long long mt = MODE == MODE_DGRAD ? (xpart ? t - prm.num_m_tiles : t) : t / prm.num_n_tiles;
+      const int ntile = MODE == MODE_DGRAD ? 0 : (int)(t % prm.num_n_tiles);
+      const int bn_t = tile_bn(t);
       const long long row = mt * G_BLOCK_M + wq * 32 + lane;
       bool valid;
       float* dst;
@@ -191,7 +206,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int y = rem / g.Wp, x = rem - y * g.Wp;
           valid = (x < g.W) && (y < g.H);
         }
-        dst = prm.out + row * prm.cpad + ntile * prm.bn;
+        dst = prm.out + row * prm.cpad + (xpart ? 0 : prm.cxp);
       } else if (MODE == MODE_WGRAD) {
         valid = row < kGates;
         const int tap = ntile >> 1, half = ntile & 1;
@@ -203,7 +218,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256;
-      for (int c0 = 0; c0 < prm.bn; c0 += 16) {
+      for (int c0 = 0; c0 < bn_t; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
@@ -413,8 +428,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const float* 
 }
 
 template <int P, int MODE>
-static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm,
-                        int num_sms, cudaStream_t stream) {
+static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBx,
+                        const GemmParams& prm, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<P>;
   static bool configured = false;
   if (!configured) {
@@ -423,7 +438,7 @@ static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   }
   const long long tiles = prm.num_m_tiles * prm.num_n_tiles;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  pgemm_kernel<P, MODE><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  pgemm_kernel<P, MODE><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmBx, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;
@@ -437,29 +452,32 @@ static int num_sms_of_device(int* out) {
 }
 
 int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long long NS, int H, int W,
-               int cpad, int P, cudaStream_t stream) {
+               int cpad, int P, int need_x, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "cell_dgrad: planes P=%d", P);
   MVB_REQUIRE(dg_planes && wd_planes && dxh && NS > 0, "cell_dgrad: bad args");
-  MVB_REQUIRE(cpad % 32 == 0 && (cpad / 2) % 16 == 0 && cpad / 2 <= G_MAX_BN, "cell_dgrad: cpad=%d unsupported", cpad);
+  const int cxp = cpad - kHidden;
+  MVB_REQUIRE(cpad % 32 == 0 && cxp >= 32 && cxp <= 256 && cxp % 16 == 0, "cell_dgrad: cpad=%d unsupported", cpad);
   const Grid g = make_grid(H, W);
   const long long R = NS * g.S;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBx;
   int rc = encode_tmap_3d_bf16(&tmA, dg_planes, kGates, (uint64_t)R, P, kGates * 2ull, (uint64_t)R * kGates * 2,
                                G_BLOCK_K, G_BLOCK_M, P, 64);
   if (rc) return rc;
   const uint64_t ktot = 9ull * kGates;
-  rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K,
-                           cpad / 2, P, 64);
+  rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, 256, P, 64);
   if (rc) return rc;
-  GemmParams prm;
-  prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = cpad / 2;
-  prm.num_kb = 9 * (kGates / G_BLOCK_K); prm.num_m_tiles = (R + G_BLOCK_M - 1) / G_BLOCK_M; prm.num_n_tiles = 2;
+  rc = encode_tmap_3d_bf16(&tmBx, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, cxp, P, 64);
+  if (rc) return rc;
+  GemmParams prm = {};
+  prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = 256; prm.cxp = cxp; prm.need_x = need_x;
+  prm.num_kb = 9 * (kGates / G_BLOCK_K); prm.num_m_tiles = (R + G_BLOCK_M - 1) / G_BLOCK_M;
+  prm.num_n_tiles = need_x ? 2 : 1;     // kernel: tiles [0, num_m_tiles) = h part, the rest = x part
   int sms = 0;
   if ((rc = num_sms_of_device(&sms))) return rc;
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_DGRAD>(tmA, tmB, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
   }
 }
 
@@ -478,15 +496,15 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
   rc = encode_tmap_3d_bf16(&tmB, xhT_planes, (uint64_t)R, 9ull * cpad, P, (uint64_t)Rp * 2, (uint64_t)Rp * cpad * 18,
                            G_BLOCK_K, cpad / 2, P, 64);
   if (rc) return rc;
-  GemmParams prm;
+  GemmParams prm = {};
   prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = cpad / 2;
   prm.num_kb = (int)((R + G_BLOCK_K - 1) / G_BLOCK_K); prm.num_m_tiles = kGates / G_BLOCK_M; prm.num_n_tiles = 18;
   int sms = 0;
   if ((rc = num_sms_of_device(&sms))) return rc;
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_WGRAD>(tmA, tmB, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
   }
 }
 
@@ -499,7 +517,7 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   MVB_REQUIRE(cpad == 288 || cpad == 320, "cell_wgrad_mn: cpad=%d unsupported", cpad);
   const Grid g = make_grid(H, W);
   const long long R = NS * g.S;
-  GemmParams prm;
+  GemmParams prm = {};
   prm.ubn = cpad == 288 ? 96 : 160;
   prm.upt = cpad == 288 ? 2 : 1;          // pair two 96-wide units: N = 192 keeps the MMA off the smem-bandwidth limit
   prm.bn = prm.ubn * prm.upt;
@@ -533,9 +551,9 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   int rc = num_sms_of_device(&sms);
   if (rc) return rc;
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_WGRAD_MN>(tmA, tmB, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
   }
 }
 

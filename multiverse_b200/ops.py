@@ -236,9 +236,9 @@ def transpose_planes(src, dst, taps=1, w=0):
   _lib.call("mvb_transpose_planes", _p(src), _p(dst), r, c, dst.shape[-1], p, taps, w, _stream())
 
 
-def cell_dgrad(dg_planes, wd, dxh, h, w, ns):
+def cell_dgrad(dg_planes, wd, dxh, h, w, ns, need_dx=True):
   _lib.call("mvb_cell_dgrad", _p(dg_planes), _p(wd), _p(dxh), ns, h, w, dxh.shape[1],
-            dg_planes.shape[0], _stream())
+            dg_planes.shape[0], int(need_dx), _stream())
 
 
 def cell_wgrad(dgT, xhT, dw_packed, h, w, ns):

@@ -150,7 +150,7 @@ class TrainEngine(ConvRNNEngine):
     return S
 
   # ------------------------------------------------------------------ backward helpers
-  def _cell_bwd(self, S, i, packed, cg, xh, gates, c_prev, c_new, dh, dc, need_dxh=True):
+  def _cell_bwd(self, S, i, packed, cg, xh, gates, c_prev, c_new, dh, dc, need_dxh=True, need_dx=True):
     """One BPTT step of a cell: returns (dxh [R,cpad] fp32 or None, dc_prev)."""
     n, h, w = S["n"], S["h"], S["w"]
     dev, P = self.device, self.planes
@@ -162,7 +162,7 @@ class TrainEngine(ConvRNNEngine):
     dxh = None
     if need_dxh:
       dxh = self._one(("dxh", i, n, packed.cpad), lambda: torch.zeros((R, packed.cpad), device=dev))
-      ops.cell_dgrad(dg, packed.wd, dxh, h, w, n)
+      ops.cell_dgrad(dg, packed.wd, dxh, h, w, n, need_dx=need_dx)
     ops.cell_wgrad_direct(dg, xh, cg.dwp, h, w, n)     # MN-major operands: no transposed copies
     return dxh, out_dc
 
@@ -226,7 +226,8 @@ class TrainEngine(ConvRNNEngine):
     # ---- regression encoder (its input is data: only the h path is propagated)
     for t in range(T - 1, -1, -1):
       dxh, dc = self._cell_bwd(S, i, sw.enc_reg, cgr["enc_reg"], S["xh_er"][t], S["g_er"][t],
-                               None if t == 0 else S["c_er"][t - 1], S["c_er"][t], dh, dc, need_dxh=t > 0)
+                               None if t == 0 else S["c_er"][t - 1], S["c_er"][t], dh, dc, need_dxh=t > 0,
+                               need_dx=False)
       if t > 0:
         dh.copy_(dxh[:, sw.enc_reg.cxp:])
     # ---- packed accumulators -> gradients of the TF variables
