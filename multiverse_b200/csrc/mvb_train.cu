@@ -11,10 +11,10 @@
 //                    transposes of the activations; 8 x 18 output tiles = one wave of CTAs,
 //                    each looping over all R rows (K) and adding into the fp32 dW accumulator
 // Both GEMMs use the forward kernel's operand-plane scheme (P bf16 planes, products i+j<P) and
-// the same TMA / mbarrier / TMEM pipeline.  Measured on B200: the tensor pipe processes N in
-// granules of 64 (N = 144 and N = 160 both cost what N = 192 costs), so dgrad tiles are the h block
-// (N = 256) plus, only where the caller needs it, the x block (N = 32 / 64); a cta_group::2 variant
-// was built and measured too and gave no gain (the 1-CTA kernel is not smem-bandwidth bound).
+// the same TMA / mbarrier / TMEM pipeline.  dgrad tiles: two N tiles of cpad/2 when the x block is
+// needed, one N = 256 tile (h block only) when it is not (regression encoder).  Measured on B200: MMA
+// time is proportional to N (no granule penalty at N = 144); a separate 32-wide x tile is TMA-bound and
+// costs 30 % of an h tile; a cta_group::2 variant gave no gain (the kernel is not smem-bandwidth bound).
 // Algorithmic FLOPs: dgrad = wgrad = forward (2*R*9*cpad*1024 each).
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
@@ -46,8 +46,8 @@ struct GemmParams {
   long long R;         // halo rows
   int H, W;
   int cpad, bn;        // N tile of the wgrad modes
-  int cxp;             // dgrad: width of the x block; its N tiles are [cxp, cxp+256) (h) and [0, cxp) (x)
-  int need_x;          // dgrad: also produce the x block columns
+  int cxp;             // dgrad: width of the x block
+  int need_x;          // dgrad: 1 -> two N tiles of cpad/2 covering [0, cpad); 0 -> one N tile [cxp, cxp+256) (h only)
   int num_kb;          // k-blocks per tile
   long long num_m_tiles;
   int num_n_tiles;
@@ -77,9 +77,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Grid g = make_grid(prm.H, prm.W);
   const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;
-  // dgrad: tiles [0, num_m_tiles) are the h part (N = 256 - the tensor pipe works in N granules of 64,
-  // so 256 + cxp costs less than two tiles of cpad/2 = 144), tiles beyond are the x part (N = cxp)
-  auto tile_bn = [&](long long t) -> int { return MODE == MODE_DGRAD ? (t < prm.num_m_tiles ? 256 : prm.cxp) : prm.bn; };
+  auto tile_bn = [&](long long) -> int { return prm.bn; };
   auto make_idesc = [&](int bn) -> uint32_t {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(G_BLOCK_M >> 4) << 24) |
            (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
@@ -101,9 +99,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const bool xpart = MODE == MODE_DGRAD && t >= prm.num_m_tiles;
-      const long long mt = MODE == MODE_DGRAD ? (xpart ? t - prm.num_m_tiles : t) : t / prm.num_n_tiles;
-      const int ntile = MODE == MODE_DGRAD ? 0 : (int)(t % prm.num_n_tiles);
+      const long long mt = t / prm.num_n_tiles;
+      const int ntile = (int)(t % prm.num_n_tiles);
       const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + tile_bn(t) * G_BLOCK_K * 2);
       for (int kb = 0; kb < prm.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -115,8 +112,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int q = kb / 9, tap = kb - q * 9;
           const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
           tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
-          if (xpart) tma_load_3d(sb, &tmBx, &full_bar[stage], tap * kGates + q * G_BLOCK_K, 0, 0);
-          else tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K, prm.cxp, 0);
+          tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K,
+                      prm.need_x ? ntile * prm.bn : prm.cxp, 0);
         } else if (MODE == MODE_WGRAD) {
           // A = dG^T[128 gate rows, 32 halo rows];  B = tap-shifted xh^T[tap][bn channels, 32 halo rows]
           const int tap = ntile >> 1, half = ntile & 1;
@@ -192,9 +189,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      const bool xpart = MODE == MODE_DGRAD && t >= prm.num_m_tiles;
-      const long long mt = MODE == MODE_DGRAD ? (xpart ? t - prm.num_m_tiles : t) : t / prm.num_n_tiles;
-      const int ntile = MODE == MODE_DGRAD ? 0 : (int)(t % prm.num_n_tiles);
+      const long long mt = t / prm.num_n_tiles;
+      const int ntile = (int)(t % prm.num_n_tiles);
       const int bn_t = tile_bn(t);
       const long long row = mt * G_BLOCK_M + wq * 32 + lane;
       bool valid;
@@ -206,7 +202,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int y = rem / g.Wp, x = rem - y * g.Wp;
           valid = (x < g.W) && (y < g.H);
         }
-        dst = prm.out + row * prm.cpad + (xpart ? 0 : prm.cxp);
+        dst = prm.out + row * prm.cpad + (prm.need_x ? ntile * prm.bn : prm.cxp);
       } else if (MODE == MODE_WGRAD) {
         valid = row < kGates;
         const int tap = ntile >> 1, half = ntile & 1;
@@ -464,14 +460,17 @@ int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long lo
                                G_BLOCK_K, G_BLOCK_M, P, 64);
   if (rc) return rc;
   const uint64_t ktot = 9ull * kGates;
-  rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, 256, P, 64);
+  // with the x block: two N tiles of cpad/2 (144 / 160); h only: one N tile of 256.  (Measured: MMA time is
+  // proportional to N, and a separate 32-wide x tile is TMA-bound and costs 30 % of an h tile.)
+  const int bn = need_x ? cpad / 2 : 256;
+  MVB_REQUIRE(bn % 16 == 0, "cell_dgrad: cpad=%d unsupported", cpad);
+  rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, bn, P, 64);
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&tmBx, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, cxp, P, 64);
-  if (rc) return rc;
+  tmBx = tmB;
   GemmParams prm = {};
-  prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = 256; prm.cxp = cxp; prm.need_x = need_x;
+  prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = bn; prm.cxp = cxp; prm.need_x = need_x;
   prm.num_kb = 9 * (kGates / G_BLOCK_K); prm.num_m_tiles = (R + G_BLOCK_M - 1) / G_BLOCK_M;
-  prm.num_n_tiles = need_x ? 2 : 1;     // kernel: tiles [0, num_m_tiles) = h part, the rest = x part
+  prm.num_n_tiles = need_x ? 2 : 1;
   int sms = 0;
   if ((rc = num_sms_of_device(&sms))) return rc;
   switch (P) {
