@@ -279,7 +279,7 @@ class ConvRNNEngine(object):
                                                            logits=step_logits)
 
   # ------------------------------------------------------------------ whole forward
-  def forward(self, feeds):
+  def forward(self, feeds, pred_len=None):
     """feeds: device tensors
          scene_feat fp32 [F,SH,SW,SC], obs_scene int32 [N,T],
          grid_obs_labels[i] int32 [N,T], grid_obs_regress[i] fp32 [N,T,h,w,2]
@@ -287,7 +287,9 @@ class ConvRNNEngine(object):
     grid_pred_reg_decoded[i] [N,Tp,h,w,2] ([] for unused scales, :170-171) and
     beam_outputs = [logits [N,B,Tp,V], ids [N,B,Tp], logprobs [N,B]] or None (:276)."""
     cfg = self.cfg
-    tp = cfg.pred_len
+    # raw_rnn runs until `time >= pred_length` (code/pred_models.py:347,:520): the rollout length is the
+    # FED pred_length (multifuture_inference.py feeds max_pred_lengths[idx], :311), not config.pred_len
+    tp = int(pred_len) if pred_len else cfg.pred_len
     obs_scene = feeds["obs_scene"].to(torch.int32).contiguous()
     obs_scene_t = obs_scene.t().contiguous()
     n = obs_scene.shape[0]

@@ -301,7 +301,19 @@ class Model(object):
 
   def _engine_forward(self, feed):
     eng = self._ensure_engine()
-    return eng.forward(self._device_feeds(feed))
+    return eng.forward(self._device_feeds(feed), pred_len=self._fed_pred_len(feed))
+
+  def _fed_pred_len(self, feed):
+    """Rollout length = the fed pred_length (raw_rnn's stop condition, :347/:520)."""
+    pl = feed.get(self.pred_length)
+    if pl is None:
+      return self.config.pred_len
+    pl = np.asarray(pl).reshape(-1)
+    if pl.size == 0:
+      return self.config.pred_len
+    if not (pl == pl[0]).all():
+      raise NotImplementedError("per-row pred_length is not implemented (every reference feed uses one value)")
+    return int(pl[0])
 
   def learning_rate(self, step):
     """Trainer's schedule (code/pred_models.py:1645-1665): init_lr, optionally cosine or staircase
@@ -405,9 +417,10 @@ def _engine_config(config):
     raise NotImplementedError("activation %r: the kernels implement tanh (every published config)" % name)
   keys = ("batch_size scene_h scene_w scene_class scene_conv_dim scene_conv_kernel scene_grid_strides "
           "scene_grids use_grids enc_hidden_size dec_hidden_size emb_size convlstm_kernel use_scene_enc "
-          "use_gnn use_beam_search beam_size diverse_beam diverse_gamma fix_num_timestep obs_len "
+          "use_gnn use_beam_search beam_size diverse_beam diverse_gamma fix_num_timestep "
           "pred_len").split()
   d = {k: getattr(config, k) for k in keys}
+  d["obs_len"] = getattr(config, "obs_len", None)    # multifuture_inference.py's Namespace has none (:419-452)
   d["activation_func"] = "tanh"
   for k, default in (("grid_loss_weight", 1.0), ("grid_reg_loss_weight", 0.1), ("wd", 0.0),
                      ("clip_gradient_norm", None), ("is_train", False)):

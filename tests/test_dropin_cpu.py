@@ -234,3 +234,81 @@ def test_reference_train_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, c
   ck = tf.train.get_checkpoint_state(args.save_dir)
   assert ck is not None and os.path.exists(ck.model_checkpoint_path + ".npz")
   assert tf.train.get_checkpoint_state(args.save_dir_best) is not None
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not mounted")
+def test_reference_multifuture_inference_pieces_run_unchanged(dropin, tmp_path, monkeypatch):
+  """code/multifuture_inference.py (byte-identical): its PredictionModelInference subclass of OUR Model,
+  its Namespace config (:419-452), load_model_weights (:275-299) through our Saver, its own
+  get_feed_dict (:304-385) and the fetch list of :462-472 - the device forward is stubbed."""
+  tf, pm = dropin
+  from multiverse_b200 import synthetic
+  import multiverse_b200.pred_models as impl
+  import argparse
+  monkeypatch.syspath_prepend(REF)
+  monkeypatch.setattr(sys, "argv", ["multifuture_inference.py", "a", "b", "c", "d"])
+  spec = importlib.util.spec_from_file_location("ref_mfi", os.path.join(REF, "multifuture_inference.py"))
+  mfi = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mfi)                      # __main__ guard: only definitions run
+  args = mfi.parser.parse_args(["traj", "mf", "model", "out.p", "--num_out", "20", "--diverse_beam",
+                                "--diverse_gamma", "0.01", "--fix_num_timestep", "1", "--use_gnn",
+                                "--use_scene_enc", "--emb_size", "32", "--scene_h", "72", "--scene_w", "36"])
+  mfi.add_grid(args)
+  assert args.scene_grids == [(36, 18), (18, 9)] and args.use_grids == [True, False]
+  args.use_beam_search = True
+  model_config = argparse.Namespace(
+      modelname="model", batch_size=1, beam_size=args.num_out, use_beam_search=args.use_beam_search,
+      diverse_beam=args.diverse_beam, diverse_gamma=args.diverse_gamma, fix_num_timestep=args.fix_num_timestep,
+      use_teacher_forcing=False, is_train=False, scene_h=args.scene_h, scene_w=args.scene_w,
+      scene_class=args.scene_class, use_soft_grid_class=args.use_soft_grid_class,
+      use_single_decoder=args.use_single_decoder, pred_len=12, emb_size=args.emb_size,
+      enc_hidden_size=args.enc_hidden_size, dec_hidden_size=args.dec_hidden_size, activation_func=tf.nn.tanh,
+      scene_conv_kernel=args.scene_conv_kernel, use_scene_enc=args.use_scene_enc,
+      scene_conv_dim=args.scene_conv_dim, convlstm_kernel=args.convlstm_kernel, use_gnn=args.use_gnn,
+      keep_prob=1.0, scene_grid_strides=args.scene_grid_strides, scene_grids=args.scene_grids,
+      use_grids=args.use_grids)
+  # a checkpoint of the same architecture, written through the shim Saver
+  cfg = synthetic.make_config(batch_size=1, use_grids=[True, False])
+  donor_args = types.SimpleNamespace(**vars(cfg)); donor_args.modelname = "donor"
+  donor_args.use_soft_grid_class = False
+  donor = pm.get_model(donor_args, gpuid=0)
+  tf.global_variables_initializer().run()
+  want = {k: v.copy() for k, v in donor.weights().items()}
+  tf.train.Saver().save(tf.Session(), str(tmp_path / "ckpt" / "save"), global_step=7)
+  tf.reset_default_graph()
+
+  with tf.Session() as sess:
+    with tf.device("/gpu:0"):
+      model = mfi.PredictionModelInference(model_config, model_config.modelname)
+    mfi.load_model_weights(str(tmp_path / "ckpt"), sess, top_scope="person_pred")
+    for k, v in model.weights().items():
+      assert np.array_equal(v, want[k]), k
+    # inputs in the layout get_inputs (:158-272) produces, for 2 trajectories with 12 / 17 future steps
+    f = synthetic.make_feeds(cfg, 2, 3)
+    inputs = dict(obs_grid_class=[np.stack([f["grid_obs_labels"][j][i] for j in range(2)]) for i in range(2)],
+                  obs_grid_target=[[f["grid_obs_regress"][j][i] for j in range(2)] for i in range(2)],
+                  obs_scene=[np.full((8, 1), i, dtype="int32") for i in range(2)],
+                  scene_feats=f["scene_feat"], max_pred_lengths=[12, 17])
+    seen = []
+
+    def fake_forward(self, feed):
+      import torch
+      tp = self._fed_pred_len(feed)
+      seen.append(tp)
+      h, w = self.config.scene_grids[0]
+      return dict(grid_pred_decoded=[torch.zeros(1, tp, h, w, 1), []],
+                  grid_pred_reg_decoded=[torch.zeros(1, tp, h, w, 2), []],
+                  beam_outputs=[torch.zeros(1, 20, tp, h * w), torch.zeros(1, 20, tp, dtype=torch.int32),
+                                torch.zeros(1, 20)])
+
+    monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
+    for i in range(2):
+      feed_dict = model.get_feed_dict(inputs, args, i)
+      assert feed_dict[model.scene_feat].shape == (1, 72, 36, 11)
+      output_tensors = [model.grid_pred_decoded[0], model.grid_pred_reg_decoded[0], model.beam_outputs]
+      class_output, reg_output, beam_outputs = sess.run(output_tensors, feed_dict=feed_dict)
+      pred_len = inputs["max_pred_lengths"][i]
+      assert reg_output.reshape([1, pred_len, -1, 2]).shape[2] == 36 * 18      # :479
+      beam_logits, beam_grid_ids, beam_logprobs = beam_outputs
+      assert beam_grid_ids.shape == (1, 20, pred_len) and beam_logits.shape == (1, 20, pred_len, 648)
+    assert seen == [12, 17]          # the rollout length follows the FED pred_length, not config.pred_len

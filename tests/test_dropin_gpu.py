@@ -80,3 +80,35 @@ def test_tester_step_through_session(beam, monkeypatch):
   sw = R.scale_weights(R.cast_tree(w, np.float64), i)
   c_ref, h_ref = R.convlstm_cell(x.astype(np.float64), c.astype(np.float64), hh.astype(np.float64), *sw.dec_class)
   assert rel(c1, c_ref) < 3e-5 and rel(h1, h_ref) < 3e-5
+
+
+def test_rollout_length_follows_fed_pred_length(monkeypatch):
+  """raw_rnn stops at the FED pred_length (code/pred_models.py:347, :520); multifuture_inference.py
+  feeds max_pred_lengths[idx] (:311), which differs from config.pred_len."""
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  import pred_models
+  from multiverse_b200 import synthetic
+  from oracle import multiverse_ref as R
+  tf.reset_default_graph()
+  over = dict(batch_size=1, use_grids=[False, True], use_beam_search=True, beam_size=5, diverse_beam=True,
+              diverse_gamma=0.01, fix_num_timestep=1)
+  cfg = synthetic.make_config(**over)                      # config.pred_len = 12
+  args = types.SimpleNamespace(**vars(cfg)); args.modelname = "m"; args.use_soft_grid_class = False
+  args.use_gt_grid = False
+  w = synthetic.make_weights(cfg, 8); feeds = synthetic.make_feeds(cfg, 1, 8)
+  model = pred_models.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    if v.name.split(":")[0] in w:
+      v.assign(w[v.name.split(":")[0]])
+  fd = model.get_feed_dict(make_batch(cfg, dict(feeds, grid_pred_labels=[np.zeros((1, 12), np.int32)] * 2), 1)[1])
+  fd[model.pred_length] = np.array([15], dtype="int32")
+  with tf.Session() as sess:
+    cls, reg, beam = sess.run([model.grid_pred_decoded[1], model.grid_pred_reg_decoded[1], model.beam_outputs], fd)
+  ref = R.forward(R.default_config(pred_len=15, **over), w, feeds, np.float64)
+  assert cls.shape == (1, 15, 18, 9, 1) and reg.shape == (1, 15, 18, 9, 2) and beam[1].shape == (1, 5, 15)
+  assert np.array_equal(beam[1], ref["beam_outputs"][1])
+  assert float(np.abs(reg - ref["grid_pred_reg_decoded"][1]).max() / np.abs(ref["grid_pred_reg_decoded"][1]).max()) < 1e-4
