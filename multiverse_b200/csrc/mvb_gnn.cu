@@ -84,11 +84,13 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
   const long long srow0 = (s / beam) * (long long)g.H * g.W;
   const bool rok[3] = {y > 0, true, y < g.H - 1};
 
-  GnnCol L, C, R;
-  gnn_load_col(L, h32, scene_mean, hrow0, srow0, -1, g.W, g.Wp, rok, lane, y);   // zeros
-  gnn_load_col(C, h32, scene_mean, hrow0, srow0, 0, g.W, g.Wp, rok, lane, y);
+  // Rotating 3-column register window (no register moves: the loop is unrolled by three and the
+  // roles L/C/R rotate through the three structs).
+  GnnCol W0, W1, W2;
+  gnn_load_col(W0, h32, scene_mean, hrow0, srow0, -1, g.W, g.Wp, rok, lane, y);   // zeros
+  gnn_load_col(W1, h32, scene_mean, hrow0, srow0, 0, g.W, g.Wp, rok, lane, y);
   float d_cl = 0.f;   // dot(centre, left-centre), carried from the previous cell
-  for (int x = 0; x < g.W; ++x) {
+  auto step = [&](const GnnCol& L, const GnnCol& C, GnnCol& R, int x) {
     gnn_load_col(R, h32, scene_mean, hrow0, srow0, x + 1, g.W, g.Wp, rok, lane, y);
     // dots of the centre cell (C,1) with its 8 neighbours; self = squared norm
     float d[9];
@@ -144,8 +146,11 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
       uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
       *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
     }
-    L = C;
-    C = R;
+  };
+  for (int x = 0; x < g.W; x += 3) {
+    step(W0, W1, W2, x);
+    if (x + 1 < g.W) step(W1, W2, W0, x + 1);
+    if (x + 2 < g.W) step(W2, W0, W1, x + 2);
   }
 }
 
