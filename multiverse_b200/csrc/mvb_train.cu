@@ -35,10 +35,15 @@ constexpr uint32_t G_SW64_SBO = 512;
 
 enum { MODE_DGRAD = 0, MODE_WGRAD = 1, MODE_WGRAD_MN = 2 };
 
-template <int P> struct GemmCfg {
-  static constexpr int STAGE_BYTES = P * (G_A_PLANE + G_B_PLANE);
-  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 4 : 3;
+// MT = number of 128-row M sub-tiles of one CTA tile.  MT = 2 halves the B traffic per MMA (the backward GEMMs
+// are L2->smem feed bound at MT = 1: 79 / 69 B/clk/SM against ~60 the forward sustains); its two accumulators
+// fill TMEM's 512 columns, so there is one accumulator stage and the (light) epilogue is not overlapped.
+template <int P, int MT> struct GemmCfg {
+  static constexpr int A_BYTES = MT * P * G_A_PLANE;
+  static constexpr int STAGE_BYTES = A_BYTES + P * G_B_PLANE;
+  static constexpr int STAGES = (227 * 1024 - 2048) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int NACC = MT == 1 ? 2 : 1;
 };
 
 struct GemmParams {
@@ -60,11 +65,11 @@ struct GemmParams {
   uint32_t lbo, sbo;   // UMMA descriptor strides of the MN-major SWIZZLE_64B tiles
 };
 
-template <int P, int MODE>
+template <int P, int MODE, int MT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmBx, const GemmParams prm) {
-  using Cfg = GemmCfg<P>;
+             const GemmParams prm) {
+  using Cfg = GemmCfg<P, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -76,11 +81,15 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Grid g = make_grid(prm.H, prm.W);
-  const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;
-  auto tile_bn = [&](long long) -> int { return prm.bn; };
-  auto make_idesc = [&](int bn) -> uint32_t {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(G_BLOCK_M >> 4) << 24) |
-           (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
+  const long long num_tiles = prm.num_m_tiles * prm.num_n_tiles;     // num_m_tiles counts CTA tiles of MT*128 rows
+  const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + P * prm.bn * G_BLOCK_K * 2);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(prm.bn >> 3) << 17) |
+                         ((uint32_t)(G_BLOCK_M >> 4) << 24) |
+                         (MODE == MODE_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
+  // byte offset of (M sub-tile j, plane pa) inside a stage's A region
+  auto a_off = [&](int j, int pa) -> uint32_t {
+    return MODE == MODE_WGRAD_MN ? (uint32_t)(pa * MT * G_A_PLANE + j * G_A_PLANE)    // one TMA box [P][4*MT blocks]
+                                 : (uint32_t)((j * P + pa) * G_A_PLANE);              // MT boxes of [P][128 rows]
   };
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
@@ -101,17 +110,18 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const long long mt = t / prm.num_n_tiles;
       const int ntile = (int)(t % prm.num_n_tiles);
-      const uint32_t stage_tx = (uint32_t)P * (G_A_PLANE + tile_bn(t) * G_BLOCK_K * 2);
       for (int kb = 0; kb < prm.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + P * G_A_PLANE;
+        uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_expect_tx(&full_bar[stage], stage_tx);
         if (MODE == MODE_DGRAD) {
           // A = dG[rows - shift(tap), 32 gate columns];  B = Wd[N channels, tap*1024 + 32 gate columns]
           const int q = kb / 9, tap = kb - q * 9;
           const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
-          tma_load_3d(sa, &tmA, &full_bar[stage], q * G_BLOCK_K, (int)(mt * G_BLOCK_M - shift), 0);
+          for (int j = 0; j < MT; ++j)
+            tma_load_3d(sa + a_off(j, 0), &tmA, &full_bar[stage], q * G_BLOCK_K,
+                        (int)((mt * MT + j) * G_BLOCK_M - shift), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], tap * kGates + q * G_BLOCK_K,
                       prm.need_x ? ntile * prm.bn : prm.cxp, 0);
         } else if (MODE == MODE_WGRAD) {
@@ -120,11 +130,11 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_3d(sa, &tmA, &full_bar[stage], kb * G_BLOCK_K, (int)(mt * G_BLOCK_M), 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], kb * G_BLOCK_K, tap * prm.cpad + half * prm.bn, 0);
         } else {
-          // MN-major: A = dG[32 halo rows (K), 4 blocks of 32 gate columns]; B = `upt` units, each
+          // MN-major: A = dG[32 halo rows (K), 4*MT blocks of 32 gate columns]; B = `upt` units, each
           // xh[32 halo rows + shift(tap), nb blocks of 32 channels]; ntile = (unit group, k-split)
           const int ks = ntile % prm.ksplit, grp = ntile / prm.ksplit;
           const int k0 = (ks * prm.num_kb + kb) * G_BLOCK_K;
-          tma_load_4d(sa, &tmA, &full_bar[stage], 0, k0, (int)mt * 4, 0);
+          tma_load_4d(sa, &tmA, &full_bar[stage], 0, k0, (int)mt * 4 * MT, 0);
           for (int j = 0; j < prm.upt; ++j) {
             int u = grp * prm.upt + j;
             if (u >= prm.n_units) u = prm.n_units - 1;     // odd tail: duplicate, discarded by the epilogue
@@ -143,37 +153,38 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int stage = 0; uint32_t phase = 0;
     long long it = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int as = (int)(it & 1);
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const int as = (int)(it % Cfg::NACC);
+      const uint32_t aphase = (uint32_t)((it / Cfg::NACC) & 1);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 256;
-      const int bn_t = tile_bn(t);
-      const uint32_t idesc = make_idesc(bn_t);
+      const uint32_t d_tmem = tmem_base + as * MT * 256;
+      const uint32_t b_plane = (uint32_t)prm.bn * G_BLOCK_K * 2;   // TMA packs planes back to back
       for (int kb = 0; kb < prm.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + P * G_A_PLANE;
-        const uint32_t b_plane = (uint32_t)bn_t * G_BLOCK_K * 2;   // TMA packs planes back to back
-        uint32_t first = (kb == 0) ? 0u : 1u;
+        const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-        for (int pa = 0; pa < P; ++pa) {
+        for (int j = 0; j < MT; ++j) {
+          uint32_t first = (kb == 0) ? 0u : 1u;
 #pragma unroll
-          for (int pb = 0; pb < P - pa; ++pb) {
+          for (int pa = 0; pa < P; ++pa) {
 #pragma unroll
-            for (int k = 0; k < G_BLOCK_K / G_UMMA_K; ++k) {
-              uint64_t ad, bd;
-              if (MODE == MODE_WGRAD_MN) {
-                // one UMMA consumes 16 K rows = two 8-row groups (sbo apart) of every 32-wide MN block
-                ad = make_smem_desc(sa + pa * G_A_PLANE + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
-                bd = make_smem_desc(sb + pb * b_plane + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
-              } else {
-                ad = make_smem_desc(sa + pa * G_A_PLANE + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
-                bd = make_smem_desc(sb + pb * b_plane + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+            for (int pb = 0; pb < P - pa; ++pb) {
+#pragma unroll
+              for (int k = 0; k < G_BLOCK_K / G_UMMA_K; ++k) {
+                uint64_t ad, bd;
+                if (MODE == MODE_WGRAD_MN) {
+                  // one UMMA consumes 16 K rows = two 8-row groups (sbo apart) of every 32-wide MN block
+                  ad = make_smem_desc(sa + a_off(j, pa) + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
+                  bd = make_smem_desc(sb + pb * b_plane + k * 2 * prm.sbo, prm.sbo, G_SW64_LAYOUT, prm.lbo);
+                } else {
+                  ad = make_smem_desc(sa + a_off(j, pa) + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+                  bd = make_smem_desc(sb + pb * b_plane + k * G_UMMA_K * 2, G_SW64_SBO, G_SW64_LAYOUT);
+                }
+                umma_bf16(d_tmem + j * 256, ad, bd, idesc, first);
+                first = 1u;
               }
-              umma_bf16(d_tmem, ad, bd, idesc, first);
-              first = 1u;
             }
           }
         }
@@ -187,54 +198,56 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int wq = warp & 3;
     long long it = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int as = (int)(it & 1);
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const int as = (int)(it % Cfg::NACC);
+      const uint32_t aphase = (uint32_t)((it / Cfg::NACC) & 1);
       const long long mt = t / prm.num_n_tiles;
       const int ntile = (int)(t % prm.num_n_tiles);
-      const int bn_t = tile_bn(t);
-      const long long row = mt * G_BLOCK_M + wq * 32 + lane;
-      bool valid;
-      float* dst;
-      if (MODE == MODE_DGRAD) {
-        valid = row < prm.R;
-        if (valid) {
-          const int rem = (int)(row % g.S);
-          const int y = rem / g.Wp, x = rem - y * g.Wp;
-          valid = (x < g.W) && (y < g.H);
-        }
-        dst = prm.out + row * prm.cpad + (prm.need_x ? ntile * prm.bn : prm.cxp);
-      } else if (MODE == MODE_WGRAD) {
-        valid = row < kGates;
-        const int tap = ntile >> 1, half = ntile & 1;
-        dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + half * prm.bn;
-      } else {
-        valid = row < kGates;
-        dst = prm.out + (long long)(ntile % prm.ksplit) * kGates * 9LL * prm.cpad + row * (9LL * prm.cpad);
-      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * 256;
-      for (int c0 = 0; c0 < bn_t; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
-        bool ok = valid;
-        float4* d4 = reinterpret_cast<float4*>(dst + c0);
-        if (MODE == MODE_WGRAD_MN) {
-          // column c0 of the tile -> (unit, channel): dW[tap][chunk*ubn + c]; this (tile, k-split) owns its slab
-          const int j = c0 / prm.ubn;
-          const int u = (ntile / prm.ksplit) * prm.upt + j;
-          ok = valid && u < prm.n_units;
-          const int tap = u / prm.n_per_tap, chunk = u - tap * prm.n_per_tap;
-          d4 = reinterpret_cast<float4*>(dst + tap * prm.cpad + chunk * prm.ubn + (c0 - j * prm.ubn));
-        }
-        if (ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-            if (MODE != MODE_DGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-            d4[q] = o;
+      for (int j = 0; j < MT; ++j) {
+        const long long row = (mt * MT + j) * G_BLOCK_M + wq * 32 + lane;
+        bool valid;
+        float* dst;
+        if (MODE == MODE_DGRAD) {
+          valid = row < prm.R;
+          if (valid) {
+            const int rem = (int)(row % g.S);
+            const int y = rem / g.Wp, x = rem - y * g.Wp;
+            valid = (x < g.W) && (y < g.H);
+          }
+          dst = prm.out + row * prm.cpad + (prm.need_x ? ntile * prm.bn : prm.cxp);
+        } else if (MODE == MODE_WGRAD) {
+          valid = row < kGates;
+          const int tap = ntile >> 1, half = ntile & 1;
+          dst = prm.out + row * (9LL * prm.cpad) + tap * prm.cpad + half * prm.bn;
+        } else {
+          valid = row < kGates;
+          dst = prm.out + (long long)(ntile % prm.ksplit) * kGates * 9LL * prm.cpad + row * (9LL * prm.cpad);
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (as * MT + j) * 256;
+        for (int c0 = 0; c0 < prm.bn; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+          bool ok = valid;
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+          if (MODE == MODE_WGRAD_MN) {
+            // column c0 of the tile -> (unit, channel): dW[tap][chunk*ubn + c]; this (tile, k-split) owns its slab
+            const int ju = c0 / prm.ubn;
+            const int u = (ntile / prm.ksplit) * prm.upt + ju;
+            ok = valid && u < prm.n_units;
+            const int tap = u / prm.n_per_tap, chunk = u - tap * prm.n_per_tap;
+            d4 = reinterpret_cast<float4*>(dst + tap * prm.cpad + chunk * prm.ubn + (c0 - ju * prm.ubn));
+          }
+          if (ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              if (MODE != MODE_DGRAD) { const float4 old = d4[q]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              d4[q] = o;
+            }
           }
         }
       }
@@ -423,18 +436,18 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const float* 
   }
 }
 
-template <int P, int MODE>
-static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBx,
-                        const GemmParams& prm, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<P>;
+template <int P, int MODE, int MT>
+static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int num_sms,
+                        cudaStream_t stream) {
+  using Cfg = GemmCfg<P, MT>;
   static bool configured = false;
   if (!configured) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MVB_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<P, MODE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const long long tiles = prm.num_m_tiles * prm.num_n_tiles;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  pgemm_kernel<P, MODE><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmBx, prm);
+  pgemm_kernel<P, MODE, MT><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;
@@ -455,7 +468,7 @@ int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long lo
   MVB_REQUIRE(cpad % 32 == 0 && cxp >= 32 && cxp <= 256 && cxp % 16 == 0, "cell_dgrad: cpad=%d unsupported", cpad);
   const Grid g = make_grid(H, W);
   const long long R = NS * g.S;
-  CUtensorMap tmA, tmB, tmBx;
+  CUtensorMap tmA, tmB;
   int rc = encode_tmap_3d_bf16(&tmA, dg_planes, kGates, (uint64_t)R, P, kGates * 2ull, (uint64_t)R * kGates * 2,
                                G_BLOCK_K, G_BLOCK_M, P, 64);
   if (rc) return rc;
@@ -466,17 +479,27 @@ int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long lo
   MVB_REQUIRE(bn % 16 == 0, "cell_dgrad: cpad=%d unsupported", cpad);
   rc = encode_tmap_3d_bf16(&tmB, wd_planes, ktot, (uint64_t)cpad, P, ktot * 2, ktot * cpad * 2, G_BLOCK_K, bn, P, 64);
   if (rc) return rc;
-  tmBx = tmB;
   GemmParams prm = {};
   prm.out = dxh; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.bn = bn; prm.cxp = cxp; prm.need_x = need_x;
-  prm.num_kb = 9 * (kGates / G_BLOCK_K); prm.num_m_tiles = (R + G_BLOCK_M - 1) / G_BLOCK_M;
+  prm.num_kb = 9 * (kGates / G_BLOCK_K);
+  // with the x block (N = 144 / 160) a CTA tile is 256 rows (two accumulators sharing every B tile);
+  // the h-only N = 256 tile already has the forward kernel's operand intensity
+  const int mt_sub = need_x ? 2 : 1;
+  prm.num_m_tiles = (R + G_BLOCK_M * mt_sub - 1) / (G_BLOCK_M * mt_sub);
   prm.num_n_tiles = need_x ? 2 : 1;
   int sms = 0;
   if ((rc = num_sms_of_device(&sms))) return rc;
+  if (need_x) {
+    switch (P) {
+      case 1: return launch_pgemm<1, MODE_DGRAD, 2>(tmA, tmB, prm, sms, stream);
+      case 2: return launch_pgemm<2, MODE_DGRAD, 2>(tmA, tmB, prm, sms, stream);
+      default: return launch_pgemm<3, MODE_DGRAD, 2>(tmA, tmB, prm, sms, stream);
+    }
+  }
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_DGRAD>(tmA, tmB, tmBx, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_DGRAD, 1>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_DGRAD, 1>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_DGRAD, 1>(tmA, tmB, prm, sms, stream);
   }
 }
 
@@ -501,13 +524,13 @@ int cell_wgrad(const void* dgT_planes, const void* xhT_planes, float* dwp, long 
   int sms = 0;
   if ((rc = num_sms_of_device(&sms))) return rc;
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_WGRAD>(tmA, tmB, tmB, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_WGRAD, 1>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD, 1>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD, 1>(tmA, tmB, prm, sms, stream);
   }
 }
 
-int cell_wgrad_mn_slabs(int cpad) { return cpad == 288 ? 5 : 1; }
+int cell_wgrad_mn_slabs(int cpad) { return cpad == 288 ? 5 : 2; }
 
 int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long long NS, int H, int W,
                   int cpad, int P, cudaStream_t stream) {
@@ -525,7 +548,7 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   {
     const uint64_t dims[4] = {32, (uint64_t)R, kGates / 32, (uint64_t)P};
     const uint64_t st[3] = {kGates * 2ull, 64, (uint64_t)R * kGates * 2};
-    const uint32_t box[4] = {32, G_BLOCK_K, 4, (uint32_t)P};
+    const uint32_t box[4] = {32, G_BLOCK_K, 8, (uint32_t)P};      // MT = 2: 256 gate columns per CTA tile
     int rc = encode_tmap_4d_bf16(&tmA, dg_planes, dims, st, box, 64);
     if (rc) return rc;
   }
@@ -538,11 +561,11 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   }
   prm.out = dwp; prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad;
   const long long kb_total = (R + G_BLOCK_K - 1) / G_BLOCK_K;
-  // work items = 8 M tiles x unit groups x k-splits, sized to fill whole waves of 148 CTAs:
-  // cpad 288: 8 x 14 x 5 = 560 (3.8 waves); cpad 320: 8 x 18 x 1 = 144
+  // work items = 4 M tiles (256 gate columns) x unit groups x k-splits, sized to fill whole waves of 148 CTAs:
+  // cpad 288: 4 x 14 x 5 = 280 (1.9 waves); cpad 320: 4 x 18 x 2 = 144
   prm.ksplit = cell_wgrad_mn_slabs(cpad);
   prm.num_kb = (int)((kb_total + prm.ksplit - 1) / prm.ksplit);
-  prm.num_m_tiles = kGates / G_BLOCK_M;
+  prm.num_m_tiles = kGates / (2 * G_BLOCK_M);
   prm.num_n_tiles = ((prm.n_units + prm.upt - 1) / prm.upt) * prm.ksplit;
   prm.lbo = 32 * 64;   // bytes between 32-wide MN blocks ([32 K rows][64 B] each)
   prm.sbo = 8 * 64;    // bytes between groups of 8 K rows
@@ -550,9 +573,9 @@ int cell_wgrad_mn(const void* dg_planes, const void* xh_planes, float* dwp, long
   int rc = num_sms_of_device(&sms);
   if (rc) return rc;
   switch (P) {
-    case 1: return launch_pgemm<1, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
-    case 2: return launch_pgemm<2, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
-    default: return launch_pgemm<3, MODE_WGRAD_MN>(tmA, tmB, tmB, prm, sms, stream);
+    case 1: return launch_pgemm<1, MODE_WGRAD_MN, 2>(tmA, tmB, prm, sms, stream);
+    case 2: return launch_pgemm<2, MODE_WGRAD_MN, 2>(tmA, tmB, prm, sms, stream);
+    default: return launch_pgemm<3, MODE_WGRAD_MN, 2>(tmA, tmB, prm, sms, stream);
   }
 }
 
