@@ -24,6 +24,7 @@
 //               two 256-column accumulators so tile i+1's MMAs overlap tile i's epilogue.
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
+#include <stdlib.h>
 
 namespace mvb {
 
@@ -75,7 +76,11 @@ struct CellParams {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) |
                             ((BLOCK_M >> 4) << 24);
 
-template <int P>
+// MC = true: clusters of two CTAs work on two M tiles of the same N tile in lock step; each loads half of every B
+// (weight) tile and TMA-multicasts it to both, so the L2 -> shared-memory traffic per CTA and stage drops from
+// 48 KB to 32 KB (P = 2).  A stage may be refilled once BOTH CTAs' MMAs have consumed it (empty barrier count 2,
+// commits multicast to the pair).
+template <int P, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                 const __grid_constant__ CUtensorMap tmB, const CellParams prm) {
@@ -95,17 +100,23 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
   const int kc = prm.cpad / BLOCK_K;     // channel chunks per tap
   const int num_kb = 9 * kc;
   const long long num_m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
-  const long long num_tiles = num_m_tiles * N_TILES;
+  // work index w -> (m tile, n tile).  MC: the pair shares w; rank r takes m tile 2*(w / N_TILES) + r.
+  const uint32_t rank = MC ? cluster_ctarank() : 0u;
+  const long long num_tiles = (MC ? (num_m_tiles + 1) / 2 : num_m_tiles) * N_TILES;
+  const long long w_begin = MC ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long w_step = MC ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  auto tile_m0 = [&](long long w) -> long long { return ((w / N_TILES) * (MC ? 2 : 1) + rank) * BLOCK_M; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI_WARPS); }
     fence_barrier_init();
   }
+  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -115,8 +126,8 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const long long m0 = (t / N_TILES) * BLOCK_M;
+    for (long long t = w_begin; t < num_tiles; t += w_step) {
+      const long long m0 = tile_m0(t);
       const int n0 = (int)(t % N_TILES) * BLOCK_N;
       for (int kb = prm.kb_begin; kb < num_kb; ++kb) {
         // chunk-major K order: the 9 taps of one 32-channel chunk are consecutive (their A boxes
@@ -130,7 +141,14 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
         uint8_t* sb = sa + P * A_PLANE_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_3d(sa, &tmA, &full_bar[stage], q * BLOCK_K, (int)(m0 + shift), 0);
-        tma_load_3d(sb, &tmB, &full_bar[stage], tap * prm.cpad + q * BLOCK_K, n0, 0);
+        if (MC) {
+          // this CTA's half (128 rows) of every plane of the B tile, delivered to both CTAs of the pair
+          for (int p = 0; p < P; ++p)
+            tma_load_3d_mc(sb + p * B_PLANE_BYTES + rank * (B_PLANE_BYTES / 2), &tmB, &full_bar[stage],
+                           tap * prm.cpad + q * BLOCK_K, n0 + (int)rank * (BLOCK_N / 2), p, (uint16_t)3);
+        } else {
+          tma_load_3d(sb, &tmB, &full_bar[stage], tap * prm.cpad + q * BLOCK_K, n0, 0);
+        }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -138,7 +156,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
     // ===================== MMA issuer =====================
     int stage = 0; uint32_t phase = 0;
     long long it = 0;
-    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (long long t = w_begin; t < num_tiles; t += w_step, ++it) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -163,7 +181,8 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
             }
           }
         }
-        umma_commit(&empty_bar[stage]);
+        if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);
+        else umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(&tfull_bar[as]);
@@ -173,10 +192,10 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
     const int wq = warp & 3;                 // TMEM lane quarter this warp may touch
     const int cgp = (warp - 4) >> 2;         // column group (0/1): channels [32*cgp, +32)
     long long it = 0;
-    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (long long t = w_begin; t < num_tiles; t += w_step, ++it) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      const long long m0 = (t / N_TILES) * BLOCK_M;
+      const long long m0 = tile_m0(t);
       const int nt = (int)(t % N_TILES);
       const long long row = m0 + wq * 32 + lane;
       bool valid = row < prm.R;
@@ -296,6 +315,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // the peer may still multicast into this CTA's smem / barriers
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -396,18 +416,33 @@ int cell_xfold_tables(const float* kernel, const float* biases, const float* We,
 }
 
 template <int P>
-static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CellParams& prm,
-                       int num_sms, cudaStream_t stream) {
+static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
+                       const CellParams& prm, int num_sms, bool multicast, cudaStream_t stream) {
   using Cfg = CellCfg<P>;
   static bool configured = false;
   if (!configured) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     configured = true;
   }
-  const long long num_tiles = ((prm.R + BLOCK_M - 1) / BLOCK_M) * N_TILES;
+  const long long m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
+  if (multicast && m_tiles >= 2 * (long long)num_sms) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, true>, tmA, tmBh, prm));
+    count_launch(1);
+    return MVB_OK;
+  }
+  const long long num_tiles = m_tiles * N_TILES;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-  cell_fwd_kernel<P><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  cell_fwd_kernel<P, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;
@@ -427,13 +462,18 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   const long long R = NS * g.S;
   MVB_REQUIRE(R + 2LL * g.Wp + 256 < 0x7fffffffLL, "cell_fwd: too many rows (%lld) for int32 TMA coordinates", R);
 
-  CUtensorMap tmA, tmB;
+  // weight-tile multicast across CTA pairs is on by default (MVB_CELL_MULTICAST=0 turns it off for A/B runs)
+  static const bool multicast = [] { const char* e = getenv("MVB_CELL_MULTICAST"); return !(e && e[0] == '0'); }();
+  CUtensorMap tmA, tmB, tmBh;
   int rc = encode_tmap_3d_bf16(&tmA, xh_planes, (uint64_t)cpad, (uint64_t)R, (uint64_t)P,
                                (uint64_t)cpad * 2, (uint64_t)R * cpad * 2, BLOCK_K, BLOCK_M, P, 64);
   if (rc) return rc;
   const uint64_t ktot = 9ull * cpad;
   rc = encode_tmap_3d_bf16(&tmB, w_planes, ktot, (uint64_t)kGates, (uint64_t)P, ktot * 2,
                            ktot * kGates * 2, BLOCK_K, BLOCK_N, P, 64);
+  if (rc) return rc;
+  rc = encode_tmap_3d_bf16(&tmBh, w_planes, ktot, (uint64_t)kGates, (uint64_t)P, ktot * 2,
+                           ktot * kGates * 2, BLOCK_K, BLOCK_N / 2, 1, 64);     // half tile of one plane
   if (rc) return rc;
 
   CellParams prm;
@@ -453,9 +493,9 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   MVB_CHECK_CUDA(cudaGetDevice(&dev));
   MVB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   switch (P) {
-    case 1: return launch_cell<1>(tmA, tmB, prm, num_sms, stream);
-    case 2: return launch_cell<2>(tmA, tmB, prm, num_sms, stream);
-    default: return launch_cell<3>(tmA, tmB, prm, num_sms, stream);
+    case 1: return launch_cell<1>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
+    case 2: return launch_cell<2>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
+    default: return launch_cell<3>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
   }
 }
 
