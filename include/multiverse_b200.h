@@ -239,6 +239,12 @@ int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
                        const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,
                        int B, int Tp, int V, void* stream);
 
+/* ---- f-3 (next row): post-decode on the device (multifuture_inference.py:504-517,
+ *      pred_utils.py:460-492): out[n,k,t] = centers[ids[n,k,t]] + offsets[t,n,ids[n,k,t]].
+ *      ids int32 [N,K,Tp]; offsets fp32 [Tp,N,V,2] (mvb_head_reg_fwd layout); centers fp32 [V,2]. */
+int mvb_decode_trajectories(const int32_t* ids, const float* offsets, const float* centers, float* out,
+                            int64_t N, int K, int Tp, int V, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

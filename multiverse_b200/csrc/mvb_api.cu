@@ -281,6 +281,10 @@ int mvb_beam_step(const float* logits, const float* score_in, float* score_out, 
   return beam_step(logits, score_in, score_out, ids_out, parents_out, row_map_out, N, B, V,
                    first_step, zero_scores, diverse, log_gamma, S(stream));
 }
+int mvb_decode_trajectories(const int32_t* ids, const float* offsets, const float* centers, float* out,
+                            int64_t N, int K, int Tp, int V, void* stream) {
+  return decode_trajectories(ids, offsets, centers, out, N, K, Tp, V, S(stream));
+}
 int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
                        const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,
                        int B, int Tp, int V, void* stream) {

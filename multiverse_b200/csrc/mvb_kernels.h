@@ -50,6 +50,8 @@ int emb_dense_fwd(const float* x, const float* We, const float* be, int E, void*
                   cudaStream_t stream);
 
 // mvb_beam.cu
+int decode_trajectories(const int* ids, const float* offs, const float* centers, float* out, long long N,
+                        int K, int Tp, int V, cudaStream_t stream);
 int beam_step(const float* logits, const float* score_in, float* score_out, int* ids_out,
               int* parents_out, int* row_map_out, long long N, int B, int V, int first_step,
               int zero_scores, int diverse, float log_gamma, cudaStream_t stream);

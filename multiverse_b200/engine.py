@@ -324,4 +324,31 @@ class ConvRNNEngine(object):
       reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)
       out["grid_pred_decoded"].append(dec)
       out["grid_pred_reg_decoded"].append(reg)
+      out.setdefault("_offs", {})[i] = offs           # engine layout [Tp,N,HW,2], for decode_trajectories
     return out
+
+  def grid_centers(self, i, video_h=1080, video_w=1920):
+    """Cell centres of scale i in frame pixels (code/multifuture_inference.py:101-113)."""
+    h, w = self.cfg.scene_grids[i]
+    vh, vw = getattr(self.cfg, "video_h", video_h), getattr(self.cfg, "video_w", video_w)
+    ys = (torch.arange(h, device=self.device, dtype=torch.float64) + 0.5) * (vh * 1.0 / h)
+    xs = (torch.arange(w, device=self.device, dtype=torch.float64) + 0.5) * (vw * 1.0 / w)
+    return torch.stack(torch.meshgrid(xs, ys, indexing="xy"), dim=-1).reshape(h * w, 2).float().contiguous()
+
+  def decode_trajectories(self, out, i, centers=None):
+    """Post-decode of a forward() result on the device: [N,K,Tp,2] pixel trajectories
+    = centre + offset of the selected cells (beam ids, or the greedy arg-max with K = 1).  `centers`
+    [h,w,2] / [HW,2]: the caller's args.scene_grid_centers[i]; default = grid_centers(i)."""
+    offs = out["_offs"][i]
+    tp, n = offs.shape[0], offs.shape[1]
+    if out["beam_outputs"] is not None:
+      ids = out["beam_outputs"][1].contiguous()
+    else:
+      ids = out["grid_pred_decoded"][i].reshape(n, tp, -1).argmax(-1).to(torch.int32).unsqueeze(1).contiguous()
+    res = torch.empty(ids.shape + (2,), dtype=torch.float32, device=self.device)
+    if centers is None:
+      centers = self.grid_centers(i)
+    else:
+      centers = torch.as_tensor(centers).to(self.device, torch.float32).reshape(-1, 2).contiguous()
+    ops.decode_trajectories(ids, offs.contiguous(), centers, res)
+    return res

@@ -305,3 +305,10 @@ def scene_time_mean_bwd(dmean, frame_idx, dscene):
 def clip_adadelta(w, grad, acc, acc_upd, lr, clip, wd, grad_scale=1.0, rho=0.95, eps=1e-8):
   _lib.call("mvb_clip_adadelta", _p(w), _p(grad), _p(acc), _p(acc_upd), w.numel(), float(lr),
             float(rho), float(eps), float(clip or 0.0), float(wd), float(grad_scale), _stream())
+
+
+def decode_trajectories(ids, offs, centers, out):
+  """ids int32 [N,K,Tp], offs fp32 [Tp,N,V,2], centers fp32 [V,2] -> out fp32 [N,K,Tp,2]."""
+  n, k, tp = ids.shape
+  _lib.call("mvb_decode_trajectories", _p(ids), _p(offs), _p(centers), _p(out), n, k, tp, offs.shape[2],
+            _stream())

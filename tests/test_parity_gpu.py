@@ -356,3 +356,27 @@ def test_cell_onehot_fold_equals_explicit_embedding(dev):
   co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
   ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
   assert rel(co.cpu().numpy(), c_ref) < TIGHT and rel(ho.cpu().numpy(), h_ref) < TIGHT
+
+
+@pytest.mark.parametrize("name", ["beam_k5_plain", "greedy_native_18x32"])
+def test_decode_trajectories_on_device(dev, name):
+  """§8 row f-3: centre + offset of the selected cells on the device == the host post-processing of
+  code/multifuture_inference.py:504-517 applied to the fetched tensors."""
+  from multiverse_b200.engine import ConvRNNEngine
+  over, seed = cases.ROLLOUTS[name]
+  cfg = R.default_config(**over)
+  w = R.make_weights(cfg, seed); f = R.make_inputs(cfg, seed)
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  out = eng.forward(to_dev(f, dev))
+  i = [j for j in range(2) if cfg.use_grids[j]][0]
+  traj = eng.decode_trajectories(out, i).cpu().numpy()
+  reg = out["grid_pred_reg_decoded"][i].cpu().numpy()
+  n, tp = cfg.batch_size, cfg.pred_len
+  if cfg.use_beam_search:
+    ids = out["beam_outputs"][1].cpu().numpy()
+  else:
+    ids = out["grid_pred_decoded"][i].cpu().numpy().reshape(n, tp, -1).argmax(-1)[:, None]
+  for s in range(n):
+    want = R.ids_to_traj(cfg, i, ids[s], reg[s].astype(np.float64))
+    assert np.abs(traj[s] - want).max() < 1e-3          # pixels of a 1920x1080 frame
+  assert traj.shape == (n, ids.shape[1], tp, 2)
