@@ -248,18 +248,27 @@ class ConvRNNEngine(object):
     row_map = torch.empty((ns,), dtype=torch.int32, device=dev)
     tile_map = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(b).contiguous()
     xf = sw.dec_class_xf
-    # time = 0: tiled encoder state and last observed cell (:497-502, :527-531); the embedded one-hot
-    # input of every step is folded into table look-ups (ops.cell_fwd_onehot)
-    ids0 = first_ids.repeat_interleave(b).contiguous()
-    if cfg.use_gnn:
-      ops.gnn_attend_fwd(h32_enc, scene_mean, xh[0], h, w, ns, beam=b, row_map=tile_map)
-    else:
+    # time = 0 (:497-502, :527-531): the reference tiles the encoder state and the last observed cell K times, so
+    # all K beams carry identical rows until the first selection (which looks at beam 0 only, :569-573).  That
+    # step - graph attention, cell, and the time-1 head - is therefore evaluated once per sample (N rows, not
+    # N*K) and the first selection's children read it through row_map = sample index: same values, 1/K of
+    # the work for 1 of the Tp steps.  The embedded one-hot input of every step is folded into table
+    # look-ups (ops.cell_fwd_onehot).
+    if not cfg.use_gnn:
       raise NotImplementedError("beam search without use_gnn is not wired (no published config)")
-    self._cell_onehot("beam", xh[0], sw.dec_class, xf, ids0, c_enc, c[1], h32, None, h, w, ns, row_map=tile_map)
-    cur_c = 1
+    xh1 = self._xh("beam_t0", n, h, w, sw.dec_class.cpad)
+    c_t0 = self._state("beam_c_t0", n, h, w)
+    h32_t0 = self._state("beam_h32_t0", n, h, w)
+    logits_t0 = torch.empty((n, v), dtype=torch.float32, device=dev)
+    ops.gnn_attend_fwd(h32_enc, scene_mean, xh1[0], h, w, n, beam=1, row_map=None)
+    self._cell_onehot("beam_t0", xh1[0], sw.dec_class, xf, first_ids.contiguous(), c_enc, c_t0, h32_t0, None, h, w, n)
+    ops.head_class_fwd(h32_t0, sw.head_class, logits_t0, None, None, None, None, h, w, n, planes=self.planes)
+    step_logits[0].copy_(logits_t0.unsqueeze(1).expand(n, b, v))
+    h_src, c_src, cur_c = h32_t0, c_t0, 1
     for time in range(1, pred_len + 1):
-      ops.head_class_fwd(h32, sw.head_class, step_logits[time - 1], None, None, None, None, h, w,
-                         ns, planes=self.planes)
+      if time > 1:
+        ops.head_class_fwd(h32, sw.head_class, step_logits[time - 1], None, None, None, None, h, w,
+                           ns, planes=self.planes)
       s_in, s_out = scores[(time - 1) % 2], scores[time % 2]
       ops.beam_step(step_logits[time - 1], s_in, s_out, step_ids[time - 1], step_par[time - 1],
                     row_map, n, b, v, first_step=(time <= 1),
@@ -268,10 +277,12 @@ class ConvRNNEngine(object):
       if time == pred_len:
         break
       nxt = xh[time % 2]
-      ops.gnn_attend_fwd(h32, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
-      self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c[cur_c], c[1 - cur_c], h32,
-                        None, h, w, ns, row_map=row_map)
+      rm = tile_map if time == 1 else row_map       # time 1: every child's parent is its sample's single t0 row
+      ops.gnn_attend_fwd(h_src, scene_mean, nxt, h, w, ns, beam=b, row_map=rm)
+      self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c_src, c[1 - cur_c], h32,
+                        None, h, w, ns, row_map=rm)
       cur_c = 1 - cur_c
+      h_src, c_src = h32, c[cur_c]
     out_ids = torch.empty((n, b, pred_len), dtype=torch.int32, device=dev)
     out_logits = torch.empty((n, b, pred_len, v), dtype=torch.float32, device=dev)
     ops.beam_backtrace(step_ids, step_par, step_logits, out_ids, out_logits)
