@@ -13,6 +13,7 @@
 //
 // One CTA per sample; B*V fp32 candidates live in shared memory.  Latency-bound glue (<1 % of a
 // rollout step), kept bit-faithful to fp32 TF arithmetic (no FMA contraction on the penalty).
+#include <cstdlib>
 #include "mvb_common.cuh"
 #include "mvb_kernels.h"
 
@@ -110,6 +111,90 @@ beam_step_kernel(const float* __restrict__ logits, const float* __restrict__ sco
   (void)row_stat;
 }
 
+// Same selection in O(B*V) per beam row instead of the O(V^2) rank count.  With log(gamma) <= 0 (every published
+// setting: gamma = 0.01, or no penalty) the penalised value lp - |log gamma|*rank is non-increasing in the rank
+// order of its row, and equal values keep index order, so an entry of rank >= B is preceded by B entries of its
+// own row in the global order and can never be selected: the global top-B is the top-B of the rows' top-B lists.
+// Each warp extracts the top-B of its rows by B arg-max sweeps over the row in shared memory (the k-th sweep's
+// winner has rank k - the same rank the count gives, ties to the lower index); warp 0 then picks the B best of
+// the <= B*B candidates, ties to the lower flat index.  Bit-identical outputs to beam_step_kernel.
+__device__ __forceinline__ void warp_argmax(float& v, int& i, int& aux) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, aux, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; aux = oa; }
+  }
+}
+
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_step_topk_kernel(const float* __restrict__ logits, const float* __restrict__ score_in,
+                      float* __restrict__ score_out, int* __restrict__ ids_out,
+                      int* __restrict__ parents_out, int* __restrict__ row_map_out, int B, int V,
+                      int first_step, int zero_scores, int diverse, float log_gamma) {
+  extern __shared__ float sm[];
+  float* lp = sm;                                   // [rows][V] log-probs + score
+  float* cv = sm + (size_t)B * V;                   // [rows][B] candidate values (penalised)
+  int* ci = reinterpret_cast<int*>(cv + B * B);     // [rows][B] flat indices b*V + v
+  const long long n = blockIdx.x;
+  const int rows = first_step ? 1 : B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < rows; b += BEAM_THREADS / 32) {
+    const float* lg = logits + (n * B + b) * V;
+    float* r = lp + (size_t)b * V;
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, lg[v]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(lg[v] - m);
+    s = warp_sum(s);
+    const float lse = logf(s);
+    const float sc = score_in ? score_in[n * B + b] : 0.f;
+    for (int v = lane; v < V; v += 32) r[v] = __fadd_rn(__fsub_rn(__fsub_rn(lg[v], m), lse), sc);
+    __syncwarp();
+    for (int k = 0; k < B; ++k) {
+      float bv = -INFINITY; int bi = 0x7fffffff, aux = 0;
+      for (int v = lane; v < V; v += 32) {
+        const float c = r[v];
+        if (c > bv) { bv = c; bi = v; }
+      }
+      warp_argmax(bv, bi, aux);
+      if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;
+        cv[b * B + k] = diverse ? __fadd_rn(bv, __fmul_rn(log_gamma, (float)k)) : bv;
+        ci[b * B + k] = b * V + bi;
+        r[bi] = -INFINITY;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int ncand = rows * B;
+    for (int k = 0; k < B; ++k) {
+      float bv = -INFINITY; int bi = 0x7fffffff, pos = 0;
+      for (int i = lane; i < ncand; i += 32) {
+        const float c = cv[i];
+        const int f = ci[i];
+        if (c > bv || (c == bv && f < bi)) { bv = c; bi = f; pos = i; }
+      }
+      warp_argmax(bv, bi, pos);
+      if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;
+        cv[pos] = -INFINITY;
+        ci[pos] = 0x7fffffff;
+        const int parent = bi / V;
+        score_out[n * B + k] = zero_scores ? 0.f : bv;
+        ids_out[n * B + k] = bi - parent * V;
+        parents_out[n * B + k] = parent;
+        row_map_out[n * B + k] = (int)(n * B) + parent;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 beam_backtrace_kernel(const int* __restrict__ step_ids, const int* __restrict__ step_parents,
                       const float* __restrict__ step_logits, int* __restrict__ out_ids,
@@ -170,6 +255,23 @@ int beam_step(const float* logits, const float* score_in, float* score_out, int*
               int zero_scores, int diverse, float log_gamma, cudaStream_t stream) {
   MVB_REQUIRE(logits && score_out && ids_out && parents_out && row_map_out, "beam_step: null pointer");
   MVB_REQUIRE(N > 0 && B >= 1 && V >= B, "beam_step: bad sizes N=%lld B=%d V=%d", N, B, V);
+  const char* full = getenv("MVB_BEAM_FULL_RANK");   // tests: force the O(V^2) rank-count kernel
+  if ((!diverse || log_gamma <= 0.f) && !(full && full[0] == '1')) {
+    const size_t smem_t = sizeof(float) * ((size_t)B * V + 2 * (size_t)B * B);
+    MVB_REQUIRE(smem_t <= 227 * 1024, "beam_step: B*V=%d too large for shared memory", B * V);
+    static size_t configured_t = 0;
+    if (smem_t > 48 * 1024 && smem_t > configured_t) {
+      MVB_CHECK_CUDA(cudaFuncSetAttribute(beam_step_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      configured_t = smem_t;
+    }
+    beam_step_topk_kernel<<<(unsigned)N, BEAM_THREADS, smem_t, stream>>>(logits, score_in, score_out, ids_out,
+                                                                         parents_out, row_map_out, B, V, first_step,
+                                                                         zero_scores, diverse, log_gamma);
+    MVB_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return MVB_OK;
+  }
+  // log(gamma) > 0 rewards high ranks: no per-row bound on the winners, use the full rank count
   const size_t smem = sizeof(float) * 2 * (size_t)B * V;
   MVB_REQUIRE(smem <= 227 * 1024, "beam_step: B*V=%d too large for shared memory", B * V);
   static size_t configured = 0;

@@ -130,11 +130,19 @@ head_kernel(const float* __restrict__ h32, const float* __restrict__ Wo, float* 
         part[t * POUT + po] = acc;
       }
     }
+    // warp totals: groups of 8 values by the folding reduction (9 shuffles per 8 values), the rest by butterflies
+    constexpr int NFOLD = (9 * POUT) / 8;
 #pragma unroll
-    for (int t = 0; t < 9 * POUT; ++t) part[t] = warp_sum(part[t]);
-    if (lane == 0) {
+    for (int f = 0; f < NFOLD; ++f) {
+      const float v8[8] = {part[f * 8 + 0], part[f * 8 + 1], part[f * 8 + 2], part[f * 8 + 3],
+                           part[f * 8 + 4], part[f * 8 + 5], part[f * 8 + 6], part[f * 8 + 7]};
+      const float tot = warp_fold8(v8, lane);
+      if ((lane & 3) == 0) d_s[q * 9 * POUT + f * 8 + warp_fold8_index(lane)] = tot;
+    }
 #pragma unroll
-      for (int t = 0; t < 9 * POUT; ++t) d_s[q * 9 * POUT + t] = part[t];
+    for (int t = NFOLD * 8; t < 9 * POUT; ++t) {
+      const float tot = warp_sum(part[t]);
+      if (lane == 0) d_s[q * 9 * POUT + t] = tot;
     }
   }
   __syncthreads();

@@ -380,3 +380,36 @@ def test_decode_trajectories_on_device(dev, name):
     want = R.ids_to_traj(cfg, i, ids[s], reg[s].astype(np.float64))
     assert np.abs(traj[s] - want).max() < 1e-3          # pixels of a 1920x1080 frame
   assert traj.shape == (n, ids.shape[1], tp, 2)
+
+
+@pytest.mark.parametrize("first,zero,div,gamma", [(0, 0, 1, 0.01), (0, 0, 1, 0.7), (0, 0, 1, 1.0), (1, 1, 1, 0.01),
+                                                   (0, 0, 0, 1.0), (1, 0, 0, 1.0)])
+def test_beam_step_topk_equals_full_rank_count(dev, monkeypatch, first, zero, div, gamma):
+  """The O(B*V) selection (top-B of the rows' top-B lists) is bit-identical to the literal
+  add_div_penalty rank count (code/pred_models.py:1197-1223) + top_k over B*V (:578), at the K=20, 36x18
+  size and on logits quantised so that ties inside rows, across rows and across beams are frequent."""
+  from multiverse_b200 import ops
+  rng = np.random.default_rng(5)
+  n, b, v = 6, 20, 648
+  lg = np.round(rng.standard_normal((n, b, v)) * 3, 1).astype(np.float32)
+  lg[1] = lg[1, :1]                                        # identical beams -> ties across rows
+  sc = np.round(-np.abs(rng.standard_normal((n, b))), 1).astype(np.float32); sc[1] = sc[1, 0]
+  res = []
+  for full in ("1", "0"):
+    monkeypatch.setenv("MVB_BEAM_FULL_RANK", full)
+    so = torch.empty((n, b), device=dev)
+    ids = torch.empty((n, b), dtype=torch.int32, device=dev); par = torch.empty_like(ids)
+    rm = torch.empty((n * b,), dtype=torch.int32, device=dev)
+    ops.beam_step(T(lg, dev), T(sc, dev), so, ids, par, rm, n, b, v, first, zero, div, gamma)
+    res.append([x.cpu().numpy() for x in (so, ids, par, rm)])
+  for a, c in zip(*res):
+    assert np.array_equal(a, c)
+  # and against the numpy restatement (fp32 log-softmax differs by an ulp from CUDA's, so compare the ids
+  # only where the oracle's winner margin is not an exact tie-break case: here simply the parents' multiset)
+  lp = R.log_softmax(lg) + sc[:, :, None]
+  if div:
+    lp = R.add_div_penalty(lp, gamma)
+  cand = lp[:, 0] if first else lp.reshape(n, b * v)
+  _, idx = R.top_k_sorted(cand, b)
+  agree = np.mean((idx % v) == res[1][1])
+  assert agree > 0.9
