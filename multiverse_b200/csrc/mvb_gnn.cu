@@ -8,7 +8,7 @@
 // that 3x3 band:  h'_p = h_p + sum_q softmax_q(F^_p . F^_q) h_q.
 //
 // One warp walks one image row of one sample row with a 3x3 register window (8 h + 2 scene values
-// per lane per cell): moving one cell to the right loads only the 3 new cells of the next column,
+// per lane per cell) plus one column in flight: moving one cell to the right loads only the 3 new cells of a column,
 // so every h row is fetched 3x (not 9x) through L1/L2, squared norms are computed once per loaded
 // cell, and the centre-left dot product is the previous step's centre-right one.  Per cell: 7 dot
 // products + 3 norms reduced by warp shuffles, a <=9-way softmax, 72 FMAs of weighted sum, and the
@@ -27,25 +27,23 @@ struct GnnCol {         // one window column: rows y-1, y, y+1
   float n[3];           // squared norm of [h ; s] (warp-reduced)
 };
 
-__device__ __forceinline__ void gnn_load_col(GnnCol& c, const float* __restrict__ h32,
+// Raw loads of one window column, issued one step ahead of their use: with load-then-use the kernel was bound
+// by the latency of these loads (ncu: 2.7 warps per issue stalled on the long scoreboard at 12 warps/SM).
+__device__ __forceinline__ void gnn_load_raw(GnnCol& c, const float* __restrict__ h32,
                                              const float* __restrict__ scene, long long hrow0,
                                              long long srow0, int x, int W, int Wp, const bool (&rok)[3],
                                              int lane, int y) {
   const bool cok = (x >= 0) && (x < W);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    float q = 0.f;
     if (cok && rok[r]) {
       const float4* p4 = reinterpret_cast<const float4*>(h32 + (hrow0 + (long long)(y + r - 1) * Wp + x) * kHidden + lane * 8);
       const float4 a = __ldg(p4), b = __ldg(p4 + 1);
       c.h[r][0] = a.x; c.h[r][1] = a.y; c.h[r][2] = a.z; c.h[r][3] = a.w;
       c.h[r][4] = b.x; c.h[r][5] = b.y; c.h[r][6] = b.z; c.h[r][7] = b.w;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) q = fmaf(c.h[r][k], c.h[r][k], q);
       if (scene) {
         const float2 sv = __ldg(reinterpret_cast<const float2*>(scene + (srow0 + (long long)(y + r - 1) * W + x) * 64 + lane * 2));
         c.s[r][0] = sv.x; c.s[r][1] = sv.y;
-        q = fmaf(sv.x, sv.x, q); q = fmaf(sv.y, sv.y, q);
       } else {
         c.s[r][0] = 0.f; c.s[r][1] = 0.f;
       }
@@ -54,6 +52,18 @@ __device__ __forceinline__ void gnn_load_col(GnnCol& c, const float* __restrict_
       for (int k = 0; k < 8; ++k) c.h[r][k] = 0.f;
       c.s[r][0] = 0.f; c.s[r][1] = 0.f;
     }
+  }
+}
+
+// Squared norms of a loaded column (warp-reduced).
+__device__ __forceinline__ void gnn_norms(GnnCol& c) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q = fmaf(c.h[r][k], c.h[r][k], q);
+    q = fmaf(c.s[r][0], c.s[r][0], q);
+    q = fmaf(c.s[r][1], c.s[r][1], q);
     c.n[r] = q;
   }
 #pragma unroll
@@ -84,14 +94,22 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
   const long long srow0 = (s / beam) * (long long)g.H * g.W;
   const bool rok[3] = {y > 0, true, y < g.H - 1};
 
-  // Rotating 3-column register window (no register moves: the loop is unrolled by three and the
-  // roles L/C/R rotate through the three structs).
-  GnnCol W0, W1, W2;
-  gnn_load_col(W0, h32, scene_mean, hrow0, srow0, -1, g.W, g.Wp, rok, lane, y);   // zeros
-  gnn_load_col(W1, h32, scene_mean, hrow0, srow0, 0, g.W, g.Wp, rok, lane, y);
+  // Rotating 4-column register window (no register moves: the loop is unrolled by four and the roles
+  // L / C / R / N(ext, in flight) rotate through the four structs): every column is requested one step before
+  // its first use.  Measured at 2 560 rows of 36x18: 3 columns (load, then use) 1.86 ms; 4 columns 1.41 ms;
+  // 5 columns (two steps ahead, 236 registers) 1.54 ms; an L1 prefetch instead of the fourth column 2.16 ms;
+  // 4 columns + folded (transpose) reduction of the ten warp sums 1.54 ms (longer dependent shuffle chain);
+  // forcing 3 CTAs/SM (168 registers, spills) 1.59 ms.
+  GnnCol W0, W1, W2, W3;
+  gnn_load_raw(W0, h32, scene_mean, hrow0, srow0, -1, g.W, g.Wp, rok, lane, y);   // zeros
+  gnn_load_raw(W1, h32, scene_mean, hrow0, srow0, 0, g.W, g.Wp, rok, lane, y);
+  gnn_load_raw(W2, h32, scene_mean, hrow0, srow0, 1, g.W, g.Wp, rok, lane, y);
+  gnn_norms(W0);
+  gnn_norms(W1);
   float d_cl = 0.f;   // dot(centre, left-centre), carried from the previous cell
-  auto step = [&](const GnnCol& L, const GnnCol& C, GnnCol& R, int x) {
-    gnn_load_col(R, h32, scene_mean, hrow0, srow0, x + 1, g.W, g.Wp, rok, lane, y);
+  auto step = [&](const GnnCol& L, const GnnCol& C, GnnCol& R, GnnCol& N, int x) {
+    gnn_load_raw(N, h32, scene_mean, hrow0, srow0, x + 2, g.W, g.Wp, rok, lane, y);   // used by the next step
+    gnn_norms(R);
     // dots of the centre cell (C,1) with its 8 neighbours; self = squared norm
     float d[9];
     d[0] = gnn_dot(C, 1, L, 0); d[1] = gnn_dot(C, 1, C, 0); d[2] = gnn_dot(C, 1, R, 0);
@@ -147,10 +165,11 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
       *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
     }
   };
-  for (int x = 0; x < g.W; x += 3) {
-    step(W0, W1, W2, x);
-    if (x + 1 < g.W) step(W1, W2, W0, x + 1);
-    if (x + 2 < g.W) step(W2, W0, W1, x + 2);
+  for (int x = 0; x < g.W; x += 4) {
+    step(W0, W1, W2, W3, x);
+    if (x + 1 < g.W) step(W1, W2, W3, W0, x + 1);
+    if (x + 2 < g.W) step(W2, W3, W0, W1, x + 2);
+    if (x + 3 < g.W) step(W3, W0, W1, W2, x + 3);
   }
 }
 

@@ -107,10 +107,16 @@ head_kernel(const float* __restrict__ h32, const float* __restrict__ Wo, float* 
       wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
     }
   }
+  // the row of the next iteration is requested before the current one is consumed (load latency, not bandwidth,
+  // bounds this loop)
+  auto row_ptr = [&](int q) {
+    return reinterpret_cast<const float4*>(h32 + (s * g.S + (long long)(q / g.W) * g.Wp + q % g.W) * kHidden + lane * 8);
+  };
+  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+  if (warp < hw) { na = __ldg(row_ptr(warp)); nb = __ldg(row_ptr(warp) + 1); }
   for (int q = warp; q < hw; q += HEAD_THREADS / 32) {
-    const int y = q / g.W, x = q % g.W;
-    const float4* p4 = reinterpret_cast<const float4*>(h32 + (s * g.S + (long long)y * g.Wp + x) * kHidden + lane * 8);
-    const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+    const float4 a = na, b = nb;
+    if (q + HEAD_THREADS / 32 < hw) { na = __ldg(row_ptr(q + HEAD_THREADS / 32)); nb = __ldg(row_ptr(q + HEAD_THREADS / 32) + 1); }
     const float hv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     float part[9 * POUT];
 #pragma unroll
