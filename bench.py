@@ -360,18 +360,46 @@ def main():
   clocks = sampler.stop() if rank == 0 else None
   value = gb * args.steps / (ms_total * 1e-3)
 
-  # ---- end to end through host buffers (`e2e`) ----------------------------------------------
-  out0 = eng.forward(dev_feeds)
-  host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outputs_of(out0)]
-  d2h_bytes = sum(t.numel() * t.element_size() for t in host_out)
+  # ---- end to end through the reference-facing call (`e2e`) --------------------------------------
+  # What code/pred_models.py:1779 (Tester.step) and code/multifuture_inference.py:471 do: sess.run(fetches,
+  # feed_dict) on the drop-in Model through the `tensorflow`-named shim - numpy host arrays in (pinned), numpy host
+  # arrays out; H2D, forward and D2H of every fetched tensor inside the timed region.
+  d2h_probe = outputs_of(eng.forward(dev_feeds))
+  d2h_bytes = sum(t.numel() * t.element_size() for t in d2h_probe)
+  del d2h_probe, eng, dev_feeds
+  torch.cuda.empty_cache()
+  import types
+  sys.path.insert(0, os.path.join(ROOT, "multiverse_b200", "dropin"))
+  import tensorflow as tf          # the shim (multiverse_b200/dropin/tensorflow), not TensorFlow
+  import pred_models as pm
+  margs = types.SimpleNamespace(**vars(cfg))
+  margs.modelname, margs.use_soft_grid_class, margs.use_gt_grid, margs.is_train = "bench", False, False, False
+  model = pm.get_model(margs, gpuid=local)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    key = v.name.split(":")[0]
+    if key in weights:
+      v.assign(weights[key])
+  sess = tf.Session(config=tf.ConfigProto(allow_soft_placement=True))
+  feed_dict = {model.scene_feat: host_pinned["scene_feat"].numpy(), model.obs_scene: host_pinned["obs_scene"].numpy(),
+               model.obs_length: np.full((n_local,), cfg.obs_len, dtype="int32"),
+               model.pred_length: np.full((n_local,), cfg.pred_len, dtype="int32"), model.is_train: False}
+  fetches = []
+  for i in range(len(cfg.scene_grids)):
+    if cfg.use_grids[i]:
+      feed_dict[model.grid_obs_labels[i]] = host_pinned["grid_obs_labels"][i].numpy()
+      feed_dict[model.grid_obs_regress[i]] = host_pinned["grid_obs_regress"][i].numpy()
+      fetches += [model.grid_pred_decoded[i], model.grid_pred_reg_decoded[i]]
+  if cfg.use_beam_search:
+    fetches.append(model.beam_outputs)
 
   def e2e_step():
-    out = eng.forward(h2d())
-    for dst, src in zip(host_out, outputs_of(out)):
-      dst.copy_(src, non_blocking=True)
+    return sess.run(fetches, feed_dict=feed_dict)
 
   for _ in range(2):
-    e2e_step()
+    res = e2e_step()
+  assert all(isinstance(r, np.ndarray) for r in res[:2])
+  del res
   ms_e2e = timed(e2e_step, args.steps)
   e2e_value = gb * args.steps / (ms_e2e * 1e-3)
 

@@ -82,6 +82,7 @@ class ConvRNNEngine(object):
     self.set_weights(weights)
     self._bufs = {}
     self.cell_events = None   # set to [] to record (tag, cx, start, end) events per cell launch
+    self._graphs = {}         # forward_graph(): feed signature -> (CUDAGraph, static feeds, static outputs)
 
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
@@ -290,14 +291,17 @@ class ConvRNNEngine(object):
                                                            logits=step_logits)
 
   # ------------------------------------------------------------------ whole forward
-  def forward(self, feeds, pred_len=None):
+  def forward(self, feeds, pred_len=None, on_output=None):
     """feeds: device tensors
          scene_feat fp32 [F,SH,SW,SC], obs_scene int32 [N,T],
          grid_obs_labels[i] int32 [N,T], grid_obs_regress[i] fp32 [N,T,h,w,2]
     Returns a dict shaped like the reference fetches: grid_pred_decoded[i] [N,Tp,h,w,1],
     grid_pred_reg_decoded[i] [N,Tp,h,w,2] ([] for unused scales, :170-171) and
-    beam_outputs = [logits [N,B,Tp,V], ids [N,B,Tp], logprobs [N,B]] or None (:276)."""
+    beam_outputs = [logits [N,B,Tp,V], ids [N,B,Tp], logprobs [N,B]] or None (:276).
+    on_output(name, index, tensor) is called as soon as a fetched tensor is complete on the current stream, so a
+    caller can start its device->host copy on another stream while the remaining branches still run."""
     cfg = self.cfg
+    emit = on_output if on_output is not None else (lambda *a: None)
     # raw_rnn runs until `time >= pred_length` (code/pred_models.py:347,:520): the rollout length is the
     # FED pred_length (multifuture_inference.py feeds max_pred_lengths[idx], :311), not config.pred_len
     tp = int(pred_len) if pred_len else cfg.pred_len
@@ -325,17 +329,60 @@ class ConvRNNEngine(object):
                                                           means[i], tp)
         out["beam_outputs"] = [logits, ids, logprobs]
         dec = logits[:, 0].reshape(n, tp, h, w, 1)                      # :799-803
+        for j, t in enumerate(out["beam_outputs"]):
+          emit("beam_outputs", j, t)
       else:
         lg, _ = self.decode_class_greedy(i, c_e, h_e, labels_t[-1].contiguous(), means[i], tp)
         dec = lg.permute(1, 0, 2).reshape(n, tp, h, w, 1)
+      emit("grid_pred_decoded", i, dec)
       # regression branch
       xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad)
       c_r, _ = self.encode_reg(i, obs_reg_t, xh_reg[0])
       offs = self.decode_reg(i, c_r, obs_reg_t[-1], tp, xh_reg)
       reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)
+      emit("grid_pred_reg_decoded", i, reg)
       out["grid_pred_decoded"].append(dec)
       out["grid_pred_reg_decoded"].append(reg)
       out.setdefault("_offs", {})[i] = offs           # engine layout [Tp,N,HW,2], for decode_trajectories
+    return out
+
+  # ------------------------------------------------------------------ CUDA-graph replay of forward()
+  @staticmethod
+  def _flat_feeds(feeds):
+    items = [("scene_feat", feeds["scene_feat"]), ("obs_scene", feeds["obs_scene"])]
+    for name in ("grid_obs_labels", "grid_obs_regress"):
+      for i, t in enumerate(feeds[name]):
+        if t is not None:
+          items.append(("%s/%d" % (name, i), t))
+    return items
+
+  def forward_graph(self, feeds, pred_len=None):
+    """forward() captured once per feed signature (shapes, dtypes, rollout length) into a CUDA graph and replayed:
+    a forward is 120-950 kernel launches with no host-side data dependence (the beam loop has a fixed trip count and
+    parents travel as device row maps), so at small batches - where the ~20 us the host spends per launch exceeds
+    the kernels' run time - one graph launch replaces them.  Bit-identical to forward().  The returned tensors
+    are the graph's static outputs: they are overwritten by the next replay of the same signature."""
+    tp = int(pred_len) if pred_len else self.cfg.pred_len
+    flat = self._flat_feeds(feeds)
+    key = (tp,) + tuple((k, tuple(t.shape), t.dtype) for k, t in flat)
+    ent = self._graphs.get(key)
+    if ent is None:
+      if self.cell_events is not None:
+        raise RuntimeError("forward_graph: per-launch event recording (cell_events) is an eager-mode feature")
+      static = dict(scene_feat=feeds["scene_feat"].clone(), obs_scene=feeds["obs_scene"].clone(),
+                    grid_obs_labels=[None if t is None else t.clone() for t in feeds["grid_obs_labels"]],
+                    grid_obs_regress=[None if t is None else t.clone() for t in feeds["grid_obs_regress"]])
+      self.forward(static, tp)        # eager pass: persistent buffers, kernel attributes, lazy caches
+      torch.cuda.synchronize(self.device)
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph):
+        out = self.forward(static, tp)
+      ent = (graph, static, out)
+      self._graphs[key] = ent
+    graph, static, out = ent
+    for (_, dst), (_, src) in zip(self._flat_feeds(static), flat):
+      dst.copy_(src, non_blocking=True)
+    graph.replay()
     return out
 
   def grid_centers(self, i, video_h=1080, video_w=1920):

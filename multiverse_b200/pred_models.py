@@ -284,24 +284,74 @@ class Model(object):
     tr = None
     if any(isinstance(h, Handle) and h.name in train_names for h in handles):
       tr = self._train_step(feed, apply=any(isinstance(h, Handle) and h.name == "train_op" for h in handles))
-    res = self._engine_forward(feed) if need_fwd else None
+    fwd_names = ("grid_pred_decoded", "grid_pred_reg_decoded", "beam_outputs")
+    host = self._engine_forward(feed, {(h.name, h.index) for h in handles if isinstance(h, Handle)
+                                        and h.kind == "fetch" and h.name in fwd_names}) if need_fwd else None
     out = []
     for h in handles:
       if isinstance(h, tf.Variable):
         out.append(h.eval())
       elif h.name in train_names:
         out.append(tr[h.name] if h.index is None else tr[h.name][h.index])
-      elif h.name == "beam_outputs":
-        out.append(res["beam_outputs"][h.index].cpu().numpy())
       elif h.kind == "fetch":
-        out.append(res[h.name][h.index].cpu().numpy())
+        out.append(host[(h.name, h.index)])
       else:
         raise ValueError("cannot fetch %r" % (h,))
     return out
 
-  def _engine_forward(self, feed):
+  def _engine_forward(self, feed, wanted):
+    """One engine forward; every requested fetch is copied to pinned host memory on a side stream as soon as the
+    engine reports it complete (the beam logits, 90 % of the fetched bytes, travel while the regression branch
+    still computes), and comes back as a numpy array that owns its pinned block."""
+    import torch
     eng = self._ensure_engine()
-    return eng.forward(self._device_feeds(feed), pred_len=self._fed_pred_len(feed))
+    dev = eng.device
+    if getattr(self, "_copy_stream", None) is None:
+      self._copy_stream = torch.cuda.Stream(device=dev)
+    side, host = self._copy_stream, {}
+
+    def on_output(name, index, t):
+      if (name, index) not in wanted or not torch.is_tensor(t):
+        return
+      t = t.contiguous()
+      side.wait_event(torch.cuda.current_stream(dev).record_event())
+      with torch.cuda.stream(side):
+        dst = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        dst.copy_(t, non_blocking=True)
+      t.record_stream(side)
+      host[(name, index)] = dst
+
+    with torch.cuda.device(dev):
+      feeds, tp = self._device_feeds(feed), self._fed_pred_len(feed)
+      if self._launch_bound(feeds):
+        # small batch: the host cannot launch ~10^3 kernels as fast as the GPU runs them -> one graph replay,
+        # then the copies (the static outputs are consumed before the next replay)
+        out = eng.forward_graph(feeds, pred_len=tp)
+        for i in range(len(self.config.scene_grids)):
+          on_output("grid_pred_decoded", i, out["grid_pred_decoded"][i])
+          on_output("grid_pred_reg_decoded", i, out["grid_pred_reg_decoded"][i])
+        for j, t in enumerate(out["beam_outputs"] or []):
+          on_output("beam_outputs", j, t)
+      else:
+        eng.forward(feeds, pred_len=tp, on_output=on_output)
+      side.synchronize()
+    res = {k: v.numpy() for k, v in host.items()}
+    for k in wanted:
+      if k not in res:
+        if k[0] in ("grid_pred_decoded", "grid_pred_reg_decoded"):
+          res[k] = []                                   # unused scale (:170-171)
+        else:
+          raise ValueError("fetch %s[%s] is not produced by this configuration" % k)
+    return res
+
+  def _launch_bound(self, feeds):
+    """CUDA-graph replay (ConvRNNEngine.forward_graph) when a forward is host-launch bound: fewer than
+    MVB_GRAPH_MAX_ROWS (default 2000) sample rows x beams; MVB_CUDA_GRAPH=0/1 forces eager / graph."""
+    mode = os.environ.get("MVB_CUDA_GRAPH", "")
+    if mode in ("0", "1"):
+      return mode == "1"
+    rows = int(feeds["obs_scene"].shape[0]) * (self.config.beam_size if self.config.use_beam_search else 1)
+    return rows <= int(os.environ.get("MVB_GRAPH_MAX_ROWS", "2000"))
 
   def _fed_pred_len(self, feed):
     """Rollout length = the fed pred_length (raw_rnn's stop condition, :347/:520)."""
@@ -402,10 +452,13 @@ class Model(object):
   def decode(self, feed):
     """Whole rollout for a feed dict (grid_decoder / grid_decoder_beam_search, :311-806):
     returns (grid_pred_decoded, grid_pred_reg_decoded, beam_outputs) as numpy."""
-    res = self._engine_forward(feed)
-    npy = lambda t: t.cpu().numpy() if hasattr(t, "cpu") else t
-    return ([npy(t) for t in res["grid_pred_decoded"]], [npy(t) for t in res["grid_pred_reg_decoded"]],
-            None if res["beam_outputs"] is None else [npy(t) for t in res["beam_outputs"]])
+    ns = len(self.config.scene_grids)
+    wanted = {(nm, i) for nm in ("grid_pred_decoded", "grid_pred_reg_decoded") for i in range(ns)}
+    if self.config.use_beam_search:
+      wanted |= {("beam_outputs", j) for j in range(3)}
+    res = self._engine_forward(feed, wanted)
+    return ([res[("grid_pred_decoded", i)] for i in range(ns)], [res[("grid_pred_reg_decoded", i)] for i in range(ns)],
+            [res[("beam_outputs", j)] for j in range(3)] if self.config.use_beam_search else None)
 
 
 def _engine_config(config):

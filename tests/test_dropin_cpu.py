@@ -20,6 +20,12 @@ REF = "/root/reference/code"
 have_ref = os.path.exists(os.path.join(REF, "pred_utils.py"))
 
 
+def as_host(out, wanted):
+  """Model._engine_forward's contract: {(fetch name, index): numpy array (or [] for an unused scale)}."""
+  conv = lambda t: t.numpy() if hasattr(t, "numpy") else t
+  return {k: conv(out[k[0]][k[1]]) for k in wanted}
+
+
 @pytest.fixture()
 def dropin(monkeypatch):
   monkeypatch.syspath_prepend(DROPIN)
@@ -156,7 +162,7 @@ def test_reference_test_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, ca
 
   calls = []
 
-  def fake_forward(self, feed):
+  def fake_forward(self, feed, wanted):
     import torch
     n, tp = self.N, self.config.pred_len
     calls.append(feed)
@@ -167,7 +173,7 @@ def test_reference_test_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, ca
       else:
         out["grid_pred_decoded"].append(torch.zeros(n, tp, h, w, 1))
         out["grid_pred_reg_decoded"].append(torch.zeros(n, tp, h, w, 2))
-    return out
+    return as_host(out, wanted)
 
   monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
   ref_test.main(args)
@@ -215,7 +221,7 @@ def test_reference_train_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, c
     return dict(loss=np.float32(1.0 / (1 + len(steps))), wd_loss=np.float32(0.1), train_op=None,
                 classification_loss={0: np.float32(0.5)}, regression_loss={0: np.float32(0.4)})
 
-  def fake_forward(self, feed):
+  def fake_forward(self, feed, wanted):
     import torch
     n, tp = self.N, self.config.pred_len
     out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
@@ -223,7 +229,7 @@ def test_reference_train_py_flow_runs_unchanged(dropin, tmp_path, monkeypatch, c
       ok = self.config.use_grids[i]
       out["grid_pred_decoded"].append(torch.zeros(n, tp, h, w, 1) if ok else [])
       out["grid_pred_reg_decoded"].append(torch.zeros(n, tp, h, w, 2) if ok else [])
-    return out
+    return as_host(out, wanted)
 
   monkeypatch.setattr(impl.Model, "_train_step", fake_train_step)
   monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
@@ -291,15 +297,15 @@ def test_reference_multifuture_inference_pieces_run_unchanged(dropin, tmp_path, 
                   scene_feats=f["scene_feat"], max_pred_lengths=[12, 17])
     seen = []
 
-    def fake_forward(self, feed):
+    def fake_forward(self, feed, wanted):
       import torch
       tp = self._fed_pred_len(feed)
       seen.append(tp)
       h, w = self.config.scene_grids[0]
-      return dict(grid_pred_decoded=[torch.zeros(1, tp, h, w, 1), []],
-                  grid_pred_reg_decoded=[torch.zeros(1, tp, h, w, 2), []],
-                  beam_outputs=[torch.zeros(1, 20, tp, h * w), torch.zeros(1, 20, tp, dtype=torch.int32),
-                                torch.zeros(1, 20)])
+      return as_host(dict(grid_pred_decoded=[torch.zeros(1, tp, h, w, 1), []],
+                          grid_pred_reg_decoded=[torch.zeros(1, tp, h, w, 2), []],
+                          beam_outputs=[torch.zeros(1, 20, tp, h * w), torch.zeros(1, 20, tp, dtype=torch.int32),
+                                        torch.zeros(1, 20)]), wanted)
 
     monkeypatch.setattr(impl.Model, "_engine_forward", fake_forward)
     for i in range(2):

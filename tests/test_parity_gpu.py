@@ -413,3 +413,27 @@ def test_beam_step_topk_equals_full_rank_count(dev, monkeypatch, first, zero, di
   _, idx = R.top_k_sorted(cand, b)
   agree = np.mean((idx % v) == res[1][1])
   assert agree > 0.9
+
+
+@pytest.mark.parametrize("name", ["greedy_two_scale", "beam_k20_diverse"])
+def test_forward_graph_replay_is_bit_identical(dev, name):
+  """ConvRNNEngine.forward_graph (one CUDA-graph replay per forward) == forward() launch by launch, also when the
+  replay runs on feeds other than the ones it was captured with."""
+  from multiverse_b200.engine import ConvRNNEngine
+  over, seed = cases.ROLLOUTS[name]
+  cfg = R.default_config(**over)
+  w = R.make_weights(cfg, seed)
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  fa, fb = to_dev(R.make_inputs(cfg, seed), dev), to_dev(R.make_inputs(cfg, seed + 100), dev)
+  eng.forward_graph(fa)                                        # capture on feeds A
+  for f in (fb, fa):
+    want = eng.forward(f)
+    want = [t.clone() for t in want["grid_pred_decoded"] + want["grid_pred_reg_decoded"] + (want["beam_outputs"] or [])
+            if torch.is_tensor(t)]
+    got = eng.forward_graph(f)
+    got = [t for t in got["grid_pred_decoded"] + got["grid_pred_reg_decoded"] + (got["beam_outputs"] or [])
+           if torch.is_tensor(t)]
+    assert len(got) == len(want) and len(got) >= 2
+    for a, b in zip(got, want):
+      assert torch.equal(a, b)
+  assert len(eng._graphs) == 1
