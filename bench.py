@@ -240,9 +240,10 @@ def run_train(args, wl):
   line = dict(metric="training trajectories/sec (obs8->pred12, fwd+bwd+update)", value=gb * args.steps / (ms_total * 1e-3),
               unit="trajectories/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
               ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
-              dtype="bf16x%d planes -> f32 accumulate" % args.planes, data="synthetic",
+              dtype="f32", data="synthetic",
               config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
-                          micro_batch=mb, parallelism="data-parallel x%d, NCCL all-reduce of %.1f MB fp32 grads"
+                          micro_batch=mb, arithmetic="fp32-grade: bf16x%d operand planes, fp32 accumulate" % args.planes,
+                          parallelism="data-parallel x%d, NCCL all-reduce of %.1f MB fp32 grads"
                           % (world, eng.flat_grad.numel() * 4 / 1e6),
                           l2="activation store >> 126 MB L2, no flush needed"),
               clocks=clocks,
@@ -448,11 +449,13 @@ def main():
 
   line = dict(metric=METRIC, value=value, unit="trajectories/s", n_gpus=world, steps=args.steps,
               warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
-              scaling="strong", vs_baseline=None, dtype="bf16x%d planes -> f32 accumulate" % args.planes,
+              scaling="strong", vs_baseline=None, dtype="f32",
               data="synthetic",
               config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
                           obs_len=cfg.obs_len, pred_len=cfg.pred_len, beam=cfg.beam_size,
                           parallelism="trajectory-sharded x%d, no collective" % world,
+                          arithmetic="fp32-grade: operands split into %d bf16 planes, %d tcgen05 passes per product, "
+                                     "fp32 TMEM accumulate, fp32 gates/state" % (args.planes, args.planes * (args.planes + 1) // 2),
                           l2="working set per step (%.1f GB of state) >> 126 MB L2, no flush needed"
                              % (rows * (h0 + 1) * (w0 + 1) * 256 * 4 * 3 / 1e9),
                           gflop_per_trajectory=flops_per_trajectory(cfg) / 1e9),
