@@ -83,6 +83,15 @@ int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, co
                                  const int32_t* row_map, float* c_out, float* h32_out, void* hp_out,
                                  int64_t hp_plane_stride, int cpad_out, int ch_off_out, int64_t NS, int H,
                                  int W, int cpad, int planes, float forget_bias, void* stream);
+/* First K-row step of the beam decoder (pred_models.py:611-666 right after the first selection): the K = fanout
+ * children of a sample share their parent - the same graph-attended h and the same c - and differ only in the
+ * selected cell ids[s*K + k], i.e. in the folded table rows.  The GEMM runs once per PARENT row (xh_planes, c_in:
+ * NS sample rows) and the epilogue emits the K children (c_out, h32_out: NS*K sample rows, child-major within a
+ * sample): 1/K of the MMAs, identical values. */
+int mvb_convlstm_cell_fwd_onehot_fanout(const void* xh_planes, const void* w_planes, const float* table_B,
+                                        const float* table_T2, const int32_t* ids, const float* c_in,
+                                        float* c_out, float* h32_out, int64_t NS, int fanout, int H, int W,
+                                        int cpad, int planes, float forget_bias, void* stream);
 
 /* ---- a13: BPTT step of the cell (Trainer, pred_models.py:1636-1742; tf.gradients :1698 through
  *      ConvLSTMCell) ------------------------------------------------------------------------ */

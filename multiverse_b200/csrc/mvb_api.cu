@@ -117,7 +117,7 @@ int mvb_convlstm_cell_fwd(const void* xh_planes, const void* w_planes, const flo
                           void* stream) {
   return cell_fwd(xh_planes, w_planes, bias_packed, c_in, row_map, c_out, h32_out, hp_out,
                   hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
-                  nullptr, nullptr, nullptr, nullptr, S(stream));
+                  nullptr, nullptr, nullptr, nullptr, 1, S(stream));
 }
 int mvb_cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be,
                           int E, float* table_B, float* table_T2, void* stream) {
@@ -129,8 +129,15 @@ int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, co
                                  int64_t hp_plane_stride, int cpad_out, int ch_off_out, int64_t NS, int H,
                                  int W, int cpad, int planes, float forget_bias, void* stream) {
   return cell_fwd(xh_planes, w_planes, table_B, c_in, row_map, c_out, h32_out, hp_out, hp_plane_stride,
-                  cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias, nullptr, table_B, table_T2, ids,
+                  cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias, nullptr, table_B, table_T2, ids, 1,
                   S(stream));
+}
+int mvb_convlstm_cell_fwd_onehot_fanout(const void* xh_planes, const void* w_planes, const float* table_B,
+                                        const float* table_T2, const int32_t* ids, const float* c_in,
+                                        float* c_out, float* h32_out, int64_t NS, int fanout, int H, int W,
+                                        int cpad, int planes, float forget_bias, void* stream) {
+  return cell_fwd(xh_planes, w_planes, table_B, c_in, nullptr, c_out, h32_out, nullptr, 0, 0, 0, NS, H, W, cpad,
+                  planes, forget_bias, nullptr, table_B, table_T2, ids, fanout, S(stream));
 }
 
 int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
@@ -140,7 +147,7 @@ int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
                                 int planes, float forget_bias, void* stream) {
   return cell_fwd(xh_planes, w_planes, bias_packed, c_in, nullptr, c_out, h32_out, hp_out,
                   hp_plane_stride, cpad_out, ch_off_out, NS, H, W, cpad, planes, forget_bias,
-                  gates_out, nullptr, nullptr, nullptr, S(stream));
+                  gates_out, nullptr, nullptr, nullptr, 1, S(stream));
 }
 int mvb_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh,
                        const float* dc_in, void* dg_planes, int64_t plane_stride, float* dc_prev,

@@ -63,6 +63,8 @@ struct CellParams {
   const int* xf_ids;        // [NS] arg-max cell of every sample row
   int kb_begin;             // first k-block of the K loop (9 * number of skipped 32-channel chunks)
   int order;                // work order, see work_index()
+  int fanout;               // > 1 (x-fold only): every GEMM row is a parent whose K = fanout children differ only in
+                            // their one-hot input; the epilogue emits sample row smp*K + k for k < K (xf_ids [NS*K])
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
   long long hp_plane_stride;  // elements between planes of hp_out
   int cpad_out;             // row pitch of hp_out (elements)
@@ -208,7 +210,8 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
       bool valid = row < prm.R;
       long long src_row = row;
       const float* xfb = nullptr;      // x-fold: table row of this cell's border class (bias included)
-      const float* xft = nullptr;      // x-fold: table row of the offset to the arg-max cell, if within 5x5
+      int py = 0, px = 0, prem = 0;    // cell position and row offset inside its sample row
+      long long psmp = 0;
       if (valid) {
         const long long smp = row / g.S;
         const int rem = (int)(row - smp * g.S);
@@ -218,15 +221,17 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
         if (valid && prm.xf_B) {
           const int cy = y == 0 ? 0 : (y == g.H - 1 ? 2 : 1), cx = x == 0 ? 0 : (x == g.W - 1 ? 2 : 1);
           xfb = prm.xf_B + (cy * 3 + cx) * kGates;
-          const int a = prm.xf_ids[smp];
-          const int ay = a / g.W, ax = a - ay * g.W;
-          const int ry = y - ay, rx = x - ax;
-          if (ry >= -2 && ry <= 2 && rx >= -2 && rx <= 2) {
-            const int acy = ay == 0 ? 0 : (ay == g.H - 1 ? 2 : 1), acx = ax == 0 ? 0 : (ax == g.W - 1 ? 2 : 1);
-            xft = prm.xf_T2 + ((long long)(acy * 3 + acx) * 25 + (ry + 2) * 5 + (rx + 2)) * kGates;
-          }
         }
+        py = y; px = x; psmp = smp; prem = rem;
       }
+      // x-fold table row of this cell for the sample row whose arg-max cell is `a` (nullptr outside its 5x5)
+      auto xft_of = [&](int a) -> const float* {
+        const int ay = a / g.W, ax = a - ay * g.W;
+        const int ry = py - ay, rx = px - ax;
+        if (ry < -2 || ry > 2 || rx < -2 || rx > 2) return nullptr;
+        const int acy = ay == 0 ? 0 : (ay == g.H - 1 ? 2 : 1), acx = ax == 0 ? 0 : (ax == g.W - 1 ? 2 : 1);
+        return prm.xf_T2 + ((long long)(acy * 3 + acx) * 25 + (ry + 2) * 5 + (rx + 2)) * kGates;
+      };
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BLOCK_N;
@@ -253,7 +258,12 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         tmem_ld_wait();
         if (valid) {
-          const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
+         const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
+#pragma unroll 1
+         for (int k = 0; k < prm.fanout; ++k) {      // 1 pass, or one per child of this parent row
+          const long long osmp = prm.fanout > 1 ? psmp * prm.fanout + k : psmp;
+          const long long orow = prm.fanout > 1 ? osmp * g.S + prem : row;
+          const float* xft = prm.xf_B ? xft_of(prm.xf_ids[osmp]) : nullptr;
           const float* tptr = xft ? xft + nt * BLOCK_N + j0 : nullptr;
           float cn[16], hn[16];
 #pragma unroll
@@ -277,7 +287,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
             }
           }
           if (prm.gates_out) {
-            float* gp = prm.gates_out + row * kGates + nt * BLOCK_N + j0;
+            float* gp = prm.gates_out + orow * kGates + nt * BLOCK_N + j0;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               reinterpret_cast<uint4*>(gp + 0 * TILE_CH)[v] = make_uint4(gi[4 * v], gi[4 * v + 1], gi[4 * v + 2], gi[4 * v + 3]);
@@ -286,11 +296,11 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
               reinterpret_cast<uint4*>(gp + 3 * TILE_CH)[v] = make_uint4(go[4 * v], go[4 * v + 1], go[4 * v + 2], go[4 * v + 3]);
             }
           }
-          float4* co = reinterpret_cast<float4*>(prm.c_out + row * kHidden + ch0);
+          float4* co = reinterpret_cast<float4*>(prm.c_out + orow * kHidden + ch0);
 #pragma unroll
           for (int v = 0; v < 4; ++v) co[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
           if (prm.h32_out) {
-            float4* ho = reinterpret_cast<float4*>(prm.h32_out + row * kHidden + ch0);
+            float4* ho = reinterpret_cast<float4*>(prm.h32_out + orow * kHidden + ch0);
 #pragma unroll
             for (int v = 0; v < 4; ++v) ho[v] = make_float4(hn[4 * v], hn[4 * v + 1], hn[4 * v + 2], hn[4 * v + 3]);
           }
@@ -307,11 +317,12 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
             for (int p = 0; p < P; ++p) {
               uint4* po = reinterpret_cast<uint4*>(prm.hp_out + p * prm.hp_plane_stride +
-                                                   row * prm.cpad_out + prm.ch_off_out + ch0);
+                                                   orow * prm.cpad_out + prm.ch_off_out + ch0);
               po[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
               po[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
             }
           }
+         }
         }
       }
       tc_fence_before();
@@ -459,8 +470,10 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
              float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
-             cudaStream_t stream) {
+             int fanout, cudaStream_t stream) {
   MVB_REQUIRE(P >= 1 && P <= 3, "cell_fwd: planes P=%d not in {1,2,3}", P);
+  MVB_REQUIRE(fanout <= 1 || (xf_B && xf_T2 && xf_ids && !gates_out && !row_map && !hp_out),
+              "cell_fwd: fanout=%d needs the x-fold tables and no row_map / gates_out / hp_out", fanout);
   MVB_REQUIRE(cpad % BLOCK_K == 0 && cpad >= kHidden + BLOCK_K, "cell_fwd: cpad=%d must be a multiple of 32 and >= 288", cpad);
   MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
   MVB_REQUIRE(xh_planes && w_planes && bias && c_out, "cell_fwd: null pointer");
@@ -488,6 +501,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   prm.gates_out = gates_out;
   prm.xf_B = xf_B; prm.xf_T2 = xf_T2; prm.xf_ids = xf_ids;
   prm.kb_begin = 0;
+  prm.fanout = fanout > 1 ? fanout : 1;
   // measured on the K=20 beam step: order 1 keeps the DRAM reads at 1.05x algorithmic with the CTA-pair clusters
   // (order 0: 1.39x) and is 3 % faster; MVB_CELL_ORDER=0 selects the strided order for A/B runs.
   static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : 1; }();

@@ -131,6 +131,15 @@ class ConvRNNEngine(object):
     e1.record()
     self.cell_events.append((tag, (args[8], args[9], args[10]), e0, e1))   # (h, w, ns)
 
+  def _cell_fanout(self, tag, *args, **kw):
+    if self.cell_events is None:
+      return ops.cell_fwd_onehot_fanout(*args, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.cell_fwd_onehot_fanout(*args, **kw)
+    e1.record()
+    self.cell_events.append((tag, (args[7], args[8], args[9]), e0, e1))   # (h, w, ns)
+
   # ------------------------------------------------------------------ pieces
   def scene_cnn(self, scene_feat, obs_scene):
     """code/pred_models.py:146-165 on the unique frames; returns per-scale [F,h,w,64] maps and
@@ -247,7 +256,6 @@ class ConvRNNEngine(object):
     step_par = torch.empty((pred_len, n, b), dtype=torch.int32, device=dev)
     scores = [torch.zeros((n, b), dtype=torch.float32, device=dev) for _ in range(2)]
     row_map = torch.empty((ns,), dtype=torch.int32, device=dev)
-    tile_map = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(b).contiguous()
     xf = sw.dec_class_xf
     # time = 0 (:497-502, :527-531): the reference tiles the encoder state and the last observed cell K times, so
     # all K beams carry identical rows until the first selection (which looks at beam 0 only, :569-573).  That
@@ -278,10 +286,17 @@ class ConvRNNEngine(object):
       if time == pred_len:
         break
       nxt = xh[time % 2]
-      rm = tile_map if time == 1 else row_map       # time 1: every child's parent is its sample's single t0 row
-      ops.gnn_attend_fwd(h_src, scene_mean, nxt, h, w, ns, beam=b, row_map=rm)
-      self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c_src, c[1 - cur_c], h32,
-                        None, h, w, ns, row_map=rm)
+      if time == 1:
+        # every child's parent is its sample's single t0 row: the K children share the graph-attended h and c and
+        # differ only in the selected cell, i.e. in the folded table rows -> attention and GEMM once per sample,
+        # the cell epilogue fans the K children out (ops.cell_fwd_onehot_fanout; 1/K of the step's MMAs)
+        ops.gnn_attend_fwd(h32_t0, scene_mean, xh1[1], h, w, n, beam=1, row_map=None)
+        self._cell_fanout("beam_fanout", xh1[1], sw.dec_class, xf, step_ids[0].view(-1), c_t0, c[1 - cur_c], h32,
+                          h, w, n, b)
+      else:
+        ops.gnn_attend_fwd(h_src, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
+        self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c_src, c[1 - cur_c], h32,
+                          None, h, w, ns, row_map=row_map)
       cur_c = 1 - cur_c
       h_src, c_src = h32, c[cur_c]
     out_ids = torch.empty((n, b, pred_len), dtype=torch.int32, device=dev)

@@ -115,6 +115,12 @@ def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns
             packed.cpad, packed.planes, float(forget_bias), _stream())
 
 
+def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, fanout, forget_bias=1.0):
+  """First K-row beam step: GEMM on the `ns` parent rows, epilogue emits ns*fanout child rows (ids [ns*fanout])."""
+  _lib.call("mvb_convlstm_cell_fwd_onehot_fanout", _p(xh), _p(packed.w), _p(xf.B), _p(xf.T2), _p(ids), _p(c_in),
+            _p(c_out), _p(h32_out), ns, fanout, h, w, packed.cpad, packed.planes, float(forget_bias), _stream())
+
+
 def nhwc_to_planes(src, xh, ch_off, h, w, comp=False):
   ns, c = src.shape[0], src.shape[-1]
   _lib.call("mvb_nhwc_to_planes", _p(src), _p(xh), xh.stride(0), xh.shape[2], ch_off, ns, h, w,

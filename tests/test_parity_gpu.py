@@ -437,3 +437,39 @@ def test_forward_graph_replay_is_bit_identical(dev, name):
     for a, b in zip(got, want):
       assert torch.equal(a, b)
   assert len(eng._graphs) == 1
+
+
+def test_cell_onehot_fanout_equals_tiled_rows(dev):
+  """mvb_convlstm_cell_fwd_onehot_fanout (GEMM once per parent row, epilogue emits the K children that differ only
+  in their selected cell) is bit-identical to the K-times tiled launch through a row map - what
+  grid_decoder_beam_search does at the first K-row step (code/pred_models.py:611-666) - and matches the oracle."""
+  from multiverse_b200 import ops
+  d = cases.cell_case("dec_cx32"); hd = cases.head_case()
+  n, k, h, w = 3, 4, 6, 5
+  rng = np.random.default_rng(19)
+  hh = np.tanh(rng.standard_normal((n, h, w, 256))).astype(np.float32)
+  c = rng.standard_normal((n, h, w, 256)).astype(np.float32)
+  ids = rng.integers(0, h * w, size=(n * k,)).astype(np.int32)
+  ids[:4] = [0, w - 1, (h - 1) * w, h * w - 1]
+  We, be = hd["We1"], hd["be"]
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), 2)
+  xf = ops.XFold(T(d["kernel"], dev), T(d["biases"], dev), T(We, dev), T(be, dev))
+  xh_p = ops.alloc_xh(n, h, w, pk.cpad, 2, dev); ops.nhwc_to_planes(T(hh, dev), xh_p, pk.cxp, h, w)
+  c_p = ops.alloc_state(n, h, w, dev); ops.nhwc_to_halo(T(c, dev), c_p, h, w)
+  # fan-out launch
+  c_f = ops.alloc_state(n * k, h, w, dev); h_f = ops.alloc_state(n * k, h, w, dev)
+  ops.cell_fwd_onehot_fanout(xh_p, pk, xf, T(ids, dev), c_p, c_f, h_f, h, w, n, k)
+  # tiled launch: every child row carries its parent's planes; c through the row map
+  hh_t = np.repeat(hh, k, axis=0)
+  xh_t = ops.alloc_xh(n * k, h, w, pk.cpad, 2, dev); ops.nhwc_to_planes(T(hh_t, dev), xh_t, pk.cxp, h, w)
+  rm = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(k).contiguous()
+  c_t = ops.alloc_state(n * k, h, w, dev); h_t = ops.alloc_state(n * k, h, w, dev)
+  ops.cell_fwd_onehot(xh_t, pk, xf, T(ids, dev), c_p, c_t, h_t, None, h, w, n * k, row_map=rm)
+  assert torch.equal(c_f, c_t) and torch.equal(h_f, h_t)
+  oh = R.one_hot(ids, h * w, np.float64).reshape(n * k, h, w, 1)
+  x = R.grid_emb(oh, We.astype(np.float64), be.astype(np.float64))
+  c_ref, h_ref = R.convlstm_cell(x, np.repeat(c, k, axis=0).astype(np.float64), hh_t.astype(np.float64),
+                                 d["kernel"].astype(np.float64), d["biases"].astype(np.float64))
+  co = torch.empty((n * k, h, w, 256), device=dev); ho = torch.empty((n * k, h, w, 256), device=dev)
+  ops.halo_to_nhwc(c_f, co, h, w); ops.halo_to_nhwc(h_f, ho, h, w)
+  assert rel(co.cpu().numpy(), c_ref) < TIGHT and rel(ho.cpu().numpy(), h_ref) < TIGHT
