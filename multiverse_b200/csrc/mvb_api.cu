@@ -99,7 +99,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 3; }
+int mvb_abi_version(void) { return 4; }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 
