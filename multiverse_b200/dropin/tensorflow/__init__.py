@@ -164,7 +164,8 @@ def _index_file(dirname):
 class _Train(object):
   class Saver(object):
     """Writes `<path>-<step>.npz` keyed by the TF variable names plus a TF-style `checkpoint`
-    index file; restore accepts those files (TF bundle import is SURVEY.md §8 row f-2)."""
+    index file; restore accepts those files and TensorFlow's own checkpoint bundles
+    (`<path>.index` + `<path>.data-*`, read by tensorflow/_bundle.py - SURVEY.md §8 row f-2)."""
 
     def __init__(self, var_list=None, max_to_keep=5):
       self.var_list = var_list
@@ -191,14 +192,22 @@ class _Train(object):
       return path
 
     def restore(self, sess, save_path):
+      from . import _bundle
       f = save_path if save_path.endswith(".npz") else save_path + ".npz"
-      if not os.path.exists(f):
-        raise IOError("checkpoint %s not found (TF bundle files are not readable here)" % f)
-      data = np.load(f)
+      if os.path.exists(f):
+        data = np.load(f)
+      elif _bundle.is_bundle(save_path):
+        f = save_path + ".index"
+        data = _bundle.read_bundle(save_path, names={v.name.split(":")[0] for v in self._vars()})
+      else:
+        raise IOError("checkpoint %s(.npz | .index) not found" % save_path)
       for v in self._vars():
         key = v.name.split(":")[0]
         if key not in data:
-          raise KeyError("variable %s missing from %s" % (key, f))
+          names = sorted(data.keys() if hasattr(data, "keys") else data.files)
+          tail = key.split("/")[-1]
+          near = [n for n in names if n.split("/")[-1] == tail][:8]
+          raise KeyError("variable %s missing from %s (%d tensors; same leaf name: %s)" % (key, f, len(names), near))
         v.assign(data[key])
 
   @staticmethod
@@ -209,7 +218,10 @@ class _Train(object):
     with open(idx) as f:
       for line in f:
         if line.startswith("model_checkpoint_path"):
-          return _CheckpointState(line.split(":", 1)[1].strip().strip('"'))
+          path = line.split(":", 1)[1].strip().strip('"')
+          if not os.path.isabs(path):                     # TF resolves relative entries against the directory
+            path = os.path.join(dirname, path)
+          return _CheckpointState(path)
     return None
 
 

@@ -318,3 +318,45 @@ def test_reference_multifuture_inference_pieces_run_unchanged(dropin, tmp_path, 
       beam_logits, beam_grid_ids, beam_logprobs = beam_outputs
       assert beam_grid_ids.shape == (1, 20, pred_len) and beam_logits.shape == (1, 20, pred_len, 648)
     assert seen == [12, 17]          # the rollout length follows the FED pred_length, not config.pred_len
+
+
+def test_tf_checkpoint_bundle_reader(dropin, tmp_path):
+  """`Saver.restore` reads TensorFlow's tensor-bundle checkpoints (`.index` table +
+  `.data-00000-of-00001`).  The files here come from the writer in tensorflow/_bundle.py, which follows the same
+  published format (no TensorFlow-produced checkpoint exists in this container)."""
+  tf, pm = dropin
+  from tensorflow import _bundle
+  assert _bundle.crc32c(b"123456789") == 0xE3069283                 # the CRC-32C check value
+  rng = np.random.default_rng(3)
+  tensors = {"person_pred/scene_conv1/W": rng.standard_normal((3, 3, 11, 64)).astype(np.float32),
+             "person_pred/scene_conv1/b": rng.standard_normal(64).astype(np.float32),
+             "person_pred/scene_conv1/W/Adadelta": np.zeros((3, 3, 11, 64), np.float32),
+             "global_step": np.asarray(1234, dtype=np.int64),
+             "person_pred/ids": np.arange(7, dtype=np.int32)}
+  for i in range(40):                                               # several table blocks, shared key prefixes
+    tensors["person_pred/filler_%02d/kernel" % i] = rng.standard_normal((i % 3 + 1, 5)).astype(np.float32)
+  prefix = str(tmp_path / "model" / "save-best-1234")
+  _bundle.write_bundle(prefix, tensors)
+  header, entries = _bundle.read_index(prefix)
+  assert header["num_shards"] == 1 and set(entries) == set(tensors)
+  assert entries["person_pred/scene_conv1/W"]["shape"] == (3, 3, 11, 64) and entries["global_step"]["shape"] == ()
+  back = _bundle.read_bundle(prefix)
+  for k, v in tensors.items():
+    assert back[k].dtype == v.dtype and np.array_equal(back[k], v), k
+  # through the Saver, the way pred_utils.initialize restores a released model (code/pred_utils.py:186-198)
+  (tmp_path / "model" / "checkpoint").write_text('model_checkpoint_path: "save-best-1234"\n')
+  ckpt = tf.train.get_checkpoint_state(str(tmp_path / "model"))
+  assert ckpt.model_checkpoint_path == prefix
+  w = tf.Variable("person_pred/scene_conv1/W", (3, 3, 11, 64))
+  b = tf.Variable("person_pred/scene_conv1/b", (64,))
+  tf.train.Saver([w, b]).restore(None, ckpt.model_checkpoint_path)
+  assert np.array_equal(w.eval(), tensors["person_pred/scene_conv1/W"])
+  assert np.array_equal(b.eval(), tensors["person_pred/scene_conv1/b"])
+  missing = tf.Variable("person_pred/not_there", (3,))
+  with pytest.raises(KeyError):
+    tf.train.Saver([missing]).restore(None, prefix)
+  # a flipped byte in the index is detected by the block checksums
+  raw = bytearray(open(prefix + ".index", "rb").read()); raw[10] ^= 0xFF
+  open(prefix + ".index", "wb").write(bytes(raw))
+  with pytest.raises(IOError):
+    _bundle.read_index(prefix)
