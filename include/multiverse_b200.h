@@ -248,6 +248,12 @@ int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
                        const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,
                        int B, int Tp, int V, void* stream);
 
+/* ---- f-1 (next row): feed generation on the device (multifuture_inference.py:115-156, preprocess.py:436-475):
+ *      traj fp64 [NT,2] frame pixels, centers fp64 [H*W,2] (the caller's scene_grid_centers) ->
+ *      labels int32 [NT] (cell of every point), regress fp32 [NT,H,W,2] (point - centre of every cell). */
+int mvb_traj_to_grid(const double* traj, const double* centers, double h_gap, double w_gap, int32_t* labels,
+                     float* regress, int64_t NT, int H, int W, void* stream);
+
 /* ---- f-3 (next row): post-decode on the device (multifuture_inference.py:504-517,
  *      pred_utils.py:460-492): out[n,k,t] = centers[ids[n,k,t]] + offsets[t,n,ids[n,k,t]].
  *      ids int32 [N,K,Tp]; offsets fp32 [Tp,N,V,2] (mvb_head_reg_fwd layout); centers fp32 [V,2]. */

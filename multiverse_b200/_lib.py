@@ -57,6 +57,7 @@ SIGNATURES = {
     "mvb_emb_onehot_fwd": [_vp, _vp, _vp, _i, _vp, _i64, _i, _i64, _i, _i, _i, _vp],
     "mvb_emb_dense_fwd": [_vp, _vp, _vp, _i, _vp, _i64, _i, _i64, _i, _i, _i, _vp],
     "mvb_beam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
+    "mvb_traj_to_grid": [_vp, _vp, C.c_double, C.c_double, _vp, _vp, _i64, _i, _i, _vp],
     "mvb_decode_trajectories": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_beam_backtrace": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
 }

@@ -99,7 +99,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 4; }
+int mvb_abi_version(void) { return 5; }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 
@@ -227,6 +227,10 @@ int mvb_nhwc_to_planes(const float* src, void* dst_planes, int64_t plane_stride,
                        void* stream) {
   return nhwc_to_planes(src, dst_planes, plane_stride, cpad, ch_off, NS, H, W, C, planes, comp,
                         S(stream));
+}
+int mvb_traj_to_grid(const double* traj, const double* centers, double h_gap, double w_gap, int32_t* labels,
+                     float* regress, int64_t NT, int H, int W, void* stream) {
+  return traj_to_grid(traj, centers, h_gap, w_gap, labels, regress, NT, H, W, S(stream));
 }
 int mvb_nhwc_to_halo(const float* src, float* dst, int64_t NS, int H, int W, int C, void* stream) {
   return nhwc_halo_copy(src, dst, NS, H, W, C, 0, S(stream));

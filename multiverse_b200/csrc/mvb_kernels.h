@@ -21,6 +21,8 @@ int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, 
 // mvb_layout.cu
 int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
                    long long NS, int H, int W, int C, int P, int comp, cudaStream_t stream);
+int traj_to_grid(const double* traj, const double* centers, double h_gap, double w_gap, int* labels,
+                 float* regress, long long NT, int H, int W, cudaStream_t stream);
 int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int C, int to_nhwc,
                    cudaStream_t stream);
 int enc_class_input(const float* scene_conv, const int* frame_idx, const int* label,

@@ -119,6 +119,43 @@ int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, i
   return MVB_OK;
 }
 
+// Feed generation on the device: what get_grid_input does per trajectory on the host
+// (code/multifuture_inference.py:115-156 == code/preprocess.py:436-475): cell index = ceil(x / gap) (0 -> 1) - 1 per
+// axis, offsets = point - centre of every cell.  Double arithmetic on the caller's float64 points and centres, so
+// labels are bit-identical to numpy's and the fp32 offsets equal numpy's float64 result cast to float32.
+__global__ void traj_to_grid_kernel(const double* __restrict__ traj, const double* __restrict__ centers,
+                                    double h_gap, double w_gap, int* __restrict__ labels,
+                                    float* __restrict__ regress, long long NT, int H, int W) {
+  const int hw = H * W;
+  const long long total = NT * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / hw;
+    const int cell = (int)(i - p * hw);
+    const double x = traj[2 * p], y = traj[2 * p + 1];
+    if (cell == 0) {
+      long long xi = (long long)ceil(x / w_gap), yi = (long long)ceil(y / h_gap);
+      if (xi == 0) xi = 1;
+      if (yi == 0) yi = 1;
+      labels[p] = (int)((yi - 1) * W + (xi - 1));
+    }
+    reinterpret_cast<float2*>(regress)[i] =
+        make_float2((float)(x - centers[2 * cell]), (float)(y - centers[2 * cell + 1]));
+  }
+}
+
+int traj_to_grid(const double* traj, const double* centers, double h_gap, double w_gap, int* labels,
+                 float* regress, long long NT, int H, int W, cudaStream_t stream) {
+  MVB_REQUIRE(traj && centers && labels && regress && NT > 0 && H > 0 && W > 0 && h_gap > 0 && w_gap > 0,
+              "traj_to_grid: bad args");
+  const long long total = NT * H * W;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  traj_to_grid_kernel<<<blocks, 256, 0, stream>>>(traj, centers, h_gap, w_gap, labels, regress, NT, H, W);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int C, int to_nhwc,
                    cudaStream_t stream) {
   MVB_REQUIRE(src && dst && NS > 0 && C > 0 && C % 4 == 0, "nhwc_halo_copy: bad args (C=%d must be a multiple of 4)", C);

@@ -400,6 +400,35 @@ class ConvRNNEngine(object):
     graph.replay()
     return out
 
+  def grid_feeds_from_traj(self, obs_traj, centers=None, video_h=1080, video_w=1920):
+    """Feed generation on the device: the observed trajectories fp64 [N,T,2] (frame
+    pixels; numpy or tensor) -> (grid_obs_labels, grid_obs_regress) lists per scale, i.e. what get_grid_input
+    builds per trajectory on the host (code/multifuture_inference.py:115-156) and what 99 % of the fed bytes are.
+    `centers[i]` fp64 [h,w,2]: the caller's args.scene_grid_centers; default = the reference's formula (:101-113)."""
+    import numpy as np
+    cfg = self.cfg
+    vh, vw = getattr(cfg, "video_h", video_h), getattr(cfg, "video_w", video_w)
+    traj = torch.as_tensor(obs_traj, dtype=torch.float64).to(self.device).contiguous()
+    n, t = traj.shape[0], traj.shape[1]
+    labels, regress = [], []
+    for i, (h, w) in enumerate(cfg.scene_grids):
+      if not cfg.use_grids[i]:
+        labels.append(None); regress.append(None)
+        continue
+      h_gap, w_gap = vh * 1.0 / h, vw * 1.0 / w
+      if centers is not None and centers[i] is not None:
+        c = np.asarray(centers[i], dtype=np.float64).reshape(h * w, 2)
+      else:
+        cx = np.cumsum([w_gap] * w) - w_gap / 2.0
+        cy = np.cumsum([h_gap] * h) - h_gap / 2.0
+        c = np.stack((np.tile(cx[None], (h, 1)), np.tile(cy[:, None], (1, w))), axis=-1).reshape(h * w, 2)
+      c_dev = torch.from_numpy(np.ascontiguousarray(c)).to(self.device)
+      lab = torch.empty((n, t), dtype=torch.int32, device=self.device)
+      reg = torch.empty((n, t, h, w, 2), dtype=torch.float32, device=self.device)
+      ops.traj_to_grid(traj, c_dev, h_gap, w_gap, lab, reg, h, w)
+      labels.append(lab); regress.append(reg)
+    return labels, regress
+
   def grid_centers(self, i, video_h=1080, video_w=1920):
     """Cell centres of scale i in frame pixels (code/multifuture_inference.py:101-113)."""
     h, w = self.cfg.scene_grids[i]

@@ -318,3 +318,9 @@ def decode_trajectories(ids, offs, centers, out):
   n, k, tp = ids.shape
   _lib.call("mvb_decode_trajectories", _p(ids), _p(offs), _p(centers), _p(out), n, k, tp, offs.shape[2],
             _stream())
+
+
+def traj_to_grid(traj, centers, h_gap, w_gap, labels, regress, h, w):
+  """traj fp64 [...,2], centers fp64 [h*w,2] -> labels int32 [...], regress fp32 [...,h,w,2]."""
+  _lib.call("mvb_traj_to_grid", _p(traj), _p(centers), float(h_gap), float(w_gap), _p(labels), _p(regress),
+            traj.numel() // 2, h, w, _stream())

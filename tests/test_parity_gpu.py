@@ -473,3 +473,23 @@ def test_cell_onehot_fanout_equals_tiled_rows(dev):
   co = torch.empty((n * k, h, w, 256), device=dev); ho = torch.empty((n * k, h, w, 256), device=dev)
   ops.halo_to_nhwc(c_f, co, h, w); ops.halo_to_nhwc(h_f, ho, h, w)
   assert rel(co.cpu().numpy(), c_ref) < TIGHT and rel(ho.cpu().numpy(), h_ref) < TIGHT
+
+
+def test_grid_feeds_from_traj_on_device(dev):
+  """§8 row f-1: labels and offsets generated on the device from fp64 trajectories are bit-identical to the host
+  computation of get_grid_input (code/multifuture_inference.py:115-156), including points on cell borders and at
+  the frame origin (ceil(0) -> cell 0)."""
+  from multiverse_b200.engine import ConvRNNEngine
+  cfg = R.default_config(batch_size=5)
+  w = R.make_weights(cfg, 2)
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  rng = np.random.default_rng(8)
+  traj = rng.uniform(0, [cfg.video_w, cfg.video_h], size=(5, cfg.obs_len, 2))
+  traj[0, 0] = [0.0, 0.0]; traj[0, 1] = [cfg.video_w, cfg.video_h]
+  traj[1, 0] = [cfg.video_w / 18 * 3, cfg.video_h / 36 * 7]            # exactly on cell borders of the fine grid
+  labels, regress = eng.grid_feeds_from_traj(traj)
+  for s in range(5):
+    want_l, want_r = R.traj_to_grid(cfg, traj[s])
+    for i in range(2):
+      assert np.array_equal(labels[i][s].cpu().numpy(), want_l[i])
+      assert np.array_equal(regress[i][s].cpu().numpy(), want_r[i])
