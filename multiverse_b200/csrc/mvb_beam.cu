@@ -259,11 +259,8 @@ int beam_step(const float* logits, const float* score_in, float* score_out, int*
   if ((!diverse || log_gamma <= 0.f) && !(full && full[0] == '1')) {
     const size_t smem_t = sizeof(float) * ((size_t)B * V + 2 * (size_t)B * B);
     MVB_REQUIRE(smem_t <= 227 * 1024, "beam_step: B*V=%d too large for shared memory", B * V);
-    static size_t configured_t = 0;
-    if (smem_t > 48 * 1024 && smem_t > configured_t) {
-      MVB_CHECK_CUDA(cudaFuncSetAttribute(beam_step_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      configured_t = smem_t;
-    }
+    static SmemOptIn opt_t;
+    if (smem_t > 48 * 1024) MVB_CHECK_CUDA(smem_opt_in(opt_t, beam_step_topk_kernel, smem_t));
     beam_step_topk_kernel<<<(unsigned)N, BEAM_THREADS, smem_t, stream>>>(logits, score_in, score_out, ids_out,
                                                                          parents_out, row_map_out, B, V, first_step,
                                                                          zero_scores, diverse, log_gamma);
@@ -274,11 +271,8 @@ int beam_step(const float* logits, const float* score_in, float* score_out, int*
   // log(gamma) > 0 rewards high ranks: no per-row bound on the winners, use the full rank count
   const size_t smem = sizeof(float) * 2 * (size_t)B * V;
   MVB_REQUIRE(smem <= 227 * 1024, "beam_step: B*V=%d too large for shared memory", B * V);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  if (smem > 48 * 1024) MVB_CHECK_CUDA(smem_opt_in(opt, beam_step_kernel, smem));
   beam_step_kernel<<<(unsigned)N, BEAM_THREADS, smem, stream>>>(logits, score_in, score_out, ids_out,
                                                                 parents_out, row_map_out, B, V, first_step,
                                                                 zero_scores, diverse, log_gamma);

@@ -437,14 +437,9 @@ template <int P>
 static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
                        const CellParams& prm, int num_sms, bool multicast, cudaStream_t stream) {
   using Cfg = CellCfg<P>;
-  static bool configured = false;
-  if (!configured) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(cell_fwd_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static SmemOptIn opt_plain, opt_mc;
+  MVB_CHECK_CUDA(smem_opt_in(opt_plain, cell_fwd_kernel<P, false>, Cfg::SMEM_BYTES));
+  MVB_CHECK_CUDA(smem_opt_in(opt_mc, cell_fwd_kernel<P, true>, Cfg::SMEM_BYTES));
   const long long m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   if (multicast && m_tiles >= 2 * (long long)num_sms) {
     cudaLaunchConfig_t cfg = {};

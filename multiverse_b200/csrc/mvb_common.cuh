@@ -96,6 +96,22 @@ __device__ __forceinline__ float tanh_acc(float x) {
 // ----------------------------------------------------------------------------------
 // warp reductions
 // ----------------------------------------------------------------------------------
+// Opt-in to more than 48 KB of dynamic shared memory: once per (kernel, device) and again whenever a launch needs
+// more than was granted.  The attribute lives in the device's context, so a process that drives several GPUs
+// through this library needs it set on each of them; a racing second thread at worst repeats the idempotent call.
+struct SmemOptIn { size_t granted[64] = {}; };
+template <class Kernel>
+inline cudaError_t smem_opt_in(SmemOptIn& st, Kernel kernel, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (bytes <= st.granted[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) st.granted[dev] = bytes;
+  return e;
+}
+
 // Sums each of v[0..7] over the warp with 9 shuffles instead of 8 butterflies (40): at every halving step a lane
 // keeps one half of its values and hands the other half to its partner.  Lane l returns the warp total of value
 // ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1); the four lanes that share l >> 2 hold the same total.

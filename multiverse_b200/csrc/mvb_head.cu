@@ -228,11 +228,10 @@ static int launch_head(const float* h32, const float* Wo, float* out, int* ids_o
                        const float* be, int E, void* xh_next, long long plane_stride, int cpad,
                        long long NS, const Grid& g, cudaStream_t stream) {
   const size_t smem = sizeof(float) * ((size_t)9 * kHidden * POUT + (size_t)g.H * g.W * (9 * POUT + POUT));
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static SmemOptIn opt;
+  if (smem > 48 * 1024) {
     MVB_REQUIRE(smem <= 227 * 1024, "head_fwd: grid %dx%d needs %zu B shared memory", g.H, g.W, smem);
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(head_kernel<P, POUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    MVB_CHECK_CUDA(smem_opt_in(opt, head_kernel<P, POUT>, smem));
   }
   head_kernel<P, POUT><<<(unsigned)NS, HEAD_THREADS, smem, stream>>>(
       h32, Wo, out, ids_out, We, be, E, reinterpret_cast<__nv_bfloat16*>(xh_next), plane_stride, cpad, g);

@@ -440,11 +440,8 @@ template <int P, int MODE, int MT>
 static int launch_pgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& prm, int num_sms,
                         cudaStream_t stream) {
   using Cfg = GemmCfg<P, MT>;
-  static bool configured = false;
-  if (!configured) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<P, MODE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static SmemOptIn opt;
+  MVB_CHECK_CUDA(smem_opt_in(opt, pgemm_kernel<P, MODE, MT>, Cfg::SMEM_BYTES));
   const long long tiles = prm.num_m_tiles * prm.num_n_tiles;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   pgemm_kernel<P, MODE, MT><<<grid, G_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);

@@ -518,8 +518,8 @@ int head_bwd(const float* h32, const float* dout, const float* Wo, int Pout, flo
   if (Pout == 1) {
     head_bwd_kernel<1><<<(unsigned)NS, 256, smem, stream>>>(h32, dout, Wo, dWo, dh, accumulate_dh, g);
   } else {
-    static bool conf = false;
-    if (!conf) { MVB_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); conf = true; }
+    static SmemOptIn opt;
+    MVB_CHECK_CUDA(smem_opt_in(opt, head_bwd_kernel<2>, 100 * 1024));
     MVB_REQUIRE(smem <= 100 * 1024, "head_bwd: grid too large");
     head_bwd_kernel<2><<<(unsigned)NS, 256, smem, stream>>>(h32, dout, Wo, dWo, dh, accumulate_dh, g);
   }
@@ -535,12 +535,9 @@ int emb_bwd(const float* dxh, int cpad, const int* ids, const float* in_map, con
   MVB_REQUIRE((Pout == 1 && ids) || (Pout == 2 && in_map), "emb_bwd: need ids (Pout=1) or in_map (Pout=2)");
   const Grid g = make_grid(H, W);
   const size_t smem = sizeof(float) * ((size_t)H * W * (2 + E) + 9 * Pout * E + E);
-  static bool conf = false;
-  if (!conf) {
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(emb_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    MVB_CHECK_CUDA(cudaFuncSetAttribute(emb_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    conf = true;
-  }
+  static SmemOptIn opt1, opt2;
+  MVB_CHECK_CUDA(smem_opt_in(opt1, emb_bwd_kernel<1>, 160 * 1024));
+  MVB_CHECK_CUDA(smem_opt_in(opt2, emb_bwd_kernel<2>, 160 * 1024));
   MVB_REQUIRE(smem <= 160 * 1024, "emb_bwd: grid too large");
   if (Pout == 1) emb_bwd_kernel<1><<<(unsigned)NS, 256, smem, stream>>>(dxh, cpad, ids, in_map, We, be, E, dWe, dbe, d_in, accumulate_din, g);
   else emb_bwd_kernel<2><<<(unsigned)NS, 256, smem, stream>>>(dxh, cpad, ids, in_map, We, be, E, dWe, dbe, d_in, accumulate_din, g);

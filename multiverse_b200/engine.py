@@ -390,7 +390,8 @@ class ConvRNNEngine(object):
       self.forward(static, tp)        # eager pass: persistent buffers, kernel attributes, lazy caches
       torch.cuda.synchronize(self.device)
       graph = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(graph):
+      # thread_local: calls made by other threads (NCCL watchdog, profilers) must not invalidate the capture
+      with torch.cuda.graph(graph, capture_error_mode="thread_local"):
         out = self.forward(static, tp)
       ent = (graph, static, out)
       self._graphs[key] = ent
