@@ -1,8 +1,7 @@
 # coding=utf-8
 """How many host threads give the torch-CPU reference restatement its best throughput?"""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
 import bench
 print("cpu_count", os.cpu_count())
 for th in (8, 16, 32, 64, 128):

@@ -1,6 +1,6 @@
 # coding=utf-8
 """GPU probe: ConvLSTM cell kernel vs the numpy oracle under a set of ablations (debug aid)."""
-import os, sys, time
+import os, sys
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,10 +1,9 @@
 # coding=utf-8
 """GPU probe: whole forward (greedy two-scale, then beam) vs the numpy oracle."""
-import os, sys, time
+import os, sys
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from multiverse_b200 import ops
 from multiverse_b200.engine import ConvRNNEngine
 from oracle import multiverse_ref as R
 
