@@ -87,6 +87,8 @@ class ConvRNNEngine(object):
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
     dev = self.device
+    if getattr(self, "_graphs", None):
+      self._graphs.clear()      # captured graphs point at the previous weight buffers
     w = {k: (v if torch.is_tensor(v) else torch.as_tensor(v)).to(dev) for k, v in weights.items()}
     self.scene_w = [(w[P_ + "scene_conv%d/W" % (i + 1)].float().contiguous(),
                      w[P_ + "scene_conv%d/b" % (i + 1)].float().contiguous())
