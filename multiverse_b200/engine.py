@@ -67,6 +67,7 @@ class ScaleWeights(object):
 
 class ConvRNNEngine(object):
   """Inference engine for one config (batch size, grids, flags) and one weight set."""
+  GRAPH_CACHE = 4             # captured forward graphs kept per engine
 
   def __init__(self, cfg, weights, device=None, planes=None):
     self.cfg = cfg
@@ -83,6 +84,7 @@ class ConvRNNEngine(object):
     self._bufs = {}
     self.cell_events = None   # set to [] to record (tag, cx, start, end) events per cell launch
     self._graphs = {}         # forward_graph(): feed signature -> (CUDAGraph, static feeds, static outputs)
+    self._graph_seen = set()  # signatures seen once (captured at their second occurrence)
 
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
@@ -374,7 +376,7 @@ class ConvRNNEngine(object):
     return items
 
   def forward_graph(self, feeds, pred_len=None):
-    """forward() captured once per feed signature (shapes, dtypes, rollout length) into a CUDA graph and replayed:
+    """forward() captured per feed signature (shapes, dtypes, rollout length) into a CUDA graph and replayed:
     a forward is 120-950 kernel launches with no host-side data dependence (the beam loop has a fixed trip count and
     parents travel as device row maps), so at small batches - where the ~20 us the host spends per launch exceeds
     the kernels' run time - one graph launch replaces them.  Bit-identical to forward().  The returned tensors
@@ -386,6 +388,14 @@ class ConvRNNEngine(object):
     if ent is None:
       if self.cell_events is not None:
         raise RuntimeError("forward_graph: per-launch event recording (cell_events) is an eager-mode feature")
+      # A signature is captured the second time it is seen, and at most GRAPH_CACHE graphs are kept (each owns
+      # the memory of its temporaries): callers whose feed shapes change from batch to batch - the number of
+      # unique scene frames does in the reference's evaluation loop - just run launch by launch.
+      if key not in self._graph_seen:
+        if len(self._graph_seen) >= 64:
+          self._graph_seen.clear()
+        self._graph_seen.add(key)
+        return self.forward(feeds, tp)
       static = dict(scene_feat=feeds["scene_feat"].clone(), obs_scene=feeds["obs_scene"].clone(),
                     grid_obs_labels=[None if t is None else t.clone() for t in feeds["grid_obs_labels"]],
                     grid_obs_regress=[None if t is None else t.clone() for t in feeds["grid_obs_regress"]])
@@ -396,6 +406,8 @@ class ConvRNNEngine(object):
       with torch.cuda.graph(graph, capture_error_mode="thread_local"):
         out = self.forward(static, tp)
       ent = (graph, static, out)
+      while len(self._graphs) >= self.GRAPH_CACHE:
+        self._graphs.pop(next(iter(self._graphs)))      # oldest first (dicts keep insertion order)
       self._graphs[key] = ent
     graph, static, out = ent
     for (_, dst), (_, src) in zip(self._flat_feeds(static), flat):

@@ -360,3 +360,53 @@ def test_tf_checkpoint_bundle_reader(dropin, tmp_path):
   open(prefix + ".index", "wb").write(bytes(raw))
   with pytest.raises(IOError):
     _bundle.read_index(prefix)
+
+
+def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
+  """Host logic of ConvRNNEngine.forward_graph with the CUDA pieces stubbed: a signature runs eagerly the first
+  time, is captured the second time and replayed afterwards; at most GRAPH_CACHE graphs are kept (oldest evicted);
+  replacing the weights drops them all."""
+  import torch
+  from multiverse_b200 import engine as E
+
+  class FakeGraph(object):
+    replays = 0
+    def replay(self):
+      FakeGraph.replays += 1
+
+  class FakeCtx(object):
+    def __init__(self, g, **kw): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+
+  monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+  monkeypatch.setattr(torch.cuda, "graph", FakeCtx)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  eng = E.ConvRNNEngine.__new__(E.ConvRNNEngine)
+  eng.cfg = types.SimpleNamespace(pred_len=12)
+  eng.device, eng.cell_events, eng._graphs, eng._graph_seen = torch.device("cpu"), None, {}, set()
+  calls = []
+  eng.forward = lambda feeds, tp, on_output=None: calls.append((tuple(feeds["obs_scene"].shape), tp)) or dict(tag=len(calls))
+
+  def feeds(n):
+    return dict(scene_feat=torch.zeros(3, 4, 4, 11), obs_scene=torch.zeros(n, 8, dtype=torch.int32),
+                grid_obs_labels=[torch.zeros(n, 8, dtype=torch.int32), None],
+                grid_obs_regress=[torch.zeros(n, 8, 2, 2, 2), None])
+
+  eng.forward_graph(feeds(2))                      # first sight: eager
+  assert len(calls) == 1 and not eng._graphs and FakeGraph.replays == 0
+  out = eng.forward_graph(feeds(2))                # second sight: eager warm-up + capture, then replay
+  assert len(calls) == 3 and len(eng._graphs) == 1 and FakeGraph.replays == 1 and out["tag"] == 3
+  eng.forward_graph(feeds(2)); eng.forward_graph(feeds(2), pred_len=12)
+  assert len(calls) == 3 and FakeGraph.replays == 3              # pure replays (pred_len default == 12)
+  eng.forward_graph(feeds(2), pred_len=17)         # another rollout length is another signature
+  assert len(calls) == 4 and len(eng._graphs) == 1
+  for n in range(3, 3 + eng.GRAPH_CACHE + 1):      # more signatures than the cache holds
+    eng.forward_graph(feeds(n)); eng.forward_graph(feeds(n))
+  assert len(eng._graphs) == eng.GRAPH_CACHE
+  assert not any(k[1][1] == (2, 8) for k in eng._graphs)          # the oldest (n = 2) was evicted
+  eng.scene_w = eng.scales = None
+  eng.cfg = types.SimpleNamespace(pred_len=12, scene_grid_strides=[], scene_grids=[], use_grids=[])
+  eng.planes = 2
+  eng.set_weights({})
+  assert not eng._graphs
