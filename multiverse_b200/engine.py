@@ -382,23 +382,29 @@ class ConvRNNEngine(object):
     the kernels' run time - one graph launch replaces them.  Bit-identical to forward().  The returned tensors
     are the graph's static outputs: they are overwritten by the next replay of the same signature."""
     tp = int(pred_len) if pred_len else self.cfg.pred_len
+    # The number of unique scene frames F changes from batch to batch in the reference's loops (scene_feat is
+    # re-compacted per batch, code/pred_utils.py:680-704), so the graph is captured for F rounded up to a multiple
+    # of 64: the scene CNN also runs on the padding frames, which no obs_scene index ever points at.
+    sf = feeds["scene_feat"]
+    f_pad = -(-int(sf.shape[0]) // 64) * 64
     flat = self._flat_feeds(feeds)
-    key = (tp,) + tuple((k, tuple(t.shape), t.dtype) for k, t in flat)
+    key = (tp, f_pad) + tuple((k, tuple(t.shape[1:] if k == "scene_feat" else t.shape), t.dtype) for k, t in flat)
     ent = self._graphs.get(key)
     if ent is None:
       if self.cell_events is not None:
         raise RuntimeError("forward_graph: per-launch event recording (cell_events) is an eager-mode feature")
       # A signature is captured the second time it is seen, and at most GRAPH_CACHE graphs are kept (each owns
-      # the memory of its temporaries): callers whose feed shapes change from batch to batch - the number of
-      # unique scene frames does in the reference's evaluation loop - just run launch by launch.
+      # the memory of its temporaries): callers whose feed shapes keep changing just run launch by launch.
       if key not in self._graph_seen:
         if len(self._graph_seen) >= 64:
           self._graph_seen.clear()
         self._graph_seen.add(key)
         return self.forward(feeds, tp)
-      static = dict(scene_feat=feeds["scene_feat"].clone(), obs_scene=feeds["obs_scene"].clone(),
+      static = dict(scene_feat=torch.zeros((f_pad,) + tuple(sf.shape[1:]), dtype=sf.dtype, device=sf.device),
+                    obs_scene=feeds["obs_scene"].clone(),
                     grid_obs_labels=[None if t is None else t.clone() for t in feeds["grid_obs_labels"]],
                     grid_obs_regress=[None if t is None else t.clone() for t in feeds["grid_obs_regress"]])
+      static["scene_feat"][:sf.shape[0]].copy_(sf)
       self.forward(static, tp)        # eager pass: persistent buffers, kernel attributes, lazy caches
       torch.cuda.synchronize(self.device)
       graph = torch.cuda.CUDAGraph()
@@ -410,8 +416,8 @@ class ConvRNNEngine(object):
         self._graphs.pop(next(iter(self._graphs)))      # oldest first (dicts keep insertion order)
       self._graphs[key] = ent
     graph, static, out = ent
-    for (_, dst), (_, src) in zip(self._flat_feeds(static), flat):
-      dst.copy_(src, non_blocking=True)
+    for (name, dst), (_, src) in zip(self._flat_feeds(static), flat):
+      (dst[:src.shape[0]] if name == "scene_feat" else dst).copy_(src, non_blocking=True)
     graph.replay()
     return out
 

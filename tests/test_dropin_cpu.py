@@ -401,10 +401,15 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   assert len(calls) == 3 and FakeGraph.replays == 3              # pure replays (pred_len default == 12)
   eng.forward_graph(feeds(2), pred_len=17)         # another rollout length is another signature
   assert len(calls) == 4 and len(eng._graphs) == 1
+  f5 = feeds(2); f5["scene_feat"] = torch.ones(5, 4, 4, 11)       # another frame count, same 64-frame bucket
+  eng.forward_graph(f5)
+  assert len(calls) == 4 and FakeGraph.replays == 4
+  static_sf = next(iter(eng._graphs.values()))[1]["scene_feat"]
+  assert static_sf.shape[0] == 64 and bool((static_sf[:5] == 1).all()) and bool((static_sf[5:] == 0).all())
   for n in range(3, 3 + eng.GRAPH_CACHE + 1):      # more signatures than the cache holds
     eng.forward_graph(feeds(n)); eng.forward_graph(feeds(n))
   assert len(eng._graphs) == eng.GRAPH_CACHE
-  assert not any(k[1][1] == (2, 8) for k in eng._graphs)          # the oldest (n = 2) was evicted
+  assert not any(dict((e[0], e[1]) for e in k[2:])["obs_scene"] == (2, 8) for k in eng._graphs)   # n = 2 was evicted
   eng.scene_w = eng.scales = None
   eng.cfg = types.SimpleNamespace(pred_len=12, scene_grid_strides=[], scene_grids=[], use_grids=[])
   eng.planes = 2

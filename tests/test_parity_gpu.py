@@ -437,6 +437,15 @@ def test_forward_graph_replay_is_bit_identical(dev, name):
     for a, b in zip(got, want):
       assert torch.equal(a, b)
   assert len(eng._graphs) == 1
+  # a batch with another number of unique scene frames replays the same graph (frame count bucketed to 64)
+  fc = dict(fb); fc["scene_feat"] = torch.cat([fb["scene_feat"], fb["scene_feat"][:1] * 0.5])
+  want = eng.forward(fc)
+  want = [t.clone() for t in want["grid_pred_decoded"] + want["grid_pred_reg_decoded"] + (want["beam_outputs"] or [])
+          if torch.is_tensor(t)]
+  got = eng.forward_graph(fc)
+  got = [t for t in got["grid_pred_decoded"] + got["grid_pred_reg_decoded"] + (got["beam_outputs"] or [])
+         if torch.is_tensor(t)]
+  assert len(eng._graphs) == 1 and all(torch.equal(a, b) for a, b in zip(got, want))
 
 
 def test_cell_onehot_fanout_equals_tiled_rows(dev):
