@@ -12,9 +12,11 @@ TensorFlow 1.15 (``tf.contrib.rnn.ConvLSTMCell``, ``tf.nn.raw_rnn``,
 reference tree nor installable in this image (Python 3.12, no wheel, no network).
 This file therefore *restates* the reference wiring (``code/pred_models.py``) plus
 the published TF-1.15 semantics of the ops it calls (sheet in SURVEY.md §8c).  It
-is cross-checked against independent implementations (torch conv2d, the literal
-dense [HW,HW] graph attention, brute-force beam replay) in ``tests/`` but cannot
-be checked against an execution of the reference itself.
+is cross-checked against independent implementations in ``tests/`` - torch conv2d with
+TF's SAME rule, torch.nn.LSTMCell (the cell on a 1x1 grid), torch.optim.Adadelta, torch's
+Huber / cross-entropy, the literal dense [HW,HW] graph attention, brute-force beam replay,
+a second, independently written torch port of the whole model - but cannot be checked
+against an execution of the reference itself.
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  All functions are dtype-generic: pass float64 arrays for the
