@@ -1,8 +1,12 @@
 # coding=utf-8
-"""Regenerates tests/golden/*.npz from the CPU oracle (fp64).  Run from the repo root:
+"""Regenerates tests/golden/*.npz (fp64).  Run from the repo root, in the container that has
+/root/reference:
     python tests/golden/make_golden.py
-The reference itself cannot run here (TensorFlow 1.15 is not installable), so these vectors pin
-the ORACLE, not the reference: "parity unpinned" (see oracle/multiverse_ref.py)."""
+The ROLLOUT goldens are outputs of the reference's own code: the unmodified
+/root/reference/code/pred_models.py executed on the eager TF-1.15 stand-in of oracle/tf1_eager
+(``source = "reference_exec"``); the script asserts that the oracle restatement agrees to 1e-12
+with identical ids before writing them.  The unit-op goldens (cell, gnn, head, beam_step, scene)
+come from the oracle functions that the same execution pins."""
 import os
 import sys
 
@@ -13,6 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from oracle import multiverse_ref as R  # noqa: E402
+from oracle.tf1_eager import run_reference as X  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 f64 = lambda d: {k: (v.astype(np.float64) if v.dtype.kind == "f" else v) for k, v in d.items()}
@@ -68,7 +73,21 @@ def main():
     cfg = R.default_config(**over)
     w = R.make_weights(cfg, seed); f = R.make_inputs(cfg, seed)
     r = R.forward(cfg, w, f, np.float64)
-    out = dict(checksum=cases.checksum(*w.values()) + cases.checksum(f["scene_feat"], f["traj"]))
+    source = "oracle"
+    if X.available():
+      x = X.forward(cfg, w, f)
+      for i in range(len(cfg.scene_grids)):
+        if cfg.use_grids[i]:
+          for k in ("grid_pred_decoded", "grid_pred_reg_decoded"):
+            assert np.abs(x[k][i] - r[k][i]).max() <= 1e-12 * np.abs(r[k][i]).max(), (name, k, i)
+      if r["beam_outputs"] is not None:
+        assert np.array_equal(x["beam_outputs"][1], r["beam_outputs"][1])
+        assert np.abs(x["beam_outputs"][0] - r["beam_outputs"][0]).max() < 1e-11
+        assert np.abs(x["beam_outputs"][2] - r["beam_outputs"][2]).max() < 1e-11
+      r = dict(r, grid_pred_decoded=x["grid_pred_decoded"], grid_pred_reg_decoded=x["grid_pred_reg_decoded"],
+               beam_outputs=x["beam_outputs"])
+      source = "reference_exec"
+    out = dict(source=source, checksum=cases.checksum(*w.values()) + cases.checksum(f["scene_feat"], f["traj"]))
     for i in range(len(cfg.scene_grids)):
       if not cfg.use_grids[i]:
         continue
