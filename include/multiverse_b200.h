@@ -51,9 +51,23 @@ int mvb_cell_cpad(int cx);
  * large magnitude (the regression encoder's raw pixel offsets, pred_models.py:232): the zero
  * padding of the x block instead carries [W | W | W-w0-w1 | w1] against the activation side's
  * [x | x-x0-x1 | x | x1] (mvb_nhwc_to_planes with comp), so the terms the 3-product bf16 scheme
- * drops are added back by the same MMAs and the x contribution is exact to fp32. */
+ * drops are added back by the same MMAs and the x contribution is exact to fp32.
+ *
+ * planes == MVB_PLANES_F16F8 (16) selects the "f16f8" operand format everywhere a `planes` argument appears
+ * (inference only): an operand value v = a0 + a1, a0 = fp16(v), is stored as one fp16 plane and two e4m3 planes
+ * e0 = e4m3(a0), e1 = e4m3(a1 * 2^12) - for R rows of cpad channels [fp16 R*cpad][fp8 R rows of 2*cpad bytes], the
+ * same bytes as two bf16 planes; inside an fp8 row the planes are interleaved per K chunk: [x block: e0 | e1]
+ * then per 64 channels of the h block [e0 (64) | e1 (64)] - and the cell accumulates a0*b0 (fp16 tensor-core pass)
+ * + the two cross terms as e4m3 passes at twice the rate into the same fp32 accumulator: 2 bf16-pass equivalents
+ * instead of 3 at the accuracy class of planes == 2.  w_planes then holds [fp16 1024*9*cpad][fp8 1024*9 rows of
+ * 2*cpad bytes][fp32 1024 column scales] (4*1024*9*cpad + 4096 bytes; weights are stored times a per-column power
+ * of two).  comp must be 0. */
+#define MVB_PLANES_F16F8 16
 int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_planes,
                           float* bias_packed, int cx, int planes, int comp, void* stream);
+/* Which cell kernel the calling process launched last: planes * 2 + (1 if the CTA-pair / weight-multicast
+ * variant ran), -1 before the first launch.  Lets tests assert that the variant they mean to check ran. */
+int mvb_cell_last_variant(void);
 
 /* One cell step over NS sample rows:  (c_in, xh) -> (c_out, h).
  *   xh_planes  bf16 [P][NS*S][cpad]: concat([x (cx, zero-padded to roundup(cx,32)), h (256)])

@@ -20,6 +20,7 @@ SIGNATURES = {
     "mvb_launch_count": [],
     "mvb_reset_launch_count": [],
     "mvb_cell_cpad": [_i],
+    "mvb_cell_last_variant": [],
     "mvb_pack_cell_weights": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvb_convlstm_cell_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                               _i, _i, _f, _vp],

@@ -40,7 +40,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+static int encode_tmap_3d_any(CUtensorMapDataType dt, CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                         uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
                         uint32_t b2, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
@@ -53,7 +53,7 @@ int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -63,6 +63,19 @@ int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_
     return MVB_ERR_DRIVER;
   }
   return MVB_OK;
+}
+
+int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                        uint32_t b2, int swizzle_bytes) {
+  return encode_tmap_3d_any(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, base, d0, d1, d2, stride1_bytes, stride2_bytes,
+                            b0, b1, b2, swizzle_bytes);
+}
+int encode_tmap_3d_u8(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                      int swizzle_bytes) {
+  return encode_tmap_3d_any(CU_TENSOR_MAP_DATA_TYPE_UINT8, out, base, d0, d1, d2, stride1_bytes, stride2_bytes,
+                            b0, b1, b2, swizzle_bytes);
 }
 
 int encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t (&dims)[4],
@@ -99,7 +112,8 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 5; }
+int mvb_abi_version(void) { return 6; }
+int mvb_cell_last_variant(void) { return cell_last_variant(); }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 

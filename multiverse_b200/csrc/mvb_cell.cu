@@ -30,25 +30,45 @@ namespace mvb {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 32;   // bf16 elements = 64 B = one SWIZZLE_64B row
+constexpr int XPAD = 32;      // the x block is zero-padded to a multiple of 32 channels (cpad = roundup(cx,32) + 256)
+constexpr int CHUNK = 64;     // channels per K chunk: 64 16-bit elements = 128 B = one SWIZZLE_128B row
+constexpr int ROW_BYTES = 128;
 constexpr int UMMA_K = 16;
 constexpr int TILE_CH = 64;   // hidden channels per N tile
 constexpr int N_TILES = kGates / BLOCK_N;  // 4
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
-constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;  // 8 KB
-constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KB
-constexpr uint32_t SW64_LAYOUT = 4;
-constexpr uint32_t SW64_SBO = 8 * BLOCK_K * 2;  // 512 B between 8-row groups
+constexpr int B_SLOT_BYTES = BLOCK_N * ROW_BYTES;  // 32 KB: 256 weight rows x 128 B
+constexpr uint32_t SW128_LAYOUT = 2;
+constexpr uint32_t SW128_SBO = 8 * ROW_BYTES;      // 1024 B between 8-row groups
 
+// Shared-memory rings.  What bounded the round-1 kernel was not the tensor pipe but the operand feed: the TMA unit
+// writes about ONE BOX ROW PER CLOCK into shared memory whatever the row's width (measured with the MMAs and the
+// epilogue switched off: 275 / 549 / 824 rows per k-block -> 3.2 / 6.0 / 8.6 ms, 32- and 64-byte rows alike), and
+// the round-1 stages were made of 32- and 64-byte rows, nine shifted copies of every activation row among them.
+//   B ring: slots of 256 rows x 128 B = 64 channels of ONE plane of the weight tile (SWIZZLE_128B): per (chunk,
+//           tap) P slots (bf16 planes) or 2 (f16f8: the fp16 plane, then both e4m3 planes interleaved in one row).
+//   A ring: one stage per 64-channel chunk: rows [m0 - (Wp+1), m0 + 128 + (Wp+1)) of every activation plane,
+//           rounded up to a multiple of 8 rows (RA8).  The nine taps of the chunk read THE SAME stage through UMMA
+//           descriptors that start (dy Wp + dx) rows into it: tcgen05 applies the swizzle to absolute shared-memory
+//           address bits, so a K-major operand may start at any row of a TMA-written swizzled tile (probed on B200
+//           for SWIZZLE_32B / 64B / 128B: tools/umma_rowshift_probe.cu).
+// Rows written per 32 channels and tap: 147 (round 1: 768 bf16 x 2, 1152 f16f8); L2 -> SM bytes 18.4 KB (48 KB).
 template <int P> struct CellCfg {
-  static constexpr int STAGE_BYTES = P * (A_PLANE_BYTES + B_PLANE_BYTES);
-  static constexpr int STAGES = (P == 1) ? 8 : (P == 2) ? 4 : 3;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int A_STAGES = 2;
+  static constexpr int MAX_RA8 = 256;           // TMA box limit: 128 + 2 (W + 2) <= 256  ->  W <= 62
+  static constexpr int a_stage_bytes(int ra8) { return P * ra8 * ROW_BYTES; }
+  static constexpr int b_slots(int ra8) {       // 4 slots when they fit beside the A ring, else 3
+    return (4 * B_SLOT_BYTES + A_STAGES * a_stage_bytes(ra8) + 2048 <= 227 * 1024) ? 4 : 3;
+  }
+  static constexpr int smem_bytes(int ra8) {
+    return b_slots(ra8) * B_SLOT_BYTES + A_STAGES * a_stage_bytes(ra8) + 1024 /*align*/ + 512 /*barriers*/;
+  }
 };
 
 struct CellParams {
   const float* bias;        // [1024] packed (tile, gate, channel) order
+  const float* col_scale;   // f16f8 only: [1024] 2^-S of every packed column (the weights are stored times 2^S)
   const float* c_in;        // [R_src, 256] or nullptr (zero state)
   const int* row_map;       // [NS] source sample-row of c_in, or nullptr (identity)
   float* c_out;             // [R, 256]
@@ -57,12 +77,14 @@ struct CellParams {
   // "x-fold" (class decoder only): the input is grid_emb(one_hot(id)), i.e. tanh(b) everywhere except
   // the 3x3 cells around id, so its whole contribution to the pre-activations is a table look-up:
   // xf_B[border class of the cell][1024] (bias folded in) + xf_T2[border class of id][5x5 offset][1024]
-  // for the <=25 cells around id.  The x chunks are then skipped in the K loop (kb_begin).
+  // for the <=25 cells around id.  The x chunk is then skipped in the K loop (skip_x).
   const float* xf_B;        // [9][1024] packed column order, or nullptr
   const float* xf_T2;       // [9][25][1024]
   const int* xf_ids;        // [NS] arg-max cell of every sample row
-  int kb_begin;             // first k-block of the K loop (9 * number of skipped 32-channel chunks)
+  int skip_x;               // x-fold: the x chunk of the K loop is skipped
   int order;                // work order, see work_index()
+  int abl;                  // debug ablations (MVB_CELL_ABL; results are then WRONG): 1 skip the fp8 MMAs, 2 skip the
+                            // 16-bit MMAs, 4 skip the epilogue's math and stores
   int fanout;               // > 1 (x-fold only): every GEMM row is a parent whose K = fanout children differ only in
                             // their one-hot input; the epilogue emits sample row smp*K + k for k < K (xf_ids [NS*K])
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
@@ -78,30 +100,48 @@ struct CellParams {
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) |
                             ((BLOCK_M >> 4) << 24);
+// same with A=B=fp16 for kind::f16 (format code 0), which is also A=B=e4m3 for kind::f8f6f4 (format code 0)
+constexpr uint32_t kIdescF16 = (1u << 4) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
 
 // MC = true: clusters of two CTAs work on two M tiles of the same N tile in lock step; each loads half of every B
 // (weight) tile and TMA-multicasts it to both, so the L2 -> shared-memory traffic per CTA and stage drops from
 // 48 KB to 32 KB (P = 2).  A stage may be refilled once BOTH CTAs' MMAs have consumed it (empty barrier count 2,
 // commits multicast to the pair).
-template <int P, bool MC>
+// FMT = 1: f16f8 operands (P must be 2: same stage bytes).  tmA / tmB then describe the fp16 regions (one
+// "plane") and tmA8 / tmB8 the two fp8 planes; per 32-channel stage the issuer sends two kind::f16 MMAs (K = 16
+// each) and two kind::f8f6f4 MMAs (K = 32 each) into the same accumulator: 4 dispatches instead of 6.
+template <int P, bool MC, int FMT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
-                const __grid_constant__ CUtensorMap tmB, const CellParams prm) {
+cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
+                const CellParams prm) {
+  static_assert(FMT == 0 || P == 2, "the f16f8 format occupies the bytes of two bf16 planes");
   using Cfg = CellCfg<P>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  const int ra8 = (BLOCK_M + 2 * (prm.W + 2) + 7) & ~7;     // rows of an A stage
+  const int a_stage_bytes = Cfg::a_stage_bytes(ra8);
+  const int b_slots = Cfg::b_slots(ra8);
+  uint8_t* smem_a = smem + b_slots * B_SLOT_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + Cfg::A_STAGES * a_stage_bytes);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* afull_bar = empty_bar + 4;
+  uint64_t* aempty_bar = afull_bar + Cfg::A_STAGES;
+  uint64_t* tfull_bar = aempty_bar + Cfg::A_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const Grid g = make_grid(prm.H, prm.W);
-  const int kc = prm.cpad / BLOCK_K;     // channel chunks per tap
-  const int num_kb = 9 * kc;
+  // K chunks of 64 channels: the x chunk [0, 64) - of which only the cxp channels of the x block are multiplied -
+  // then the four chunks of the h block [cxp + 64 j, +64).  fp8 rows (f16f8): [x: e0 (cxp) | e1 (cxp)] then per h
+  // chunk [e0 (64) | e1 (64)], 2 * cpad bytes per row (mvb_common.cuh f8_off).
+  const int cxp = prm.cpad - kHidden;
+  const int q_begin = prm.skip_x ? 1 : 0;
+  constexpr int NQ = 1 + kHidden / CHUNK;      // 5
+  constexpr int NS = FMT ? 2 : P;              // B slots per (chunk, tap)
   const long long num_m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   // work index w -> (m tile, n tile).  MC: the pair shares w; rank r takes m tile 2*(w / N_TILES) + r.
   const uint32_t rank = MC ? cluster_ctarank() : 0u;
@@ -119,9 +159,11 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (FMT == 1) { prefetch_tmap(&tmA8); prefetch_tmap(&tmB8); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
+    for (int s = 0; s < b_slots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
+    for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -134,65 +176,101 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int stage = 0; uint32_t phase = 0;
+    int slot = 0, astage = 0; uint32_t phase = 0, aphase = 0;
     for (long long it = 0, t; (t = work_index(it)) < num_tiles; ++it) {
       const long long m0 = tile_m0(t);
       const int n0 = (int)(t % N_TILES) * BLOCK_N;
-      for (int kb = prm.kb_begin; kb < num_kb; ++kb) {
-        // chunk-major K order: the 9 taps of one 32-channel chunk are consecutive (their A boxes
-        // overlap in L2), and the x block - whose terms can be orders of magnitude larger than the
-        // h terms (raw pixel offsets in the regression encoder) - is accumulated first, so the
-        // small h products are never added onto a large transient partial sum.
-        const int q = kb / 9, tap = kb - q * 9;
-        const int shift = (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + P * A_PLANE_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        tma_load_3d(sa, &tmA, &full_bar[stage], q * BLOCK_K, (int)(m0 + shift), 0);
-        if (MC) {
-          // this CTA's half (128 rows) of every plane of the B tile, delivered to both CTAs of the pair
-          for (int p = 0; p < P; ++p)
-            tma_load_3d_mc(sb + p * B_PLANE_BYTES + rank * (B_PLANE_BYTES / 2), &tmB, &full_bar[stage],
-                           tap * prm.cpad + q * BLOCK_K, n0 + (int)rank * (BLOCK_N / 2), p, (uint16_t)3);
-        } else {
-          tma_load_3d(sb, &tmB, &full_bar[stage], tap * prm.cpad + q * BLOCK_K, n0, 0);
+      // chunk-major K order: the x block - whose terms can be orders of magnitude larger than the h terms (raw
+      // pixel offsets in the regression encoder) - is accumulated first, so the small h products are never added
+      // onto a large transient partial sum.
+      for (int q = q_begin; q < NQ; ++q) {
+        const int c16 = q == 0 ? 0 : cxp + (q - 1) * CHUNK;              // 16-bit channel coordinate
+        const int c8 = q == 0 ? 0 : 2 * cxp + (q - 1) * 2 * CHUNK;       // fp8 byte coordinate
+        mbar_wait(&aempty_bar[astage], aphase ^ 1);
+        uint8_t* sa = smem_a + astage * a_stage_bytes;
+        mbar_expect_tx(&afull_bar[astage], a_stage_bytes);
+        tma_load_3d(sa, &tmA, &afull_bar[astage], c16, (int)(m0 - g.Wp - 1), 0);
+        if (FMT == 1) tma_load_3d(sa + ra8 * ROW_BYTES, &tmA8, &afull_bar[astage], c8, (int)(m0 - g.Wp - 1), 0);
+        if (++astage == Cfg::A_STAGES) { astage = 0; aphase ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int sl = 0; sl < NS; ++sl) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            uint8_t* sb = smem + slot * B_SLOT_BYTES;
+            mbar_expect_tx(&full_bar[slot], B_SLOT_BYTES);
+            const bool f8 = FMT == 1 && sl == 1;
+            const CUtensorMap* tm = f8 ? &tmB8 : &tmB;
+            const int kcol = f8 ? tap * 2 * prm.cpad + c8 : tap * prm.cpad + c16;
+            const int plane = FMT == 1 ? 0 : sl;
+            // MC: this CTA's half (128 rows) of the slot, delivered to both CTAs of the pair
+            if (MC) tma_load_3d_mc(sb + rank * (B_SLOT_BYTES / 2), tm, &full_bar[slot], kcol,
+                                   n0 + (int)rank * (BLOCK_N / 2), plane, (uint16_t)3);
+            else tma_load_3d(sb, tm, &full_bar[slot], kcol, n0, plane);
+            if (++slot == b_slots) { slot = 0; phase ^= 1; }
+          }
         }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    int stage = 0; uint32_t phase = 0;
+    int slot = 0, astage = 0; uint32_t phase = 0, aphase = 0;
     long long it = 0;
     for (long long t; (t = work_index(it)) < num_tiles; ++it) {
       const int as = (int)(it & 1);
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      const uint32_t tphase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tempty_bar[as], tphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      for (int kb = prm.kb_begin; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + P * A_PLANE_BYTES;
-        uint32_t first = (kb == prm.kb_begin) ? 0u : 1u;
+      uint32_t first = 0u;
+      for (int q = q_begin; q < NQ; ++q) {
+        const int ks16 = (q == 0 ? cxp : CHUNK) / UMMA_K;       // K = 16 dispatches per 16-bit plane pair
+        const int ks8 = (q == 0 ? cxp : CHUNK) / 32;            // K = 32 dispatches per fp8 plane
+        const uint32_t poff8 = q == 0 ? (uint32_t)cxp : (uint32_t)CHUNK;   // byte offset of e1 inside an fp8 row
+        mbar_wait(&afull_bar[astage], aphase);
+        const uint32_t sa_base = smem_u32(smem_a + astage * a_stage_bytes);
+        const uint32_t a_plane = (uint32_t)ra8 * ROW_BYTES;
+        for (int tap = 0; tap < 9; ++tap) {
+          // the tap's A tile: the stage's rows starting (dy-1) Wp + (dx-1) + (Wp+1) = dy Wp + dx rows in
+          const uint32_t sa = sa_base + (uint32_t)((tap / 3) * g.Wp + (tap % 3)) * ROW_BYTES;
 #pragma unroll
-        for (int pa = 0; pa < P; ++pa) {
+          for (int sl = 0; sl < NS; ++sl) {
+            mbar_wait(&full_bar[slot], phase);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + slot * B_SLOT_BYTES);
+            if (FMT == 1 && sl == 0) {
+              for (int k = 0; k < ks16; ++k) {                    // a0 * b0, fp16
+                if (prm.abl & 2) break;
+                umma_bf16(d_tmem, make_smem_desc(sa + k * 32, SW128_SBO, SW128_LAYOUT),
+                          make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdescF16, first);
+                first = 1u;
+              }
+            } else if (FMT == 1) {
 #pragma unroll
-          for (int pb = 0; pb < P - pa; ++pb) {
+              for (int p = 0; p < 2; ++p)                         // e4m3 cross terms, K = 32 per dispatch
+                for (int k = 0; k < ks8; ++k) {
+                  if (prm.abl & 1) break;
+                  umma_f8(d_tmem, make_smem_desc(sa + a_plane + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT),
+                          make_smem_desc(sb + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT), kIdescF16, first);
+                  first = 1u;
+                }
+            } else {
+              // B plane sl against the A planes pa with pa + sl < P
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t ad = make_smem_desc(sa + pa * A_PLANE_BYTES + k * UMMA_K * 2, SW64_SBO, SW64_LAYOUT);
-              const uint64_t bd = make_smem_desc(sb + pb * B_PLANE_BYTES + k * UMMA_K * 2, SW64_SBO, SW64_LAYOUT);
-              umma_bf16(d_tmem, ad, bd, kIdesc, first);
-              first = 1u;
+              for (int pa = 0; pa < P - sl; ++pa)
+                for (int k = 0; k < ks16; ++k) {
+                  if (prm.abl & 2) break;
+                  umma_bf16(d_tmem, make_smem_desc(sa + pa * a_plane + k * 32, SW128_SBO, SW128_LAYOUT),
+                            make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdesc, first);
+                  first = 1u;
+                }
             }
+            if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3);
+            else umma_commit(&empty_bar[slot]);
+            if (++slot == b_slots) { slot = 0; phase ^= 1; }
           }
         }
-        if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);
-        else umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&aempty_bar[astage]);      // this CTA's nine taps have consumed the A stage
+        if (++astage == Cfg::A_STAGES) { astage = 0; aphase ^= 1; }
       }
       umma_commit(&tfull_bar[as]);
     }
@@ -234,6 +312,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
       };
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (prm.abl & 4) valid = false;
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -259,6 +338,16 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
         tmem_ld_wait();
         if (valid) {
          const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
+         if (FMT == 1) {      // the weights were stored times 2^S per column: scale the accumulators back once
+           const float* sp = prm.col_scale + nt * BLOCK_N + j0;
+#pragma unroll
+           for (int v = 0; v < 16; ++v) {
+             gi[v] = __float_as_uint(__uint_as_float(gi[v]) * __ldg(sp + 0 * TILE_CH + v));
+             gj[v] = __float_as_uint(__uint_as_float(gj[v]) * __ldg(sp + 1 * TILE_CH + v));
+             gf[v] = __float_as_uint(__uint_as_float(gf[v]) * __ldg(sp + 2 * TILE_CH + v));
+             go[v] = __float_as_uint(__uint_as_float(go[v]) * __ldg(sp + 3 * TILE_CH + v));
+           }
+         }
 #pragma unroll 1
          for (int k = 0; k < prm.fanout; ++k) {      // 1 pass, or one per child of this parent row
           const long long osmp = prm.fanout > 1 ? psmp * prm.fanout + k : psmp;
@@ -304,7 +393,12 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
             for (int v = 0; v < 4; ++v) ho[v] = make_float4(hn[4 * v], hn[4 * v + 1], hn[4 * v + 2], hn[4 * v + 3]);
           }
-          if (prm.hp_out) {
+          if (prm.hp_out && FMT == 1) {
+            const float (&h0)[8] = *reinterpret_cast<const float (*)[8]>(&hn[0]);
+            const float (&h1)[8] = *reinterpret_cast<const float (*)[8]>(&hn[8]);
+            store_f16f8_x8(prm.hp_out, prm.hp_plane_stride, orow, prm.ch_off_out + ch0, prm.cpad_out, h0);
+            store_f16f8_x8(prm.hp_out, prm.hp_plane_stride, orow, prm.ch_off_out + ch0 + 8, prm.cpad_out, h1);
+          } else if (prm.hp_out) {
             uint32_t pk[P][8];
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
@@ -433,31 +527,41 @@ int cell_xfold_tables(const float* kernel, const float* biases, const float* We,
   return MVB_OK;
 }
 
-template <int P>
-static int launch_cell(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
-                       const CellParams& prm, int num_sms, bool multicast, cudaStream_t stream) {
+// variant of the last launch_cell() of this process: planes code * 2 + multicast (tests assert which kernel ran)
+static int g_last_variant = -1;
+int cell_last_variant() { return g_last_variant; }
+
+struct CellMaps { CUtensorMap A, B, Bh, A8, B8, B8h; };
+
+template <int P, int FMT>
+static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, bool multicast, cudaStream_t stream) {
   using Cfg = CellCfg<P>;
   static SmemOptIn opt_plain, opt_mc;
-  MVB_CHECK_CUDA(smem_opt_in(opt_plain, cell_fwd_kernel<P, false>, Cfg::SMEM_BYTES));
-  MVB_CHECK_CUDA(smem_opt_in(opt_mc, cell_fwd_kernel<P, true>, Cfg::SMEM_BYTES));
+  const int ra8 = (BLOCK_M + 2 * (prm.W + 2) + 7) & ~7;
+  const int smem_bytes = Cfg::smem_bytes(ra8);
+  MVB_REQUIRE(ra8 <= Cfg::MAX_RA8 && smem_bytes <= 227 * 1024, "cell_fwd: grid width W=%d too large (A stage of %d rows, %d B shared memory)", prm.W, ra8, smem_bytes);
+  MVB_CHECK_CUDA(smem_opt_in(opt_plain, cell_fwd_kernel<P, false, FMT>, smem_bytes));
+  MVB_CHECK_CUDA(smem_opt_in(opt_mc, cell_fwd_kernel<P, true, FMT>, smem_bytes));
   const long long m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   if (multicast && m_tiles >= 2 * (long long)num_sms) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(num_sms / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, true>, tmA, tmBh, prm));
+    MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, true, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
     count_launch(1);
+    g_last_variant = (FMT ? kPlanesF16F8 : P) * 2 + 1;
     return MVB_OK;
   }
   const long long num_tiles = m_tiles * N_TILES;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-  cell_fwd_kernel<P, false><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, prm);
+  cell_fwd_kernel<P, false, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm.A, tm.B, tm.A8, tm.B8, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
+  g_last_variant = (FMT ? kPlanesF16F8 : P) * 2;
   return MVB_OK;
 }
 
@@ -466,10 +570,12 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
              float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
              int fanout, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "cell_fwd: planes P=%d not in {1,2,3}", P);
+  const bool mixed = P == kPlanesF16F8;
+  MVB_REQUIRE((P >= 1 && P <= 3) || mixed, "cell_fwd: planes P=%d not in {1,2,3,%d}", P, kPlanesF16F8);
+  MVB_REQUIRE(!mixed || !gates_out, "cell_fwd: the f16f8 format is an inference format (no gates_out)");
   MVB_REQUIRE(fanout <= 1 || (xf_B && xf_T2 && xf_ids && !gates_out && !row_map && !hp_out),
               "cell_fwd: fanout=%d needs the x-fold tables and no row_map / gates_out / hp_out", fanout);
-  MVB_REQUIRE(cpad % BLOCK_K == 0 && cpad >= kHidden + BLOCK_K, "cell_fwd: cpad=%d must be a multiple of 32 and >= 288", cpad);
+  MVB_REQUIRE(cpad == kHidden + XPAD || cpad == kHidden + 2 * XPAD, "cell_fwd: cpad=%d must be 288 or 320 (x block of 32 or 64 channels)", cpad);
   MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
   MVB_REQUIRE(xh_planes && w_planes && bias && c_out, "cell_fwd: null pointer");
   if (hp_out) MVB_REQUIRE(cpad_out % 8 == 0 && ch_off_out % 8 == 0, "cell_fwd: hp_out pitch/offset must be multiples of 8");
@@ -479,31 +585,51 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
 
   // weight-tile multicast across CTA pairs is on by default (MVB_CELL_MULTICAST=0 turns it off for A/B runs)
   static const bool multicast = [] { const char* e = getenv("MVB_CELL_MULTICAST"); return !(e && e[0] == '0'); }();
-  CUtensorMap tmA, tmB, tmBh;
-  int rc = encode_tmap_3d_bf16(&tmA, xh_planes, (uint64_t)cpad, (uint64_t)R, (uint64_t)P,
-                               (uint64_t)cpad * 2, (uint64_t)R * cpad * 2, BLOCK_K, BLOCK_M, P, 64);
+  CellMaps tm;
+  const int P16 = mixed ? 1 : P;      // 16-bit "planes" the A / B maps describe
+  const uint32_t ra8 = (uint32_t)((BLOCK_M + 2 * (W + 2) + 7) & ~7);      // rows of an A stage (see CellCfg)
+  MVB_REQUIRE(ra8 <= 256, "cell_fwd: grid width W=%d too large for the halo'd A stage (%u rows > 256)", W, ra8);
+  int rc = encode_tmap_3d_bf16(&tm.A, xh_planes, (uint64_t)cpad, (uint64_t)R, (uint64_t)P16,
+                               (uint64_t)cpad * 2, (uint64_t)R * cpad * 2, CHUNK, ra8, P16, 128);
   if (rc) return rc;
   const uint64_t ktot = 9ull * cpad;
-  rc = encode_tmap_3d_bf16(&tmB, w_planes, ktot, (uint64_t)kGates, (uint64_t)P, ktot * 2,
-                           ktot * kGates * 2, BLOCK_K, BLOCK_N, P, 64);
+  rc = encode_tmap_3d_bf16(&tm.B, w_planes, ktot, (uint64_t)kGates, (uint64_t)P16, ktot * 2,
+                           ktot * kGates * 2, CHUNK, BLOCK_N, 1, 128);          // one plane of a tile = one slot
   if (rc) return rc;
-  rc = encode_tmap_3d_bf16(&tmBh, w_planes, ktot, (uint64_t)kGates, (uint64_t)P, ktot * 2,
-                           ktot * kGates * 2, BLOCK_K, BLOCK_N / 2, 1, 64);     // half tile of one plane
+  rc = encode_tmap_3d_bf16(&tm.Bh, w_planes, ktot, (uint64_t)kGates, (uint64_t)P16, ktot * 2,
+                           ktot * kGates * 2, CHUNK, BLOCK_N / 2, 1, 128);      // half of it (CTA pairs)
   if (rc) return rc;
+  tm.A8 = tm.A; tm.B8 = tm.B; tm.B8h = tm.Bh;
+  const float* col_scale = nullptr;
+  if (mixed) {
+    // [fp16 region][fp8 region: rows of 2*cpad bytes, both e4m3 planes interleaved per chunk (f8_off)]
+    // ([+ 1024 fp32 column scales] after the weights)
+    const uint8_t* a8 = reinterpret_cast<const uint8_t*>(xh_planes) + 2ull * R * cpad;
+    const uint8_t* b8 = reinterpret_cast<const uint8_t*>(w_planes) + 2ull * kGates * ktot;
+    rc = encode_tmap_3d_u8(&tm.A8, a8, 2ull * cpad, (uint64_t)R, 1, 2ull * cpad, 2ull * R * cpad, ROW_BYTES, ra8, 1, 128);
+    if (rc) return rc;
+    rc = encode_tmap_3d_u8(&tm.B8, b8, 2 * ktot, (uint64_t)kGates, 1, 2 * ktot, 2 * ktot * kGates, ROW_BYTES, BLOCK_N, 1, 128);
+    if (rc) return rc;
+    rc = encode_tmap_3d_u8(&tm.B8h, b8, 2 * ktot, (uint64_t)kGates, 1, 2 * ktot, 2 * ktot * kGates, ROW_BYTES, BLOCK_N / 2, 1, 128);
+    if (rc) return rc;
+    col_scale = reinterpret_cast<const float*>(b8 + 2ull * kGates * ktot);
+  }
 
   CellParams prm;
-  prm.bias = bias; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
+  prm.bias = bias; prm.col_scale = col_scale; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
   prm.gates_out = gates_out;
   prm.xf_B = xf_B; prm.xf_T2 = xf_T2; prm.xf_ids = xf_ids;
-  prm.kb_begin = 0;
+  prm.skip_x = 0;
   prm.fanout = fanout > 1 ? fanout : 1;
   // measured on the K=20 beam step: order 1 keeps the DRAM reads at 1.05x algorithmic with the CTA-pair clusters
   // (order 0: 1.39x) and is 3 % faster; MVB_CELL_ORDER=0 selects the strided order for A/B runs.
   static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : 1; }();
   prm.order = order;
+  static const int abl = [] { const char* e = getenv("MVB_CELL_ABL"); return e ? atoi(e) : 0; }();
+  prm.abl = abl;
   if (xf_B) {
     MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
-    prm.kb_begin = 9 * ((cpad - kHidden) / BLOCK_K);
+    prm.skip_x = 1;
   }
   prm.hp_out = reinterpret_cast<__nv_bfloat16*>(hp_out);
   prm.hp_plane_stride = hp_plane_stride; prm.cpad_out = cpad_out; prm.ch_off_out = ch_off_out;
@@ -513,18 +639,93 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   MVB_CHECK_CUDA(cudaGetDevice(&dev));
   MVB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   switch (P) {
-    case 1: return launch_cell<1>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
-    case 2: return launch_cell<2>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
-    default: return launch_cell<3>(tmA, tmB, tmBh, prm, num_sms, multicast, stream);
+    case 1: return launch_cell<1, 0>(tm, prm, num_sms, multicast, stream);
+    case 2: return launch_cell<2, 0>(tm, prm, num_sms, multicast, stream);
+    case kPlanesF16F8: return launch_cell<2, 1>(tm, prm, num_sms, multicast, stream);
+    default: return launch_cell<3, 0>(tm, prm, num_sms, multicast, stream);
   }
 }
 
+// ----------------------------------------------------------------------------------
+// f16f8 weight packing (see mvb_common.cuh): per packed column n a power-of-two scale 2^S with
+// max|w| * 2^S in [2^13, 2^14), so that b0 = fp16(w 2^S) is a normal number for every weight down to 2^-27 of the
+// column maximum, the residual b1 = w 2^S - b0 (|b1| <= 4) and b0 2^-12 (<= 4) sit in e4m3's normal range.
+//   w16 [1024][9*cpad] fp16 = b0;  w8 [1024][9][2*cpad bytes] = e4m3(b1) and e4m3(b0 * 2^-12), interleaved per chunk
+//   like the activation rows (f8_off);  col_scale [1024] = 2^-S
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float packed_weight(const float* __restrict__ kernel, int n, int k, int cx, int cxp,
+                                               int cpad) {
+  const int tap = k / cpad, kcn = k - tap * cpad;
+  const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+  const int col = gate * kHidden + tile * TILE_CH + j;
+  int cin = -1;
+  if (kcn >= cxp) cin = cx + (kcn - cxp);
+  else if (kcn < cx) cin = kcn;
+  return (cin >= 0) ? kernel[((long long)tap * (cx + kHidden) + cin) * kGates + col] : 0.f;
+}
+
+__global__ void colscale_kernel(const float* __restrict__ kernel, float* __restrict__ col_scale, int cx) {
+  // one warp per packed column: max |w| over the 9 * (cx + 256) weights that feed it
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= kGates) return;
+  const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+  const int col = gate * kHidden + tile * TILE_CH + j;
+  float m = 0.f;
+  for (int r = lane; r < 9 * (cx + kHidden); r += 32) m = fmaxf(m, fabsf(kernel[(long long)r * kGates + col]));
+  m = warp_max(m);
+  if (lane == 0) {
+    int e = 0;
+    if (m > 0.f) frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)  ->  floor(log2 m) = e - 1
+    const int S = m > 0.f ? 13 - (e - 1) : 0;
+    col_scale[n] = ldexpf(1.0f, -S);
+  }
+}
+
+__global__ void pack_weights_f16f8_kernel(const float* __restrict__ kernel, const float* __restrict__ biases,
+                                          __half* __restrict__ w16, uint8_t* __restrict__ w8,
+                                          const float* __restrict__ col_scale, float* __restrict__ bias_packed,
+                                          int cx, int cxp, int cpad) {
+  const long long ktot = 9LL * cpad;
+  const long long total = (long long)kGates * ktot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ktot);
+    const int k = (int)(i - (long long)n * ktot);
+    const float v = packed_weight(kernel, n, k, cx, cxp, cpad) / col_scale[n];     // exact: power of two
+    const __half b0 = __float2half_rn(v);
+    const float f0 = __half2float(b0);
+    w16[i] = b0;
+    const int tap = k / cpad, kcn = k - tap * cpad;
+    uint8_t* w8row = w8 + ((long long)n * 9 + tap) * 2 * cpad;
+    w8row[f8_off(kcn, 0, cpad)] = to_e4m3(v - f0);
+    w8row[f8_off(kcn, 1, cpad)] = to_e4m3(f0 * (1.0f / kF8ResidualScale));
+    if (k == 0) {
+      const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+      bias_packed[n] = biases[gate * kHidden + tile * TILE_CH + j];
+    }
+  }
+}
+
+
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,
                       int cx, int P, int comp, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "pack_cell_weights: planes P=%d not in {1,2,3}", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "pack_cell_weights: planes P=%d not in {1,2,3,%d}", P,
+              kPlanesF16F8);
   MVB_REQUIRE(cx >= 1, "pack_cell_weights: cx=%d", cx);
-  const int cxp = (cx + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  const int cxp = (cx + XPAD - 1) / XPAD * XPAD;
   const int cpad = cxp + kHidden;
+  if (P == kPlanesF16F8) {
+    MVB_REQUIRE(!comp, "pack_cell_weights: the compensated x block exists for bf16 planes only");
+    const long long total = (long long)kGates * 9 * cpad;
+    __half* w16 = reinterpret_cast<__half*>(w_planes);
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(w_planes) + 2 * total;
+    float* col_scale = reinterpret_cast<float*>(w8 + 2 * total);
+    colscale_kernel<<<kGates / 8, 256, 0, stream>>>(kernel, col_scale, cx);
+    pack_weights_f16f8_kernel<<<1184, 256, 0, stream>>>(kernel, biases, w16, w8, col_scale, bias_packed, cx, cxp, cpad);
+    MVB_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MVB_OK;
+  }
   MVB_REQUIRE(!comp || (P == 2 && 4 * cx <= cxp), "pack_cell_weights: compensated x block needs planes=2 and 4*cx <= %d", cxp);
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(w_planes);
   const int threads = 256, blocks = 1184;

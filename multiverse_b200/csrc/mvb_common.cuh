@@ -11,6 +11,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -75,6 +77,71 @@ __device__ __forceinline__ void split_planes(float v, __nv_bfloat16 (&out)[P]) {
     out[p] = __float2bfloat16_rn(r);
     r -= __bfloat162float(out[p]);
   }
+}
+
+// ----------------------------------------------------------------------------------
+// "f16f8" operand format (planes code kPlanesF16F8): v = a0 + a1 with a0 = fp16(v); the tensor cores see
+//   a0 (fp16 plane), e0 = e4m3(a0) and e1 = e4m3(a1 * 2^12) (two fp8 planes), and the product of two such
+// operands is accumulated as   a0*b0 (kind::f16)  +  e0(a)*e0'(b)  +  e1(a)*e1'(b)  (kind::f8f6f4, twice the rate)
+// where for the WEIGHT operand e0' = e4m3(b1) and e1' = e4m3(b0 * 2^-12): the two fp8 products are the cross
+// terms a0*b1 and a1*b0 to 4 significant bits, i.e. to 2^-17 of the main product; a1*b1 (2^-24) is dropped.
+// All three products have the same scale, so they share ONE fp32 TMEM accumulator.  2 bf16-pass equivalents
+// instead of 3 at the accuracy class of the bf16 x 2-plane scheme (profiles/r02_numerics_gate*.json).
+// Buffer layout for R rows of cpad channels: [fp16 R*cpad][fp8: R rows of 2*cpad bytes] = the bytes of two bf16
+// planes, so the same allocations serve both formats.  Inside an fp8 row the two planes are interleaved per K chunk
+// of the cell kernel, so that ONE 128-byte TMA row carries both (f8_off): [x block: e0 (cxp) | e1 (cxp)] then per
+// 64-channel chunk of the h block [e0 (64) | e1 (64)],  cxp = cpad - 256.
+// ----------------------------------------------------------------------------------
+constexpr int kPlanesF16F8 = 16;
+constexpr float kF8ResidualScale = 4096.f;   // 2^12: residual of an fp16 rounding, brought into e4m3's range
+
+// byte offset inside an fp8 row of channel c, plane p
+__host__ __device__ __forceinline__ int f8_off(int c, int p, int cpad) {
+  const int hoff = cpad - kHidden;
+  if (c >= hoff) { const int cc = c - hoff; return 2 * hoff + (cc >> 6) * 128 + p * 64 + (cc & 63); }
+  return p * hoff + c;
+}
+
+__device__ __forceinline__ uint8_t to_e4m3(float v) {
+  return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
+// 8 consecutive channels -> 16 B of fp16 and 8 B of each fp8 plane
+__device__ __forceinline__ void split_f16f8_x8(const float (&v)[8], uint4& f16, uint2& p0, uint2& p1) {
+  uint32_t hw[4], b0[2] = {0u, 0u}, b1[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half lo = __float2half_rn(v[2 * i]), hi = __float2half_rn(v[2 * i + 1]);
+    const float flo = __half2float(lo), fhi = __half2float(hi);
+    hw[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+    b0[i >> 1] |= ((uint32_t)to_e4m3(flo) | ((uint32_t)to_e4m3(fhi) << 8)) << (16 * (i & 1));
+    b1[i >> 1] |= ((uint32_t)to_e4m3((v[2 * i] - flo) * kF8ResidualScale) |
+                   ((uint32_t)to_e4m3((v[2 * i + 1] - fhi) * kF8ResidualScale) << 8)) << (16 * (i & 1));
+  }
+  f16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  p0 = make_uint2(b0[0], b0[1]);
+  p1 = make_uint2(b1[0], b1[1]);
+}
+// store 8 consecutive channels [ch, ch+8) (ch % 8 == 0) of one row into an f16f8 operand buffer (base = start of
+// the fp16 region, plane_stride = rows * cpad = elements of it)
+__device__ __forceinline__ void store_f16f8_x8(void* base, long long plane_stride, long long row, int ch, int cpad,
+                                               const float (&v)[8]) {
+  uint4 f16; uint2 p0, p1;
+  split_f16f8_x8(v, f16, p0, p1);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(base) + row * cpad + ch) = f16;
+  uint8_t* b8 = reinterpret_cast<uint8_t*>(base) + 2 * plane_stride + row * 2 * cpad;
+  *reinterpret_cast<uint2*>(b8 + f8_off(ch, 0, cpad)) = p0;
+  *reinterpret_cast<uint2*>(b8 + f8_off(ch, 1, cpad)) = p1;
+}
+
+// one element
+__device__ __forceinline__ void store_f16f8(void* base, long long plane_stride, long long row, int ch, int cpad,
+                                            float v) {
+  const __half a0 = __float2half_rn(v);
+  const float f0 = __half2float(a0);
+  reinterpret_cast<__half*>(base)[row * cpad + ch] = a0;
+  uint8_t* b8 = reinterpret_cast<uint8_t*>(base) + 2 * plane_stride + row * 2 * cpad;
+  b8[f8_off(ch, 0, cpad)] = to_e4m3(f0);
+  b8[f8_off(ch, 1, cpad)] = to_e4m3((v - f0) * kF8ResidualScale);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
@@ -316,6 +383,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// D[tmem] (+)= A * B with 8-bit float operands (e4m3 / e5m2 chosen by idesc), fp32 accumulate, one CTA.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // mbarrier arrive once all previously issued tcgen05.mma of this thread retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
@@ -358,6 +438,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
                         uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                         uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+int encode_tmap_3d_u8(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                      int swizzle_bytes);
 int encode_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t (&dims)[4],
                         const uint64_t (&strides_bytes)[3], const uint32_t (&box)[4],
                         int swizzle_bytes);

@@ -79,7 +79,8 @@ __device__ __forceinline__ float gnn_dot(const GnnCol& a, int ra, const GnnCol& 
   return d;
 }
 
-template <int P>
+// MIX: the output is written in the f16f8 operand format (mvb_common.cuh) instead of P bf16 planes
+template <int P, bool MIX = false>
 __global__ void __launch_bounds__(GNN_WARPS * 32)
 gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
            const float* __restrict__ scene_mean, int beam, __nv_bfloat16* __restrict__ hp_out,
@@ -149,6 +150,11 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
         o[c] = fmaf(aR, R.h[r][c], o[c]);
       }
     }
+    const long long orow = s * g.S + (long long)y * g.Wp + x;
+    if (MIX) {
+      store_f16f8_x8(hp_out, plane_stride, orow, ch_off + lane * 8, cpad_out, o);
+      return;
+    }
     uint32_t pk[P][4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -158,7 +164,6 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
 #pragma unroll
       for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
     }
-    const long long orow = s * g.S + (long long)y * g.Wp + x;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
@@ -176,7 +181,7 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
 int gnn_attend_fwd(const float* h32, const int* row_map, const float* scene_mean, int beam,
                    void* hp_out, long long hp_plane_stride, int cpad_out, int ch_off_out,
                    long long NS, int H, int W, int P, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "gnn_attend_fwd: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "gnn_attend_fwd: planes P=%d", P);
   MVB_REQUIRE(h32 && hp_out && NS > 0 && beam >= 1, "gnn_attend_fwd: bad args");
   MVB_REQUIRE(cpad_out % 8 == 0 && ch_off_out % 8 == 0, "gnn_attend_fwd: pitch/offset must be multiples of 8");
   const Grid g = make_grid(H, W);
@@ -186,6 +191,7 @@ int gnn_attend_fwd(const float* h32, const int* row_map, const float* scene_mean
   switch (P) {
     case 1: gnn_kernel<1><<<blocks, GNN_WARPS * 32, 0, stream>>>(h32, row_map, scene_mean, beam, d, hp_plane_stride, cpad_out, ch_off_out, NS, g); break;
     case 2: gnn_kernel<2><<<blocks, GNN_WARPS * 32, 0, stream>>>(h32, row_map, scene_mean, beam, d, hp_plane_stride, cpad_out, ch_off_out, NS, g); break;
+    case kPlanesF16F8: gnn_kernel<2, true><<<blocks, GNN_WARPS * 32, 0, stream>>>(h32, row_map, scene_mean, beam, d, hp_plane_stride, cpad_out, ch_off_out, NS, g); break;
     default: gnn_kernel<3><<<blocks, GNN_WARPS * 32, 0, stream>>>(h32, row_map, scene_mean, beam, d, hp_plane_stride, cpad_out, ch_off_out, NS, g); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());

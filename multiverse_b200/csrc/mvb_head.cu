@@ -55,6 +55,12 @@ __device__ __forceinline__ void emb_write(const float* __restrict__ vals, int am
         }
       }
     }
+    if (P == kPlanesF16F8) {      // f16f8 operand format (mvb_common.cuh)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = tanhf(v[c]);
+      store_f16f8_x8(xh, plane_stride, s * g.S + (long long)y * g.Wp + x, e0, cpad, v);
+      continue;
+    }
     uint32_t pk[P][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -243,7 +249,7 @@ static int launch_head(const float* h32, const float* Wo, float* out, int* ids_o
 int head_fwd(const float* h32, const float* Wo, int Pout, float* out, int* ids_out, const float* We,
              const float* be, int E, void* xh_next, long long plane_stride, int cpad, long long NS,
              int H, int W, int P, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "head_fwd: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "head_fwd: planes P=%d", P);
   MVB_REQUIRE(Pout == 1 || Pout == 2, "head_fwd: Pout=%d", Pout);
   MVB_REQUIRE(h32 && Wo && out && NS > 0, "head_fwd: bad args");
   if (xh_next) MVB_REQUIRE(We && be && E > 0 && E % 8 == 0 && E <= cpad - kHidden && cpad % 8 == 0,
@@ -253,6 +259,7 @@ int head_fwd(const float* h32, const float* Wo, int Pout, float* out, int* ids_o
   if (P == PP && Pout == PO) return launch_head<PP, PO>(h32, Wo, out, ids_out, We, be, E, xh_next, plane_stride, cpad, NS, g, stream);
   MVB_HEAD_CASE(1, 1) MVB_HEAD_CASE(2, 1) MVB_HEAD_CASE(3, 1)
   MVB_HEAD_CASE(1, 2) MVB_HEAD_CASE(2, 2) MVB_HEAD_CASE(3, 2)
+  MVB_HEAD_CASE(kPlanesF16F8, 1) MVB_HEAD_CASE(kPlanesF16F8, 2)
 #undef MVB_HEAD_CASE
   return MVB_ERR_INVALID;
 }
@@ -260,7 +267,7 @@ int head_fwd(const float* h32, const float* Wo, int Pout, float* out, int* ids_o
 int emb_onehot_fwd(const int* ids, const float* We, const float* be, int E, void* xh_next,
                    long long plane_stride, int cpad, long long NS, int H, int W, int P,
                    cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "emb_onehot_fwd: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "emb_onehot_fwd: planes P=%d", P);
   MVB_REQUIRE(ids && We && be && xh_next && NS > 0 && E > 0 && E % 8 == 0 && E <= cpad - kHidden,
               "emb_onehot_fwd: bad args (E=%d)", E);
   const Grid g = make_grid(H, W);
@@ -268,6 +275,7 @@ int emb_onehot_fwd(const int* ids, const float* We, const float* be, int E, void
   switch (P) {
     case 1: emb_onehot_kernel<1><<<(unsigned)NS, HEAD_THREADS, 0, stream>>>(ids, We, be, E, d, plane_stride, cpad, g); break;
     case 2: emb_onehot_kernel<2><<<(unsigned)NS, HEAD_THREADS, 0, stream>>>(ids, We, be, E, d, plane_stride, cpad, g); break;
+    case kPlanesF16F8: emb_onehot_kernel<kPlanesF16F8><<<(unsigned)NS, HEAD_THREADS, 0, stream>>>(ids, We, be, E, d, plane_stride, cpad, g); break;
     default: emb_onehot_kernel<3><<<(unsigned)NS, HEAD_THREADS, 0, stream>>>(ids, We, be, E, d, plane_stride, cpad, g); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());
@@ -278,7 +286,7 @@ int emb_onehot_fwd(const int* ids, const float* We, const float* be, int E, void
 int emb_dense_fwd(const float* x, const float* We, const float* be, int E, void* xh_next,
                   long long plane_stride, int cpad, long long NS, int H, int W, int P,
                   cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "emb_dense_fwd: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "emb_dense_fwd: planes P=%d", P);
   MVB_REQUIRE(x && We && be && xh_next && NS > 0 && E > 0 && E % 8 == 0 && E <= cpad - kHidden,
               "emb_dense_fwd: bad args (E=%d)", E);
   const Grid g = make_grid(H, W);
@@ -288,6 +296,7 @@ int emb_dense_fwd(const float* x, const float* We, const float* be, int E, void*
   switch (P) {
     case 1: emb_dense_kernel<1><<<(unsigned)NS, HEAD_THREADS, smem, stream>>>(x, We, be, E, d, plane_stride, cpad, g); break;
     case 2: emb_dense_kernel<2><<<(unsigned)NS, HEAD_THREADS, smem, stream>>>(x, We, be, E, d, plane_stride, cpad, g); break;
+    case kPlanesF16F8: emb_dense_kernel<kPlanesF16F8><<<(unsigned)NS, HEAD_THREADS, smem, stream>>>(x, We, be, E, d, plane_stride, cpad, g); break;
     default: emb_dense_kernel<3><<<(unsigned)NS, HEAD_THREADS, smem, stream>>>(x, We, be, E, d, plane_stride, cpad, g); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());

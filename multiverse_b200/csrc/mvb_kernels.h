@@ -13,6 +13,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              long long hp_plane_stride, int cpad_out, int ch_off_out, long long NS, int H, int W,
              int cpad, int P, float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2,
              const int* xf_ids, int fanout, cudaStream_t stream);
+int cell_last_variant();
 int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,
                       float* Bt, float* T2, cudaStream_t stream);
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,

@@ -21,8 +21,12 @@ __global__ void nhwc_to_planes_kernel(const float* __restrict__ src, __nv_bfloat
     const int y = (int)(t % g.H);
     const long long s = t / g.H;
     const long long row = s * g.S + (long long)y * g.Wp + x;
-    __nv_bfloat16 pl[P];
     const float v = src[i];
+    if (P == kPlanesF16F8) {      // f16f8 operand format (mvb_common.cuh)
+      store_f16f8(dst, plane_stride, row, ch_off + c, cpad, v);
+      continue;
+    }
+    __nv_bfloat16 pl[P];
     split_planes<P>(v, pl);
     __nv_bfloat16* d = dst + row * cpad + ch_off + c;
 #pragma unroll
@@ -83,6 +87,8 @@ __global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
     const int pl = prev_label[s];
     if (pl >= 0 && pl < hw) {
       const long long row = s * g.S + (long long)(pl / g.W) * g.Wp + (pl % g.W);
+      if (P == kPlanesF16F8) store_f16f8(xh, plane_stride, row, c, cpad, 0.f);
+      else
 #pragma unroll
       for (int p = 0; p < P; ++p) xh[p * plane_stride + row * cpad + c] = __float2bfloat16_rn(0.f);
     }
@@ -92,6 +98,7 @@ __global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
   if (lb >= 0 && lb < hw) {
     const long long row = s * g.S + (long long)(lb / g.W) * g.Wp + (lb % g.W);
     const float v = scene_conv[((long long)frame_idx[s] * hw + lb) * 64 + c];
+    if (P == kPlanesF16F8) { store_f16f8(xh, plane_stride, row, c, cpad, v); return; }
     __nv_bfloat16 pl[P];
     split_planes<P>(v, pl);
 #pragma unroll
@@ -101,7 +108,7 @@ __global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
 
 int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
                    long long NS, int H, int W, int C, int P, int comp, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "nhwc_to_planes: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "nhwc_to_planes: planes P=%d", P);
   MVB_REQUIRE(src && dst_planes && NS > 0 && C > 0 && ch_off + C <= cpad, "nhwc_to_planes: bad args");
   MVB_REQUIRE(!comp || (P == 2 && ch_off + 4 * C <= cpad - kHidden), "nhwc_to_planes: compensated block needs planes=2 and 4*C inside the x block");
   const Grid g = make_grid(H, W);
@@ -112,6 +119,7 @@ int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, i
   switch (P) {
     case 1: nhwc_to_planes_kernel<1><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
     case 2: nhwc_to_planes_kernel<2><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
+    case kPlanesF16F8: nhwc_to_planes_kernel<kPlanesF16F8><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, 0); break;
     default: nhwc_to_planes_kernel<3><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());
@@ -172,13 +180,14 @@ int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int
 int enc_class_input(const float* scene_conv, const int* frame_idx, const int* label,
                     const int* prev_label, void* xh_planes, long long plane_stride, int cpad,
                     long long NS, int H, int W, int P, cudaStream_t stream) {
-  MVB_REQUIRE(P >= 1 && P <= 3, "enc_class_input: planes P=%d", P);
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "enc_class_input: planes P=%d", P);
   MVB_REQUIRE(scene_conv && frame_idx && label && xh_planes && NS > 0, "enc_class_input: bad args");
   const Grid g = make_grid(H, W);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(xh_planes);
   switch (P) {
     case 1: enc_class_input_kernel<1><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
     case 2: enc_class_input_kernel<2><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
+    case kPlanesF16F8: enc_class_input_kernel<kPlanesF16F8><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
     default: enc_class_input_kernel<3><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, prev_label, d, plane_stride, cpad, g); break;
   }
   MVB_CHECK_CUDA(cudaGetLastError());

@@ -20,6 +20,8 @@ the next GNN / cell launch reads its state through.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -50,12 +52,14 @@ def _names(i):
 class ScaleWeights(object):
   """Packed / device-resident weights of one grid scale."""
 
-  def __init__(self, weights, i, planes):
+  def __init__(self, weights, i, planes, fast_class=False):
     nm = _names(i)
     f = lambda n: weights[n].detach().to(torch.float32).contiguous()
     self.enc_class = ops.PackedCell(f(nm["enc_class"][0]), f(nm["enc_class"][1]), planes)
     self.enc_reg = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), planes, comp=True)
-    self.dec_class = ops.PackedCell(f(nm["dec_class"][0]), f(nm["dec_class"][1]), planes)
+    # class decoder fed by the graph attention: f16f8 operands (2 instead of 3 bf16-pass equivalents per product)
+    self.dec_class = ops.PackedCell(f(nm["dec_class"][0]), f(nm["dec_class"][1]),
+                                    ops.PLANES_F16F8 if fast_class else planes)
     self.dec_reg = ops.PackedCell(f(nm["dec_reg"][0]), f(nm["dec_reg"][1]), planes)
     self.emb_class = (f(nm["emb_class"][0]), f(nm["emb_class"][1]))
     self.emb_reg = (f(nm["emb_reg"][0]), f(nm["emb_reg"][1]))
@@ -68,11 +72,18 @@ class ScaleWeights(object):
 class ConvRNNEngine(object):
   """Inference engine for one config (batch size, grids, flags) and one weight set."""
   GRAPH_CACHE = 4             # captured forward graphs kept per engine
+  ALLOW_F16F8 = True          # TrainEngine: False (its packed weights also feed the bf16 backward GEMMs)
 
   def __init__(self, cfg, weights, device=None, planes=None):
     self.cfg = cfg
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.planes = planes or ops.DEFAULT_PLANES
+    # The class decoder's cell reads only what the graph attention writes (its one-hot input is folded into table
+    # look-ups), so that producer/consumer pair switches to the f16f8 operand format as a unit; MVB_F16F8=0 keeps
+    # bf16 planes everywhere (A/B runs and the round-1 numbers).
+    self.fast_class = (self.ALLOW_F16F8 and bool(cfg.use_gnn) and self.planes == 2 and
+                       os.environ.get("MVB_F16F8", "1") != "0")
+    self.class_planes = ops.PLANES_F16F8 if self.fast_class else self.planes
     assert cfg.enc_hidden_size == ops.HIDDEN and cfg.dec_hidden_size == ops.HIDDEN, \
         "the kernels are specialised for hidden size 256 (every published config)"
     assert cfg.use_scene_enc, "only the published use_scene_enc path is implemented"
@@ -95,7 +106,7 @@ class ConvRNNEngine(object):
     self.scene_w = [(w[P_ + "scene_conv%d/W" % (i + 1)].float().contiguous(),
                      w[P_ + "scene_conv%d/b" % (i + 1)].float().contiguous())
                     for i in range(len(self.cfg.scene_grid_strides))]
-    self.scales = [ScaleWeights(w, i, self.planes) if self.cfg.use_grids[i] else None
+    self.scales = [ScaleWeights(w, i, self.planes, self.fast_class) if self.cfg.use_grids[i] else None
                    for i in range(len(self.cfg.scene_grids))]
 
   # ------------------------------------------------------------------ buffers
@@ -106,9 +117,10 @@ class ConvRNNEngine(object):
       self._bufs[key] = b
     return b
 
-  def _xh(self, tag, ns, h, w, cpad):
-    return [self._buf((tag, j, ns, h, w, cpad),
-                      lambda: ops.alloc_xh(ns, h, w, cpad, self.planes, self.device))
+  def _xh(self, tag, ns, h, w, cpad, planes=None):
+    planes = planes or self.planes
+    return [self._buf((tag, j, ns, h, w, cpad, planes),
+                      lambda: ops.alloc_xh(ns, h, w, cpad, planes, self.device))
             for j in range(2)]
 
   def _state(self, tag, ns, h, w):
@@ -202,7 +214,7 @@ class ConvRNNEngine(object):
     h, w = cfg.scene_grids[i]
     n = first_ids.shape[0]
     sw = self.scales[i]
-    xh = self._xh("dec_class", n, h, w, sw.dec_class.cpad)
+    xh = self._xh("dec_class", n, h, w, sw.dec_class.cpad, self.class_planes)
     c = [self._state("dec_c0", n, h, w), self._state("dec_c1", n, h, w)]
     h32 = self._state("dec_h32", n, h, w)
     logits = torch.empty((pred_len, n, h * w), dtype=torch.float32, device=self.device)
@@ -252,7 +264,7 @@ class ConvRNNEngine(object):
     ns = n * b
     dev = self.device
     sw = self.scales[i]
-    xh = self._xh("beam", ns, h, w, sw.dec_class.cpad)
+    xh = self._xh("beam", ns, h, w, sw.dec_class.cpad, self.class_planes)
     c = [self._state("beam_c0", ns, h, w), self._state("beam_c1", ns, h, w)]
     h32 = self._state("beam_h32", ns, h, w)
     step_logits = torch.empty((pred_len, n, b, v), dtype=torch.float32, device=dev)
@@ -269,7 +281,7 @@ class ConvRNNEngine(object):
     # look-ups (ops.cell_fwd_onehot).
     if not cfg.use_gnn:
       raise NotImplementedError("beam search without use_gnn is not wired (no published config)")
-    xh1 = self._xh("beam_t0", n, h, w, sw.dec_class.cpad)
+    xh1 = self._xh("beam_t0", n, h, w, sw.dec_class.cpad, self.class_planes)
     c_t0 = self._state("beam_c_t0", n, h, w)
     h32_t0 = self._state("beam_h32_t0", n, h, w)
     logits_t0 = torch.empty((n, v), dtype=torch.float32, device=dev)
@@ -340,7 +352,7 @@ class ConvRNNEngine(object):
       obs_reg = feeds["grid_obs_regress"][i].float()
       obs_reg_t = obs_reg.transpose(0, 1).contiguous()
       # class branch
-      xh_dec = self._xh("dec_class", n, h, w, sw.dec_class.cpad)
+      xh_dec = self._xh("dec_class", n, h, w, sw.dec_class.cpad, self.class_planes)
       c_e, h_e = self.encode_class(i, convs[i], obs_scene_t, labels_t,
                                    None if cfg.use_gnn else xh_dec[0])
       if cfg.use_beam_search:

@@ -16,6 +16,17 @@ from . import _lib
 
 HIDDEN = 256
 DEFAULT_PLANES = int(os.environ.get("MVB_PLANES", "2"))
+PLANES_F16F8 = 16    # MVB_PLANES_F16F8: one fp16 + two e4m3 planes in the bytes of two bf16 planes (inference)
+
+
+def planes_of(t):
+  """`planes` code of an operand buffer made by alloc_xh (bf16 planes: its leading dimension)."""
+  return getattr(t, "mvb_planes", t.shape[0])
+
+
+def cell_last_variant():
+  """planes * 2 + multicast of the cell kernel launched last (-1: none yet)."""
+  return int(_lib.load().mvb_cell_last_variant())
 
 
 def _p(t):
@@ -60,8 +71,13 @@ class PackedCell(object):
     self.comp = bool(comp) and planes == 2 and 4 * self.cx <= self.cxp
     kernel = kernel.detach().to(torch.float32).contiguous()
     biases = biases.detach().to(torch.float32).contiguous()
-    self.w = torch.empty((planes, 4 * HIDDEN, 9 * self.cpad), dtype=torch.bfloat16,
-                         device=kernel.device)
+    if planes == PLANES_F16F8:
+      # [fp16 1024 x 9cpad][e4m3 2 x 1024 x 9cpad][fp32 1024 column scales]
+      self.w = torch.empty((4 * 4 * HIDDEN * 9 * self.cpad + 4 * 4 * HIDDEN,), dtype=torch.uint8,
+                           device=kernel.device)
+    else:
+      self.w = torch.empty((planes, 4 * HIDDEN, 9 * self.cpad), dtype=torch.bfloat16,
+                           device=kernel.device)
     self.bias = torch.empty((4 * HIDDEN,), dtype=torch.float32, device=kernel.device)
     _lib.call("mvb_pack_cell_weights", _p(kernel), _p(biases), _p(self.w), _p(self.bias),
               self.cx, planes, int(self.comp), _stream())
@@ -69,7 +85,31 @@ class PackedCell(object):
 
 def alloc_xh(ns, h, w, cpad, planes, device):
   """Zeroed operand planes [P, R, cpad]; halo cells and channel padding must stay zero."""
+  if planes == PLANES_F16F8:
+    t = torch.zeros((2, halo_rows(ns, h, w), cpad), dtype=torch.bfloat16, device=device)   # same bytes
+    t.mvb_planes = PLANES_F16F8
+    return t
   return torch.zeros((planes, halo_rows(ns, h, w), cpad), dtype=torch.bfloat16, device=device)
+
+
+def operand_values(xh):
+  """fp32 values [R, cpad] an operand buffer represents (sum of its bf16 planes, or a0 + a1 of the f16f8 format),
+  plus, for f16f8, the e4m3 copy of a0 (else None).  Diagnostic / test helper: views and casts only."""
+  if planes_of(xh) != PLANES_F16F8:
+    return xh.float().sum(0), None
+    # pylint: disable=unreachable
+  r, cpad = xh.shape[1], xh.shape[2]
+  raw = xh.view(torch.uint8).reshape(-1)
+  n = r * cpad
+  a0 = raw[:2 * n].view(torch.float16).reshape(r, cpad).float()
+  f8 = raw[2 * n:].view(torch.float8_e4m3fn).reshape(r, 2 * cpad).float()
+  # inside an fp8 row: [x block: e0 (cxp) | e1 (cxp)], then per 64 channels of the h block [e0 (64) | e1 (64)]
+  cxp = cpad - HIDDEN
+  c = torch.arange(cpad, device=xh.device)
+  cc = (c - cxp).clamp(min=0)
+  off0 = torch.where(c >= cxp, 2 * cxp + (cc // 64) * 128 + cc % 64, c)
+  off1 = torch.where(c >= cxp, off0 + 64, c + cxp)
+  return a0 + f8[:, off1] / 4096.0, f8[:, off0]
 
 
 def alloc_state(ns, h, w, device, zero=True):
@@ -81,7 +121,8 @@ def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
              forget_bias=1.0):
   """One ConvLSTM step.  xh_next: operand planes whose h block (channel offset = its cxp)
   receives the bf16 planes of h', or None."""
-  assert xh.shape[2] == packed.cpad and xh.shape[0] == packed.planes
+  assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
+  assert xh_next is None or planes_of(xh_next) == packed.planes
   if xh_next is not None:
     stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
   else:
@@ -106,6 +147,8 @@ class XFold(object):
 def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
                     forget_bias=1.0):
   """Class-decoder step with the embedded one-hot input folded into table look-ups."""
+  assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
+  assert xh_next is None or planes_of(xh_next) == packed.planes
   if xh_next is not None:
     stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
   else:
@@ -117,6 +160,7 @@ def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns
 
 def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, fanout, forget_bias=1.0):
   """First K-row beam step: GEMM on the `ns` parent rows, epilogue emits ns*fanout child rows (ids [ns*fanout])."""
+  assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
   _lib.call("mvb_convlstm_cell_fwd_onehot_fanout", _p(xh), _p(packed.w), _p(xf.B), _p(xf.T2), _p(ids), _p(c_in),
             _p(c_out), _p(h32_out), ns, fanout, h, w, packed.cpad, packed.planes, float(forget_bias), _stream())
 
@@ -124,7 +168,7 @@ def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, 
 def nhwc_to_planes(src, xh, ch_off, h, w, comp=False):
   ns, c = src.shape[0], src.shape[-1]
   _lib.call("mvb_nhwc_to_planes", _p(src), _p(xh), xh.stride(0), xh.shape[2], ch_off, ns, h, w,
-            c, xh.shape[0], int(comp), _stream())
+            c, planes_of(xh), int(comp), _stream())
 
 
 def nhwc_to_halo(src, dst, h, w):
@@ -137,7 +181,7 @@ def halo_to_nhwc(src, dst, h, w):
 
 def enc_class_input(scene_conv, frame_idx, label, prev_label, xh, h, w):
   _lib.call("mvb_enc_class_input", _p(scene_conv), _p(frame_idx), _p(label), _p(prev_label),
-            _p(xh), xh.stride(0), xh.shape[2], label.shape[0], h, w, xh.shape[0], _stream())
+            _p(xh), xh.stride(0), xh.shape[2], label.shape[0], h, w, planes_of(xh), _stream())
 
 
 def scene_conv_fwd(x, W, b):
@@ -160,13 +204,13 @@ def scene_time_mean(scene_conv, frame_idx):
 def gnn_attend_fwd(h32, scene_mean, xh_next, h, w, ns, beam=1, row_map=None):
   _lib.call("mvb_gnn_attend_fwd", _p(h32), _p(row_map), _p(scene_mean), beam, _p(xh_next),
             xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN, ns, h, w,
-            xh_next.shape[0], _stream())
+            planes_of(xh_next), _stream())
 
 
 def head_class_fwd(h32, Wo, logits_out, ids_out, We, be, xh_next, h, w, ns, planes=None):
   e = 0 if We is None else We.shape[3]
   if xh_next is not None:
-    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], xh_next.shape[0]
+    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], planes_of(xh_next)
   else:
     stride, cpad, planes = 0, 0, planes or DEFAULT_PLANES
   _lib.call("mvb_head_class_fwd", _p(h32), _p(Wo), _p(logits_out), _p(ids_out), _p(We), _p(be), e,
@@ -176,7 +220,7 @@ def head_class_fwd(h32, Wo, logits_out, ids_out, We, be, xh_next, h, w, ns, plan
 def head_reg_fwd(h32, Wo, off_out, We, be, xh_next, h, w, ns, planes=None):
   e = 0 if We is None else We.shape[3]
   if xh_next is not None:
-    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], xh_next.shape[0]
+    stride, cpad, planes = xh_next.stride(0), xh_next.shape[2], planes_of(xh_next)
   else:
     stride, cpad, planes = 0, 0, planes or DEFAULT_PLANES
   _lib.call("mvb_head_reg_fwd", _p(h32), _p(Wo), _p(off_out), _p(We), _p(be), e, _p(xh_next),
@@ -185,12 +229,12 @@ def head_reg_fwd(h32, Wo, off_out, We, be, xh_next, h, w, ns, planes=None):
 
 def emb_onehot_fwd(ids, We, be, xh_next, h, w):
   _lib.call("mvb_emb_onehot_fwd", _p(ids), _p(We), _p(be), We.shape[3], _p(xh_next),
-            xh_next.stride(0), xh_next.shape[2], ids.numel(), h, w, xh_next.shape[0], _stream())
+            xh_next.stride(0), xh_next.shape[2], ids.numel(), h, w, planes_of(xh_next), _stream())
 
 
 def emb_dense_fwd(x, We, be, xh_next, h, w):
   _lib.call("mvb_emb_dense_fwd", _p(x), _p(We), _p(be), We.shape[3], _p(xh_next),
-            xh_next.stride(0), xh_next.shape[2], x.shape[0], h, w, xh_next.shape[0], _stream())
+            xh_next.stride(0), xh_next.shape[2], x.shape[0], h, w, planes_of(xh_next), _stream())
 
 
 def beam_step(logits, score_in, score_out, ids_out, parents_out, row_map_out, n, b, v,

@@ -37,6 +37,7 @@ class TrainEngine(ConvRNNEngine):
   """ConvRNNEngine + loss + backward + optimizer.  `params` (fp32 device tensors under the TF
   variable names) are the master weights; packed bf16 operand planes are refreshed after every
   update."""
+  ALLOW_F16F8 = False
 
   def __init__(self, cfg, weights, device=None, planes=None):
     super(TrainEngine, self).__init__(cfg, weights, device, planes)

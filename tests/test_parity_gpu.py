@@ -53,10 +53,20 @@ def run_cell(d, dev, planes, comp=False, zero_c=False):
   ops.cell_fwd(xh, pk, None if zero_c else c_in, c_out, h_out, xh2, h, w, ns)
   co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
   ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
-  planes_sum = xh2[:, :, pk.cxp:].float().sum(0).view(ns, h + 1, w + 1, 256)
-  halo = xh2.float().view(planes, ns, h + 1, w + 1, -1)
-  assert float(halo[:, :, h].abs().max()) == 0.0 and float(halo[:, :, :, w].abs().max()) == 0.0, \
-      "kernel wrote into the zero halo"
+  vals, e0 = ops.operand_values(xh2)
+  planes_sum = vals[:, pk.cxp:].reshape(ns, h + 1, w + 1, 256)
+  if planes == ops.PLANES_F16F8:     # [fp16 R*cpad][e4m3 R rows of 2*cpad bytes]
+    raw = xh2.view(torch.uint8).reshape(-1); nel = xh2.shape[1] * xh2.shape[2]
+    halos = [raw[:2 * nel].view(torch.int16).view(1, ns, h + 1, w + 1, -1),
+             raw[2 * nel:].view(torch.int8).view(1, ns, h + 1, w + 1, -1)]
+  else:
+    halos = [xh2.view(torch.int16).view(planes, ns, h + 1, w + 1, -1)]
+  for halo in halos:
+    assert int(halo[:, :, h].abs().max()) == 0 and int(halo[:, :, :, w].abs().max()) == 0, \
+        "kernel wrote into the zero halo"
+  if e0 is not None:      # the e4m3 copy of a0 carries 4 significant bits of it
+    a0 = vals[:, pk.cxp:]
+    assert float((e0[:, pk.cxp:] - a0).abs().max()) <= 2.0 ** -4 * float(a0.abs().max()) + 2.0 ** -9
   return co.cpu().numpy(), ho.cpu().numpy(), planes_sum[:, :h, :w].cpu().numpy()
 
 
@@ -72,6 +82,21 @@ def test_cell_golden(dev, name):
   assert np.abs(hp - h).max() < 2e-5          # bf16 planes of h' sum back to h'
   c0, h0, _ = run_cell(d, dev, 2, comp=comp, zero_c=True)
   assert rel(c0, g["c_zero"]) < tol and rel(h0, g["h_zero"]) < tol
+
+
+@pytest.mark.parametrize("name", ["dec_cx32", "enc_class_cx64", "tile_edge"])
+def test_cell_f16f8_golden(dev, name):
+  """The f16f8 operand format (fp16 main product + two e4m3 cross-term products into one fp32 accumulator,
+  2 bf16-pass equivalents): same bar as the bf16 x 2 scheme, on the same golden vectors."""
+  from multiverse_b200 import ops
+  d = cases.cell_case(name); g = gold("cell_" + name)
+  c, h, hp = run_cell(d, dev, ops.PLANES_F16F8)
+  print("f16f8 cell %s: rel err c %.2e h %.2e" % (name, rel(c, g["c"]), rel(h, g["h"])))
+  assert ops.cell_last_variant() // 2 == ops.PLANES_F16F8
+  assert rel(c, g["c"]) < TIGHT and rel(h, g["h"]) < TIGHT
+  assert np.abs(hp - h).max() < 1e-5          # a0 + e4m3(a1): the residual keeps 4 significant bits (2^-16 of h')
+  c0, h0, _ = run_cell(d, dev, ops.PLANES_F16F8, zero_c=True)
+  assert rel(c0, g["c_zero"]) < TIGHT and rel(h0, g["h_zero"]) < TIGHT
 
 
 def test_cell_three_planes_and_plain_bf16(dev):
