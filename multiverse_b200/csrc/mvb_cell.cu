@@ -110,23 +110,29 @@ constexpr uint32_t kIdescF16 = (1u << 4) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >>
 // FMT = 1: f16f8 operands (P must be 2: same stage bytes).  tmA / tmB then describe the fp16 regions (one
 // "plane") and tmA8 / tmB8 the two fp8 planes; per 32-channel stage the issuer sends two kind::f16 MMAs (K = 16
 // each) and two kind::f8f6f4 MMAs (K = 32 each) into the same accumulator: 4 dispatches instead of 6.
-template <int P, bool MC, int FMT>
+// CG = 2: the pair instead issues ONE cta_group::2 MMA of 256 rows per dispatch from CTA 0: every CTA keeps only ITS
+// half (128 rows) of each weight slot - the tensor cores of the pair read both halves in place - so the same 128 KB
+// ring holds 8 slots instead of 4 (twice the prefetch distance: the L2 -> shared-memory latency under load, not
+// bandwidth, is what left the tensor pipe idle with 4) and no byte of B is written into two shared memories.
+template <int P, int CG, int FMT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
                 const CellParams prm) {
   static_assert(FMT == 0 || P == 2, "the f16f8 format occupies the bytes of two bf16 planes");
   using Cfg = CellCfg<P>;
+  constexpr bool MC = CG == 1, CG2 = CG == 2, PAIR = CG != 0;
+  constexpr int SLOT_BYTES = CG2 ? B_SLOT_BYTES / 2 : B_SLOT_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int ra8 = (BLOCK_M + 2 * (prm.W + 2) + 7) & ~7;     // rows of an A stage
   const int a_stage_bytes = Cfg::a_stage_bytes(ra8);
-  const int b_slots = Cfg::b_slots(ra8);
-  uint8_t* smem_a = smem + b_slots * B_SLOT_BYTES;
+  const int b_slots = Cfg::b_slots(ra8) * (CG2 ? 2 : 1);
+  uint8_t* smem_a = smem + b_slots * SLOT_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + Cfg::A_STAGES * a_stage_bytes);
-  uint64_t* empty_bar = full_bar + 4;
-  uint64_t* afull_bar = empty_bar + 4;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* afull_bar = empty_bar + 8;
   uint64_t* aempty_bar = afull_bar + Cfg::A_STAGES;
   uint64_t* tfull_bar = aempty_bar + Cfg::A_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -144,17 +150,17 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int NS = FMT ? 2 : P;              // B slots per (chunk, tap)
   const long long num_m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   // work index w -> (m tile, n tile).  MC: the pair shares w; rank r takes m tile 2*(w / N_TILES) + r.
-  const uint32_t rank = MC ? cluster_ctarank() : 0u;
-  const long long num_tiles = (MC ? (num_m_tiles + 1) / 2 : num_m_tiles) * N_TILES;
-  const long long w_begin = MC ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
-  const long long w_step = MC ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const long long num_tiles = (PAIR ? (num_m_tiles + 1) / 2 : num_m_tiles) * N_TILES;
+  const long long w_begin = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long w_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   // iteration it of this CTA (pair) -> work index.  order 1 (default): the N tiles of an M tile run back to back on
   // the same CTA (pair), so its operand rows are re-read from L2 by the SM that fetched them; order 0: strided
   // (the N tiles of an M tile run concurrently on neighbouring CTAs).
   auto work_index = [&](long long it) -> long long {
     return prm.order ? (w_begin + (it / N_TILES) * w_step) * N_TILES + it % N_TILES : w_begin + it * w_step;
   };
-  auto tile_m0 = [&](long long w) -> long long { return ((w / N_TILES) * (MC ? 2 : 1) + rank) * BLOCK_M; };
+  auto tile_m0 = [&](long long w) -> long long { return ((w / N_TILES) * (PAIR ? 2 : 1) + rank) * BLOCK_M; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -164,13 +170,14 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < b_slots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI_WARPS); }
+    // CG2: the issuer (CTA 0) waits for the epilogue warps of BOTH CTAs before it reuses an accumulator
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NUM_EPI_WARPS * (CG2 ? 2 : 1)); }
     fence_barrier_init();
   }
-  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) { if (CG2) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers (and, CG2, its TMEM) exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -188,31 +195,48 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int c8 = q == 0 ? 0 : 2 * cxp + (q - 1) * 2 * CHUNK;       // fp8 byte coordinate
         mbar_wait(&aempty_bar[astage], aphase ^ 1);
         uint8_t* sa = smem_a + astage * a_stage_bytes;
-        mbar_expect_tx(&afull_bar[astage], a_stage_bytes);
-        tma_load_3d(sa, &tmA, &afull_bar[astage], c16, (int)(m0 - g.Wp - 1), 0);
-        if (FMT == 1) tma_load_3d(sa + ra8 * ROW_BYTES, &tmA8, &afull_bar[astage], c8, (int)(m0 - g.Wp - 1), 0);
+        if (CG2) {
+          // both CTAs' bytes are reported to CTA 0's barrier: its MMAs read the A tiles of both
+          if (rank == 0) mbar_expect_tx(&afull_bar[astage], 2 * a_stage_bytes);
+          tma_load_3d_2sm(sa, &tmA, &afull_bar[astage], c16, (int)(m0 - g.Wp - 1), 0);
+          if (FMT == 1) tma_load_3d_2sm(sa + ra8 * ROW_BYTES, &tmA8, &afull_bar[astage], c8, (int)(m0 - g.Wp - 1), 0);
+        } else {
+          mbar_expect_tx(&afull_bar[astage], a_stage_bytes);
+          tma_load_3d(sa, &tmA, &afull_bar[astage], c16, (int)(m0 - g.Wp - 1), 0);
+          if (FMT == 1) tma_load_3d(sa + ra8 * ROW_BYTES, &tmA8, &afull_bar[astage], c8, (int)(m0 - g.Wp - 1), 0);
+        }
         if (++astage == Cfg::A_STAGES) { astage = 0; aphase ^= 1; }
         for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
           for (int sl = 0; sl < NS; ++sl) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
-            uint8_t* sb = smem + slot * B_SLOT_BYTES;
-            mbar_expect_tx(&full_bar[slot], B_SLOT_BYTES);
+            uint8_t* sb = smem + slot * SLOT_BYTES;
+            if (!CG2 || rank == 0) mbar_expect_tx(&full_bar[slot], B_SLOT_BYTES);
             const bool f8 = FMT == 1 && sl == 1;
             const CUtensorMap* tm = f8 ? &tmB8 : &tmB;
             const int kcol = f8 ? tap * 2 * prm.cpad + c8 : tap * prm.cpad + c16;
             const int plane = FMT == 1 ? 0 : sl;
             // MC: this CTA's half (128 rows) of the slot, delivered to both CTAs of the pair
-            if (MC) tma_load_3d_mc(sb + rank * (B_SLOT_BYTES / 2), tm, &full_bar[slot], kcol,
-                                   n0 + (int)rank * (BLOCK_N / 2), plane, (uint16_t)3);
+            if (CG2) tma_load_3d_2sm(sb, tm, &full_bar[slot], kcol, n0 + (int)rank * (BLOCK_N / 2), plane);
+            else if (MC) tma_load_3d_mc(sb + rank * (B_SLOT_BYTES / 2), tm, &full_bar[slot], kcol,
+                                        n0 + (int)rank * (BLOCK_N / 2), plane, (uint16_t)3);
             else tma_load_3d(sb, tm, &full_bar[slot], kcol, n0, plane);
             if (++slot == b_slots) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && lane == 0 && (!CG2 || rank == 0)) {
     // ===================== MMA issuer =====================
+    constexpr uint32_t kIdM = CG2 ? ((2u * BLOCK_M) >> 4) << 24 : 0u;     // cta_group::2: M = 256
+    constexpr uint32_t kIdBf16 = CG2 ? ((kIdesc & 0x00FFFFFFu) | kIdM) : kIdesc;
+    constexpr uint32_t kIdF16 = CG2 ? ((kIdescF16 & 0x00FFFFFFu) | kIdM) : kIdescF16;
+    auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+      if (CG2) umma_bf16_2sm(d, a, b, id, acc); else umma_bf16(d, a, b, id, acc);
+    };
+    auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+      if (CG2) umma_f8_2sm(d, a, b, id, acc); else umma_f8(d, a, b, id, acc);
+    };
     int slot = 0, astage = 0; uint32_t phase = 0, aphase = 0;
     long long it = 0;
     for (long long t; (t = work_index(it)) < num_tiles; ++it) {
@@ -236,12 +260,12 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int sl = 0; sl < NS; ++sl) {
             mbar_wait(&full_bar[slot], phase);
             tc_fence_after();
-            const uint32_t sb = smem_u32(smem + slot * B_SLOT_BYTES);
+            const uint32_t sb = smem_u32(smem + slot * SLOT_BYTES);
             if (FMT == 1 && sl == 0) {
               for (int k = 0; k < ks16; ++k) {                    // a0 * b0, fp16
                 if (prm.abl & 2) break;
-                umma_bf16(d_tmem, make_smem_desc(sa + k * 32, SW128_SBO, SW128_LAYOUT),
-                          make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdescF16, first);
+                mma16(d_tmem, make_smem_desc(sa + k * 32, SW128_SBO, SW128_LAYOUT),
+                      make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdF16, first);
                 first = 1u;
               }
             } else if (FMT == 1) {
@@ -249,8 +273,8 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int p = 0; p < 2; ++p)                         // e4m3 cross terms, K = 32 per dispatch
                 for (int k = 0; k < ks8; ++k) {
                   if (prm.abl & 1) break;
-                  umma_f8(d_tmem, make_smem_desc(sa + a_plane + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT),
-                          make_smem_desc(sb + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT), kIdescF16, first);
+                  mma8(d_tmem, make_smem_desc(sa + a_plane + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT),
+                       make_smem_desc(sb + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT), kIdF16, first);
                   first = 1u;
                 }
             } else {
@@ -259,20 +283,23 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int pa = 0; pa < P - sl; ++pa)
                 for (int k = 0; k < ks16; ++k) {
                   if (prm.abl & 2) break;
-                  umma_bf16(d_tmem, make_smem_desc(sa + pa * a_plane + k * 32, SW128_SBO, SW128_LAYOUT),
-                            make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdesc, first);
+                  mma16(d_tmem, make_smem_desc(sa + pa * a_plane + k * 32, SW128_SBO, SW128_LAYOUT),
+                        make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdBf16, first);
                   first = 1u;
                 }
             }
-            if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3);
+            if (CG2) umma_commit_2sm(&empty_bar[slot]);
+            else if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3);
             else umma_commit(&empty_bar[slot]);
             if (++slot == b_slots) { slot = 0; phase ^= 1; }
           }
         }
-        umma_commit(&aempty_bar[astage]);      // this CTA's nine taps have consumed the A stage
+        if (CG2) umma_commit_2sm(&aempty_bar[astage]);
+        else umma_commit(&aempty_bar[astage]);      // this CTA's nine taps have consumed the A stage
         if (++astage == Cfg::A_STAGES) { astage = 0; aphase ^= 1; }
       }
-      umma_commit(&tfull_bar[as]);
+      if (CG2) umma_commit_2sm(&tfull_bar[as]);
+      else umma_commit(&tfull_bar[as]);
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -421,14 +448,14 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) { if (CG2) mbar_arrive_cta0(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();       // the peer may still multicast into this CTA's smem / barriers
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (PAIR) cluster_sync_all();     // the peer may still send into this CTA's smem / barriers / TMEM
+  if (warp == 2) { if (CG2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ----------------------------------------------------------------------------------
@@ -540,8 +567,12 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
   const int ra8 = (BLOCK_M + 2 * (prm.W + 2) + 7) & ~7;
   const int smem_bytes = Cfg::smem_bytes(ra8);
   MVB_REQUIRE(ra8 <= Cfg::MAX_RA8 && smem_bytes <= 227 * 1024, "cell_fwd: grid width W=%d too large (A stage of %d rows, %d B shared memory)", prm.W, ra8, smem_bytes);
-  MVB_CHECK_CUDA(smem_opt_in(opt_plain, cell_fwd_kernel<P, false, FMT>, smem_bytes));
-  MVB_CHECK_CUDA(smem_opt_in(opt_mc, cell_fwd_kernel<P, true, FMT>, smem_bytes));
+  static SmemOptIn opt_cg2;
+  MVB_CHECK_CUDA(smem_opt_in(opt_plain, cell_fwd_kernel<P, 0, FMT>, smem_bytes));
+  MVB_CHECK_CUDA(smem_opt_in(opt_mc, cell_fwd_kernel<P, 1, FMT>, smem_bytes));
+  MVB_CHECK_CUDA(smem_opt_in(opt_cg2, cell_fwd_kernel<P, 2, FMT>, smem_bytes));
+  // pair mode: 2 = cta_group::2 (default), 1 = two cta_group::1 CTAs with weight multicast (MVB_CELL_PAIR=1)
+  static const int pair_mode = [] { const char* e = getenv("MVB_CELL_PAIR"); return e ? atoi(e) : 2; }();
   const long long m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   if (multicast && m_tiles >= 2 * (long long)num_sms) {
     cudaLaunchConfig_t cfg = {};
@@ -551,14 +582,15 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, true, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
+    if (pair_mode == 2) MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, 2, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
+    else MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, 1, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
     count_launch(1);
     g_last_variant = (FMT ? kPlanesF16F8 : P) * 2 + 1;
     return MVB_OK;
   }
   const long long num_tiles = m_tiles * N_TILES;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-  cell_fwd_kernel<P, false, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm.A, tm.B, tm.A8, tm.B8, prm);
+  cell_fwd_kernel<P, 0, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm.A, tm.B, tm.A8, tm.B8, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   g_last_variant = (FMT ? kPlanesF16F8 : P) * 2;
