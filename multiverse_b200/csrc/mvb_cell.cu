@@ -87,6 +87,7 @@ struct CellParams {
                             // 16-bit MMAs, 4 skip the epilogue's math and stores
   int fanout;               // > 1 (x-fold only): every GEMM row is a parent whose K = fanout children differ only in
                             // their one-hot input; the epilogue emits sample row smp*K + k for k < K (xf_ids [NS*K])
+  int hp_mixed;             // hp_out is written in the f16f8 format (else P bf16 planes)
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
   long long hp_plane_stride;  // elements between planes of hp_out
   int cpad_out;             // row pitch of hp_out (elements)
@@ -420,7 +421,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int v = 0; v < 4; ++v) ho[v] = make_float4(hn[4 * v], hn[4 * v + 1], hn[4 * v + 2], hn[4 * v + 3]);
           }
-          if (prm.hp_out && FMT == 1) {
+          if (prm.hp_out && prm.hp_mixed) {
             const float (&h0)[8] = *reinterpret_cast<const float (*)[8]>(&hn[0]);
             const float (&h1)[8] = *reinterpret_cast<const float (*)[8]>(&hn[8]);
             store_f16f8_x8(prm.hp_out, prm.hp_plane_stride, orow, prm.ch_off_out + ch0, prm.cpad_out, h0);
@@ -602,7 +603,11 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
              float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
              int fanout, cudaStream_t stream) {
+  // planes = format of the inputs and weights | (format of hp_out << 8), the latter only when it differs
+  const int P_out = (P >> 8) ? (P >> 8) : (P & 0xFF);
+  P &= 0xFF;
   const bool mixed = P == kPlanesF16F8;
+  MVB_REQUIRE(P_out == P || P_out == kPlanesF16F8 || (mixed && P_out == 2), "cell_fwd: output planes %d with input planes %d", P_out, P);
   MVB_REQUIRE((P >= 1 && P <= 3) || mixed, "cell_fwd: planes P=%d not in {1,2,3,%d}", P, kPlanesF16F8);
   MVB_REQUIRE(!mixed || !gates_out, "cell_fwd: the f16f8 format is an inference format (no gates_out)");
   MVB_REQUIRE(fanout <= 1 || (xf_B && xf_T2 && xf_ids && !gates_out && !row_map && !hp_out),
@@ -663,6 +668,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
     MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
     prm.skip_x = 1;
   }
+  prm.hp_mixed = P_out == kPlanesF16F8;
   prm.hp_out = reinterpret_cast<__nv_bfloat16*>(hp_out);
   prm.hp_plane_stride = hp_plane_stride; prm.cpad_out = cpad_out; prm.ch_off_out = ch_off_out;
   prm.R = R; prm.H = H; prm.W = W; prm.cpad = cpad; prm.forget_bias = forget_bias;

@@ -52,15 +52,16 @@ def _names(i):
 class ScaleWeights(object):
   """Packed / device-resident weights of one grid scale."""
 
-  def __init__(self, weights, i, planes, fast_class=False):
+  def __init__(self, weights, i, planes, fast_class=False, fast=False):
     nm = _names(i)
     f = lambda n: weights[n].detach().to(torch.float32).contiguous()
-    self.enc_class = ops.PackedCell(f(nm["enc_class"][0]), f(nm["enc_class"][1]), planes)
+    fp = ops.PLANES_F16F8 if fast else planes
+    self.enc_class = ops.PackedCell(f(nm["enc_class"][0]), f(nm["enc_class"][1]), fp)
     self.enc_reg = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), planes, comp=True)
     # class decoder fed by the graph attention: f16f8 operands (2 instead of 3 bf16-pass equivalents per product)
     self.dec_class = ops.PackedCell(f(nm["dec_class"][0]), f(nm["dec_class"][1]),
                                     ops.PLANES_F16F8 if fast_class else planes)
-    self.dec_reg = ops.PackedCell(f(nm["dec_reg"][0]), f(nm["dec_reg"][1]), planes)
+    self.dec_reg = ops.PackedCell(f(nm["dec_reg"][0]), f(nm["dec_reg"][1]), fp)
     self.emb_class = (f(nm["emb_class"][0]), f(nm["emb_class"][1]))
     self.emb_reg = (f(nm["emb_reg"][0]), f(nm["emb_reg"][1]))
     self.head_class = f(nm["head_class"])
@@ -84,6 +85,10 @@ class ConvRNNEngine(object):
     self.fast_class = (self.ALLOW_F16F8 and bool(cfg.use_gnn) and self.planes == 2 and
                        os.environ.get("MVB_F16F8", "1") != "0")
     self.class_planes = ops.PLANES_F16F8 if self.fast_class else self.planes
+    # class encoder and regression decoder (inputs in (-1,1): tanh outputs) use the same format; the regression
+    # ENCODER keeps bf16 planes: its raw pixel offsets (+-1.9e3) need the compensated x block.
+    self.fast = self.ALLOW_F16F8 and self.planes == 2 and os.environ.get("MVB_F16F8", "1") != "0"
+    self.fast_planes = ops.PLANES_F16F8 if self.fast else self.planes
     assert cfg.enc_hidden_size == ops.HIDDEN and cfg.dec_hidden_size == ops.HIDDEN, \
         "the kernels are specialised for hidden size 256 (every published config)"
     assert cfg.use_scene_enc, "only the published use_scene_enc path is implemented"
@@ -106,7 +111,7 @@ class ConvRNNEngine(object):
     self.scene_w = [(w[P_ + "scene_conv%d/W" % (i + 1)].float().contiguous(),
                      w[P_ + "scene_conv%d/b" % (i + 1)].float().contiguous())
                     for i in range(len(self.cfg.scene_grid_strides))]
-    self.scales = [ScaleWeights(w, i, self.planes, self.fast_class) if self.cfg.use_grids[i] else None
+    self.scales = [ScaleWeights(w, i, self.planes, self.fast_class, self.fast) if self.cfg.use_grids[i] else None
                    for i in range(len(self.cfg.scene_grids))]
 
   # ------------------------------------------------------------------ buffers
@@ -175,7 +180,7 @@ class ConvRNNEngine(object):
     n = labels_t.shape[1]
     t_len = labels_t.shape[0]
     sw = self.scales[i]
-    xh = self._xh("enc_class", n, h, w, sw.enc_class.cpad)
+    xh = self._xh("enc_class", n, h, w, sw.enc_class.cpad, self.fast_planes)
     c = [self._state("enc_c0", n, h, w), self._state("enc_c1", n, h, w)]
     h32 = self._state("enc_h32", n, h, w)
     # a previous call left the label pixels of its last two steps in the x blocks: clear them
@@ -367,7 +372,7 @@ class ConvRNNEngine(object):
         dec = lg.permute(1, 0, 2).reshape(n, tp, h, w, 1)
       emit("grid_pred_decoded", i, dec)
       # regression branch
-      xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad)
+      xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad, self.fast_planes)
       c_r, _ = self.encode_reg(i, obs_reg_t, xh_reg[0])
       offs = self.decode_reg(i, c_r, obs_reg_t[-1], tp, xh_reg)
       reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)

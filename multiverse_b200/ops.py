@@ -83,6 +83,12 @@ class PackedCell(object):
               self.cx, planes, int(self.comp), _stream())
 
 
+def _planes_arg(packed, xh_next):
+  """`planes` argument of the cell entry points: format of inputs/weights | (format of hp_out << 8) if it differs."""
+  po = packed.planes if xh_next is None else planes_of(xh_next)
+  return packed.planes if po == packed.planes else packed.planes | (po << 8)
+
+
 def alloc_xh(ns, h, w, cpad, planes, device):
   """Zeroed operand planes [P, R, cpad]; halo cells and channel padding must stay zero."""
   if planes == PLANES_F16F8:
@@ -122,14 +128,13 @@ def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
   """One ConvLSTM step.  xh_next: operand planes whose h block (channel offset = its cxp)
   receives the bf16 planes of h', or None."""
   assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
-  assert xh_next is None or planes_of(xh_next) == packed.planes
   if xh_next is not None:
     stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
   else:
     stride, cpad_out, off = 0, 0, 0
   _lib.call("mvb_convlstm_cell_fwd", _p(xh), _p(packed.w), _p(packed.bias), _p(c_in),
             _p(row_map), _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w,
-            packed.cpad, packed.planes, float(forget_bias), _stream())
+            packed.cpad, _planes_arg(packed, xh_next), float(forget_bias), _stream())
 
 
 class XFold(object):
@@ -148,14 +153,13 @@ def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns
                     forget_bias=1.0):
   """Class-decoder step with the embedded one-hot input folded into table look-ups."""
   assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
-  assert xh_next is None or planes_of(xh_next) == packed.planes
   if xh_next is not None:
     stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
   else:
     stride, cpad_out, off = 0, 0, 0
   _lib.call("mvb_convlstm_cell_fwd_onehot", _p(xh), _p(packed.w), _p(xf.B), _p(xf.T2), _p(ids), _p(c_in),
             _p(row_map), _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w,
-            packed.cpad, packed.planes, float(forget_bias), _stream())
+            packed.cpad, _planes_arg(packed, xh_next), float(forget_bias), _stream())
 
 
 def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, fanout, forget_bias=1.0):
