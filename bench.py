@@ -10,7 +10,10 @@ A "step" is one pass of the hot path over one batch of synthetic trajectories
       diverse beam (gamma 0.01, fix_num_timestep 1) on the 36x18 grid + greedy offset decoder,
       global batch 512, sharded over the ranks (strong scaling, no data-path collective).
   c3: greedy two-scale 36x18 + 18x9 with graph attention, global batch 256.
-Prints ONE JSON line on rank 0.
+  c5: train.py step (fwd + loss + BPTT + all-reduce + clip + Adadelta), two scales, global batch 1024.
+Prints ONE JSON line on rank 0.  Without --workload the line is c4's and carries the c3 and c5 records of the same
+invocation (same N, same process group) under "extra", c5 with its NCCL all-reduce time / bus bandwidth and, for
+N >= 2, the data-parallel equivalence self-check (ranks x shards == one rank x full batch).
 """
 from __future__ import annotations
 
@@ -131,7 +134,7 @@ def run_reference(args, wl):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  n_sample = 2
+  n_sample = 8          # CPU trajectories/s is batch-independent once the cores are busy; stated in `config`
   for _ in range(args.warmup):
     cpu_reference_run(wl["cfg"], n_sample, 1)
   vals = []
@@ -144,7 +147,10 @@ def run_reference(args, wl):
               steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * tot_t / len(vals),
               higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
               config=dict(workload=args.workload + ": " + wl["desc"], global_batch=wl["global_batch"],
-                          sample_per_step=n_sample, obs_len=8, pred_len=12),
+                          sample_per_step=n_sample, obs_len=8, pred_len=12,
+                          note="same workload as the b200 arm; each CPU step is a bounded sample of %d trajectories of "
+                               "the %d-trajectory batch (the CPU rate does not depend on the batch size)"
+                               % (n_sample, wl["global_batch"])),
               cpu_baseline=dict(value=value, unit="trajectories/s", cores=threads, kind="port",
                                 sample="%d trajectories per step through the torch-CPU restatement of "
                                        "code/pred_models.py (TF 1.15 not installable)" % n_sample),
@@ -152,10 +158,9 @@ def run_reference(args, wl):
   print(json.dumps(line), flush=True)
 
 
-def run_train(args, wl):
-  """Workload c5: one Trainer.step (code/pred_models.py:1719-1742) per timed step."""
-  from multiverse_b200 import build, ops, synthetic
-  from multiverse_b200.train_engine import TrainEngine
+def setup():
+  """Device + (for N > 1) the NCCL process group of this rank: (world, rank, local, dev, dist or None)."""
+  from multiverse_b200 import build
   build.build()
   world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -165,17 +170,60 @@ def run_train(args, wl):
   if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
+  return world, rank, local, dev, dist
+
+
+def ddp_equivalence(ctx):
+  """Self-check of the data-parallel training path on this run's own ranks: G ranks x 4 trajectories with the NCCL
+  all-reduce against rank 0's single-rank step on the 4G-trajectory batch (losses are means over equal shards, the
+  weight-decay term is batch independent: SURVEY.md section 8e).  Returns the three errors on rank 0."""
+  from multiverse_b200 import synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  world, rank, local, dev, dist = ctx
+  n = 4 * world
+  kw = dict(use_grids=[False, True], is_train=True, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+            clip_gradient_norm=10.0)
+  w = synthetic.make_weights(synthetic.make_config(batch_size=n, **kw), 3)
+  f = synthetic.make_feeds(synthetic.make_config(batch_size=n, **kw), n, 3, with_pred=True)
+  g = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+  def feeds_of(r, wsize):
+    sh = synthetic.shard_feeds(f, r, wsize)
+    return {k: ([g(a) for a in v] if isinstance(v, list) else g(v)) for k, v in sh.items() if k != "traj"}
+  eng = TrainEngine(synthetic.make_config(batch_size=n // world, **kw), {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  losses, _ = eng.train_step(feeds_of(rank, world), 0.2, dist)
+  res = None
+  if rank == 0:
+    full = TrainEngine(synthetic.make_config(batch_size=n, **kw), {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+    l_full, _ = full.train_step(feeds_of(0, 1), 0.2, None)
+    moved = max(float((full.params[k].cpu() - torch.from_numpy(w[k])).abs().max()) for k in eng.names)
+    res = dict(loss_rel=float((losses - l_full).abs().max() / l_full.abs().max()),
+               grad_rel=float((eng.flat_grad / world - full.flat_grad).abs().max() / full.flat_grad.abs().max()),
+               weight_abs=max(float((eng.params[k] - full.params[k]).abs().max()) for k in eng.names),
+               update_magnitude=moved, ranks=world, trajectories=n)
+    res["ok"] = bool(res["loss_rel"] < 1e-4 and res["grad_rel"] < 5e-4 and res["weight_abs"] < 1e-3 * moved + 1e-7)
+  if dist is not None:
+    dist.barrier()
+  return res
+
+
+def run_train(args, name, ctx, steps, warmup, cpu_baseline=True):
+  """Workload c5: one Trainer.step (code/pred_models.py:1719-1742) per timed step.  Returns the record on rank 0."""
+  from multiverse_b200 import ops, synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  wl = WORKLOADS[name]
+  world, rank, local, dev, dist = ctx
   gb = args.global_batch or wl["global_batch"]
   n_local = gb // world
   mb = min(wl["micro_batch"], n_local)
   cfg = synthetic.make_config(batch_size=n_local, **wl["cfg"])
   weights = synthetic.make_weights(cfg)
   f = synthetic.make_feeds(cfg, gb, with_pred=True)
-  sl = slice(rank * n_local, (rank + 1) * n_local)
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-  host = dict(scene_feat=pin(f["scene_feat"][sl]), obs_scene=pin(f["obs_scene"][sl] - rank * n_local))
+  shard = synthetic.shard_feeds(f, rank, world)
+  host = dict(scene_feat=pin(shard["scene_feat"]), obs_scene=pin(shard["obs_scene"]))
   for k in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
-    host[k] = [pin(a[sl]) for a in f[k]]
+    host[k] = [pin(a) for a in shard[k]]
   up = lambda t: t.to(dev, non_blocking=True)
   h2d = lambda: {k: ([up(a) for a in v] if isinstance(v, list) else up(v)) for k, v in host.items()}
   h2d_bytes = sum(t.numel() * t.element_size() for v in host.values() for t in (v if isinstance(v, list) else [v]))
@@ -201,15 +249,27 @@ def run_train(args, wl):
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
 
-  for _ in range(args.warmup):
+  for _ in range(warmup):
     eng.train_step(feeds, lr, dist, mb)
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
   ops.reset_launch_count()
-  ms_total = timed(lambda: eng.train_step(feeds, lr, dist, mb), args.steps)
+  eng.allreduce_events = []
+  ms_total = timed(lambda: eng.train_step(feeds, lr, dist, mb), steps)
   launches = ops.launch_count()
+  ar_events, eng.allreduce_events = eng.allreduce_events, None
   clocks = sampler.stop() if rank == 0 else None
+  ar = None
+  if ar_events:
+    # the one collective of the path (85 MB fp32 gradient bucket): device time per step, max over ranks, and the
+    # bus bandwidth 2 (G-1)/G * bytes / time (the NCCL convention; 725 GB/s measured at 1 GiB on this pool)
+    ar_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ar_events]))], device=dev, dtype=torch.float64)
+    dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
+    nbytes = eng.flat_grad.numel() * 4
+    ar = dict(ms_per_step=float(ar_ms.item()), bytes=nbytes,
+              bus_gbs=2.0 * (world - 1) / world * nbytes / (float(ar_ms.item()) * 1e-3) / 1e9,
+              share_of_step=float(ar_ms.item()) / (ms_total / steps))
   host_loss = torch.empty(2 * sum(cfg.use_grids), dtype=torch.float32).pin_memory()
 
   def e2e_step():
@@ -217,17 +277,18 @@ def run_train(args, wl):
     host_loss.copy_(losses, non_blocking=True)
 
   e2e_step()
-  ms_e2e = timed(e2e_step, args.steps)
+  ms_e2e = timed(e2e_step, steps)
+  grad_mb = eng.flat_grad.numel() * 4 / 1e6
+  del eng
+  torch.cuda.empty_cache()
   if rank != 0:
-    if dist is not None:
-      dist.destroy_process_group()
-    return
+    return None
   peaks = load_peaks()
   fl = 3.0 * sum(cfg.obs_len * (cell_flops(h, w, 64) + cell_flops(h, w, 2)) + 2 * cfg.pred_len * cell_flops(h, w, 32)
                  for h, w in cfg.scene_grids) * gb / world
-  achieved = fl / (ms_total / args.steps * 1e-3) / 1e12
+  achieved = fl / (ms_total / steps * 1e-3) / 1e12
   cpu = None
-  if world == 1 and not args.no_cpu_baseline:
+  if world == 1 and cpu_baseline and not args.no_cpu_baseline:
     from oracle import multiverse_ref_torch as RT
     torch.set_num_threads(int(os.environ.get("MVB_CPU_THREADS", "0")) or min(32, os.cpu_count() or 1))
     c2 = synthetic.make_config(batch_size=2, **wl["cfg"])
@@ -237,27 +298,25 @@ def run_train(args, wl):
     dt = time.perf_counter() - t0
     cpu = dict(value=2 / dt, unit="trajectories/s", cores=torch.get_num_threads(), kind="port",
                sample="2 trajectories, one fwd+bwd (%.1f s) of the torch-CPU restatement (autograd); TF 1.15 is not installable" % dt)
-  line = dict(metric="training trajectories/sec (obs8->pred12, fwd+bwd+update)", value=gb * args.steps / (ms_total * 1e-3),
-              unit="trajectories/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-              ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+  line = dict(metric="training trajectories/sec (obs8->pred12, fwd+bwd+update)", value=gb * steps / (ms_total * 1e-3),
+              unit="trajectories/s", n_gpus=world, steps=steps, warmup=warmup,
+              ms_per_step=ms_total / steps, higher_is_better=True, scaling="strong", vs_baseline=None,
               dtype="f32", data="synthetic",
-              config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
+              config=dict(workload=name + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
                           micro_batch=mb, arithmetic="fp32-grade: bf16x%d operand planes, fp32 accumulate" % args.planes,
                           parallelism="data-parallel x%d, NCCL all-reduce of %.1f MB fp32 grads"
-                          % (world, eng.flat_grad.numel() * 4 / 1e6),
+                          % (world, grad_mb),
                           l2="activation store >> 126 MB L2, no flush needed"),
               clocks=clocks,
-              e2e=dict(value=gb * args.steps / (ms_e2e * 1e-3), unit="trajectories/s", ms_per_step=ms_e2e / args.steps,
+              e2e=dict(value=gb * steps / (ms_e2e * 1e-3), unit="trajectories/s", ms_per_step=ms_e2e / steps,
                        h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=host_loss.numel() * 4),
-              gpu_launches=int(launches),
+              gpu_launches=int(launches), allreduce=ar,
               roofline=dict(bound="tensor", kernel="whole train step (cell fwd + dgrad + wgrad GEMMs dominate)",
                             achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
                             frac=achieved / peaks["bf16_sustained"], traffic=None,
                             note="algorithmic FLOPs = 3 x forward cell FLOPs; ceiling 0.333 (3 bf16 passes)"),
               cpu_baseline=cpu)
-  print(json.dumps(line), flush=True)
-  if dist is not None:
-    dist.destroy_process_group()
+  return line
 
 
 def main():
@@ -266,31 +325,43 @@ def main():
   ap.add_argument("--steps", type=int, default=5)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="b200")
-  ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+  ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
   ap.add_argument("--global-batch", type=int, default=0)
   ap.add_argument("--planes", type=int, default=2)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-extras", action="store_true", help="default run: skip the c3 / c5 sub-records")
   args = ap.parse_args()
+  extras = args.workload is None and not args.no_extras and not args.global_batch
+  args.workload = args.workload or "c4"
   wl = WORKLOADS[args.workload]
   if args.impl == "reference":
     return run_reference(args, wl)
   args.warmup = max(args.warmup, 3)
-  if wl.get("train"):
-    return run_train(args, wl)
+  ctx = setup()
+  world, rank, local, dev, dist = ctx
+  run = run_train if wl.get("train") else run_infer
+  line = run(args, args.workload, ctx, args.steps, args.warmup)
+  if extras:
+    # the other two north_star workloads in the same invocation, at the same N and in the same process group
+    sub = {}
+    sub["c3"] = run_infer(args, "c3", ctx, max(args.steps, 5), args.warmup, cpu_baseline=False)
+    sub["c5"] = run_train(args, "c5", ctx, max(2, min(args.steps, 3)), args.warmup, cpu_baseline=False)
+    chk = ddp_equivalence(ctx) if world > 1 else None
+    if rank == 0:
+      sub["c5"]["ddp_equivalence"] = chk if chk is not None else "n/a at N=1 (tests/test_ddp_gpu.py runs it on 2 GPUs)"
+      line["extra"] = sub
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
 
-  from multiverse_b200 import build, ops, synthetic
+
+def run_infer(args, name, ctx, steps, warmup, cpu_baseline=True):
+  """Workloads c4 / c3: one forward (all decoders) per timed step.  Returns the record on rank 0."""
+  from multiverse_b200 import ops, synthetic
   from multiverse_b200.engine import ConvRNNEngine
-  build.build()
-
-  world = int(os.environ.get("WORLD_SIZE", "1"))
-  rank = int(os.environ.get("RANK", "0"))
-  local = int(os.environ.get("LOCAL_RANK", "0"))
-  torch.cuda.set_device(local)
-  dev = torch.device("cuda", local)
-  dist = None
-  if world > 1:
-    import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=dev)
+  wl = WORKLOADS[name]
+  world, rank, local, dev, dist = ctx
   gb = args.global_batch or wl["global_batch"]
   assert gb % world == 0
   n_local = gb // world
@@ -300,10 +371,7 @@ def main():
   # the batch shards by trajectory: rank r takes rows [r*n_local, (r+1)*n_local) and the scene
   # frames they index (re-compacted per shard like code/pred_utils.py:680-704)
   feeds_all = synthetic.make_feeds(cfg, gb)
-  sl = slice(rank * n_local, (rank + 1) * n_local)
-  host = dict(scene_feat=feeds_all["scene_feat"][sl], obs_scene=feeds_all["obs_scene"][sl] - rank * n_local,
-              grid_obs_labels=[a[sl] for a in feeds_all["grid_obs_labels"]],
-              grid_obs_regress=[a[sl] for a in feeds_all["grid_obs_regress"]])
+  host = synthetic.shard_feeds(feeds_all, rank, world)
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
   host_pinned = dict(scene_feat=pin(host["scene_feat"]), obs_scene=pin(host["obs_scene"]),
                      grid_obs_labels=[pin(a) for a in host["grid_obs_labels"]],
@@ -319,6 +387,7 @@ def main():
                   [host_pinned["scene_feat"], host_pinned["obs_scene"]] + host_pinned["grid_obs_labels"]
                   + host_pinned["grid_obs_regress"])
   eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in weights.items()}, dev, args.planes)
+  f16f8 = bool(eng.fast_class)
   dev_feeds = h2d()
   torch.cuda.synchronize()
 
@@ -347,19 +416,19 @@ def main():
     return float(ms.item())
 
   # ---- device-resident throughput (`value`) -------------------------------------------------
-  for _ in range(args.warmup):
+  for _ in range(warmup):
     eng.forward(dev_feeds)
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
   ops.reset_launch_count()
   eng.cell_events = []
-  ms_total = timed(lambda: eng.forward(dev_feeds), args.steps)
+  ms_total = timed(lambda: eng.forward(dev_feeds), steps)
   launches = ops.launch_count()
   events = eng.cell_events
   eng.cell_events = None
   clocks = sampler.stop() if rank == 0 else None
-  value = gb * args.steps / (ms_total * 1e-3)
+  value = gb * steps / (ms_total * 1e-3)
 
   # ---- end to end through the reference-facing call (`e2e`) --------------------------------------
   # What code/pred_models.py:1779 (Tester.step) and code/multifuture_inference.py:471 do: sess.run(fetches,
@@ -373,6 +442,7 @@ def main():
   sys.path.insert(0, os.path.join(ROOT, "multiverse_b200", "dropin"))
   import tensorflow as tf          # the shim (multiverse_b200/dropin/tensorflow), not TensorFlow
   import pred_models as pm
+  tf.reset_default_graph()
   margs = types.SimpleNamespace(**vars(cfg))
   margs.modelname, margs.use_soft_grid_class, margs.use_gt_grid, margs.is_train = "bench", False, False, False
   model = pm.get_model(margs, gpuid=local)
@@ -401,13 +471,14 @@ def main():
     res = e2e_step()
   assert all(isinstance(r, np.ndarray) for r in res[:2])
   del res
-  ms_e2e = timed(e2e_step, args.steps)
-  e2e_value = gb * args.steps / (ms_e2e * 1e-3)
+  ms_e2e = timed(e2e_step, steps)
+  e2e_value = gb * steps / (ms_e2e * 1e-3)
+  del sess, model
+  tf.reset_default_graph()
+  torch.cuda.empty_cache()
 
   if rank != 0:
-    if dist is not None:
-      dist.destroy_process_group()
-    return
+    return None
 
   # ---- roofline of the dominant kernel (fused ConvLSTM cell), measured live ------------------
   peaks = load_peaks()
@@ -423,48 +494,57 @@ def main():
   tp = os.path.join(ROOT, "profiles", "cell_traffic.json")
   if os.path.exists(tp):
     try:
-      traffic = json.load(open(tp)).get("%s_rows%d" % (args.workload, rows))
+      traffic = json.load(open(tp)).get("%s_rows%d" % (name, rows))
     except Exception:
       traffic = None
-  roofline = dict(bound="tensor", kernel="cell_fwd_kernel<P=%d> (%s step, %d sample rows of %dx%d)" % (
-                      args.planes, dom_tag, rows, h0, w0),
+  passes = args.planes * (args.planes + 1) // 2
+  if f16f8:
+    arith = ("fp32-grade: operands as one fp16 + two e4m3 planes (f16f8), per product one fp16 tensor pass + two "
+             "e4m3 passes at twice the rate into one fp32 TMEM accumulator (2 bf16-pass equivalents), fp32 gates/state; "
+             "the regression encoder (raw pixel offsets) keeps 2 bf16 planes / 3 passes")
+    ceil_note = ("fp32 parity costs one fp16 + two e4m3 tensor passes per product = 2 bf16-pass equivalents, so the "
+                 "ceiling of this fraction against the bf16 peak is 0.5")
+  else:
+    arith = ("fp32-grade: operands split into %d bf16 planes, %d tcgen05 passes per product, fp32 TMEM accumulate, "
+             "fp32 gates/state" % (args.planes, passes))
+    ceil_note = ("fp32 parity needs %d bf16 tensor passes per product, so the ceiling of this fraction is %.3f"
+                 % (passes, 1.0 / passes))
+  roofline = dict(bound="tensor", kernel="cell_fwd_kernel<%s, CTA pair cta_group::2> (%s step, %d sample rows of %dx%d)" % (
+                      "f16f8" if f16f8 else "P=%d" % args.planes, dom_tag, rows, h0, w0),
                   achieved=achieved, peak=peaks["bf16_sustained"], unit="TFLOP/s",
                   frac=achieved / peaks["bf16_sustained"], traffic=traffic,
                   peak_source=peaks["source"] + ", bf16 dense sustained (kernel timed inside a long step)",
-                  note="algorithmic FLOPs 2*M*N*K (dense, x block included); fp32 parity needs %d bf16 tensor "
-                       "passes per product, so the ceiling of this fraction is %.3f - times 9/8 on class-decoder "
-                       "steps, whose embedded one-hot x block is folded into table look-ups (1/9 of the MMAs skipped)"
-                       % (args.planes * (args.planes + 1) // 2, 2.0 / (args.planes * (args.planes + 1))),
+                  note="algorithmic FLOPs 2*M*N*K (dense, x block included); " + ceil_note + " - times 9/8 on "
+                       "class-decoder steps, whose embedded one-hot x block is folded into table look-ups (1/9 of the "
+                       "MMAs skipped)",
                   launches_timed=len(durs), avg_launch_ms=avg_ms,
                   cell_share_of_step=all_cell_ms / ms_total)
 
   # ---- CPU baseline beside it (N=1 only) ------------------------------------------------------
   cpu = None
-  if world == 1 and not args.no_cpu_baseline:
-    n_s = 4 if cfg.use_beam_search else 8
+  if world == 1 and cpu_baseline and not args.no_cpu_baseline:
+    n_s = 8
     v, dt, threads = cpu_reference_run(wl["cfg"], n_s, 1)
     cpu = dict(value=v, unit="trajectories/s", cores=threads, kind="port",
                sample="%d trajectories, one pass (%.1f s) of the torch-CPU restatement of "
                       "code/pred_models.py on all host threads; TF 1.15 is not installable" % (n_s, dt))
 
-  line = dict(metric=METRIC, value=value, unit="trajectories/s", n_gpus=world, steps=args.steps,
-              warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
+  line = dict(metric=METRIC if name == "c4" else "trajectories/sec (obs8->pred12, greedy two-scale)", value=value,
+              unit="trajectories/s", n_gpus=world, steps=steps,
+              warmup=warmup, ms_per_step=ms_total / steps, higher_is_better=True,
               scaling="strong", vs_baseline=None, dtype="f32",
               data="synthetic",
-              config=dict(workload=args.workload + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
+              config=dict(workload=name + ": " + wl["desc"], global_batch=gb, per_gpu_batch=n_local,
                           obs_len=cfg.obs_len, pred_len=cfg.pred_len, beam=cfg.beam_size,
                           parallelism="trajectory-sharded x%d, no collective" % world,
-                          arithmetic="fp32-grade: operands split into %d bf16 planes, %d tcgen05 passes per product, "
-                                     "fp32 TMEM accumulate, fp32 gates/state" % (args.planes, args.planes * (args.planes + 1) // 2),
+                          arithmetic=arith,
                           l2="working set per step (%.1f GB of state) >> 126 MB L2, no flush needed"
                              % (rows * (h0 + 1) * (w0 + 1) * 256 * 4 * 3 / 1e9),
                           gflop_per_trajectory=flops_per_trajectory(cfg) / 1e9),
-              clocks=clocks, e2e=dict(value=e2e_value, unit="trajectories/s", ms_per_step=ms_e2e / args.steps,
+              clocks=clocks, e2e=dict(value=e2e_value, unit="trajectories/s", ms_per_step=ms_e2e / steps,
                                       h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=d2h_bytes * world),
               gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
-  print(json.dumps(line), flush=True)
-  if dist is not None:
-    dist.destroy_process_group()
+  return line
 
 
 if __name__ == "__main__":

@@ -68,6 +68,9 @@ int mvb_pack_cell_weights(const float* kernel, const float* biases, void* w_plan
 /* Which cell kernel the calling process launched last: planes * 2 + (1 if the CTA-pair / weight-multicast
  * variant ran), -1 before the first launch.  Lets tests assert that the variant they mean to check ran. */
 int mvb_cell_last_variant(void);
+/* Bit mask of the cell kernel variants launched since the last call with reset != 0: bit (f * 2 + pair), f = 0, 1, 2
+ * for 1, 2, 3 bf16 planes and 3 for MVB_PLANES_F16F8; pair = the CTA-pair (cluster of two) variant. */
+long long mvb_cell_variants_seen(int reset);
 
 /* One cell step over NS sample rows:  (c_in, xh) -> (c_out, h).
  *   xh_planes  bf16 [P][NS*S][cpad]: concat([x (cx, zero-padded to roundup(cx,32)), h (256)])

@@ -21,6 +21,7 @@ SIGNATURES = {
     "mvb_reset_launch_count": [],
     "mvb_cell_cpad": [_i],
     "mvb_cell_last_variant": [],
+    "mvb_cell_variants_seen": [_i],
     "mvb_pack_cell_weights": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mvb_convlstm_cell_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                               _i, _i, _f, _vp],
@@ -62,7 +63,7 @@ SIGNATURES = {
     "mvb_decode_trajectories": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "mvb_beam_backtrace": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
 }
-_RESTYPES = {"mvb_last_error": C.c_char_p, "mvb_launch_count": C.c_longlong,
+_RESTYPES = {"mvb_last_error": C.c_char_p, "mvb_launch_count": C.c_longlong, "mvb_cell_variants_seen": C.c_longlong,
              "mvb_reset_launch_count": None}
 
 _lib = None

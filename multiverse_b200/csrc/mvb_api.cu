@@ -114,6 +114,7 @@ extern "C" {
 const char* mvb_last_error(void) { return get_error(); }
 int mvb_abi_version(void) { return 6; }
 int mvb_cell_last_variant(void) { return cell_last_variant(); }
+long long mvb_cell_variants_seen(int reset) { return (long long)cell_variants_seen(reset); }
 long long mvb_launch_count(void) { return g_launches; }
 void mvb_reset_launch_count(void) { g_launches = 0; }
 

@@ -557,7 +557,18 @@ int cell_xfold_tables(const float* kernel, const float* biases, const float* We,
 
 // variant of the last launch_cell() of this process: planes code * 2 + multicast (tests assert which kernel ran)
 static int g_last_variant = -1;
+static unsigned long long g_variants_seen = 0;      // bit (format index * 2 + pair): formats 1, 2, 3 planes, f16f8
 int cell_last_variant() { return g_last_variant; }
+unsigned long long cell_variants_seen(int reset) {
+  const unsigned long long v = g_variants_seen;
+  if (reset) g_variants_seen = 0;
+  return v;
+}
+static void note_variant(int planes, int pair) {
+  g_last_variant = planes * 2 + pair;
+  const int fi = planes == kPlanesF16F8 ? 3 : planes - 1;
+  g_variants_seen |= 1ull << (fi * 2 + pair);
+}
 
 struct CellMaps { CUtensorMap A, B, Bh, A8, B8, B8h; };
 
@@ -586,7 +597,7 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
     if (pair_mode == 2) MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, 2, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
     else MVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cell_fwd_kernel<P, 1, FMT>, tm.A, tm.Bh, tm.A8, tm.B8h, prm));
     count_launch(1);
-    g_last_variant = (FMT ? kPlanesF16F8 : P) * 2 + 1;
+    note_variant(FMT ? kPlanesF16F8 : P, 1);
     return MVB_OK;
   }
   const long long num_tiles = m_tiles * N_TILES;
@@ -594,7 +605,7 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
   cell_fwd_kernel<P, 0, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm.A, tm.B, tm.A8, tm.B8, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
-  g_last_variant = (FMT ? kPlanesF16F8 : P) * 2;
+  note_variant(FMT ? kPlanesF16F8 : P, 0);
   return MVB_OK;
 }
 

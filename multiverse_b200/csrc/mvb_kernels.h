@@ -14,6 +14,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              int cpad, int P, float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2,
              const int* xf_ids, int fanout, cudaStream_t stream);
 int cell_last_variant();
+unsigned long long cell_variants_seen(int reset);
 int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,
                       float* Bt, float* T2, cudaStream_t stream);
 int pack_cell_weights(const float* kernel, const float* biases, void* w_planes, float* bias_packed,

@@ -182,8 +182,12 @@ class _Train(object):
       path = save_path if step is None else "%s-%d" % (save_path, step)
       os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
       np.savez(path + ".npz", **{v.name.split(":")[0]: v.eval() for v in self._vars()})
-      with open(_index_file(os.path.dirname(os.path.abspath(path))), "w") as f:
-        f.write('model_checkpoint_path: "%s"\n' % path)
+      save_dir = os.path.dirname(os.path.abspath(path))
+      # TF's generate_checkpoint_state_proto: a relative save path is recorded RELATIVE TO THE CHECKPOINT
+      # DIRECTORY (get_checkpoint_state joins it back), an absolute one as given
+      entry = path if os.path.isabs(path) else os.path.relpath(path, save_dir)
+      with open(_index_file(save_dir), "w") as f:
+        f.write('model_checkpoint_path: "%s"\n' % entry)
       self._kept.append(path)
       while self.max_to_keep and len(self._kept) > self.max_to_keep:
         old = self._kept.pop(0)

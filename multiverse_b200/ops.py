@@ -24,6 +24,12 @@ def planes_of(t):
   return getattr(t, "mvb_planes", t.shape[0])
 
 
+def cell_variants_seen(reset=False):
+  """Set of (planes, pair) cell-kernel variants launched since the last reset."""
+  m = int(_lib.load().mvb_cell_variants_seen(int(bool(reset))))
+  return {((1, 2, 3, PLANES_F16F8)[b // 2], bool(b % 2)) for b in range(8) if m >> b & 1}
+
+
 def cell_last_variant():
   """planes * 2 + multicast of the cell kernel launched last (-1: none yet)."""
   return int(_lib.load().mvb_cell_last_variant())

@@ -118,6 +118,27 @@ def make_feeds(cfg, n=None, seed=20200614, with_pred=False):
   return feeds
 
 
+def shard_feeds(feeds, rank, world):
+  """Trajectory shard `rank` of `world` of a feed dict: the contiguous rows
+  [rank*N/world, (rank+1)*N/world) of every per-trajectory array and ONLY the scene frames those rows index,
+  re-compacted and re-indexed the way the reference compacts them per batch (code/pred_utils.py:680-704).  Keys
+  that are absent (grid_pred_* at inference) are skipped; lists are per-scale lists.  Used by bench.py (inference
+  and training arms), tests/ddp_check.py and the gloo sharding test - one definition of "a shard"."""
+  n = feeds["obs_scene"].shape[0]
+  assert n % world == 0, "the global batch must divide evenly over the ranks"
+  per = n // world
+  sl = slice(rank * per, (rank + 1) * per)
+  obs_scene = np.asarray(feeds["obs_scene"][sl])
+  frames, local = np.unique(obs_scene, return_inverse=True)
+  out = dict(scene_feat=feeds["scene_feat"][frames], obs_scene=local.reshape(obs_scene.shape).astype(np.int32))
+  for k in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
+    if k in feeds and len(feeds[k]):
+      out[k] = [a[sl] for a in feeds[k]]
+  if "traj" in feeds:
+    out["traj"] = feeds["traj"][sl]
+  return out
+
+
 def write_npz(path, cfg, n, seed=0):
   """A data_<split>.npz in the layout code/preprocess.py writes (:670-679, :789-813, :860-864)
   and code/pred_utils.read_data (:208-300) reads, filled with synthetic trajectories."""

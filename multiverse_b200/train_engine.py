@@ -300,7 +300,14 @@ class TrainEngine(ConvRNNEngine):
     world = 1
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
       world = dist.get_world_size()
+      ev = getattr(self, "allreduce_events", None)   # bench.py: CUDA events around the collective
+      if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
       dist.all_reduce(self.flat_grad)                # the one collective of the path
+      if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
       dist.all_reduce(losses)
       losses = losses / world
     self.apply_gradients(lr, world)

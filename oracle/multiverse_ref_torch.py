@@ -87,7 +87,7 @@ def decoder_greedy(first, state, tp, cell_w, emb_w, head_w, scene_mean, mask, us
 
 
 def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, diverse, gamma,
-                 fix_num_timestep):
+                 fix_num_timestep, margins=None):
   """Model.grid_decoder_beam_search, code/pred_models.py:474-806 (diverse rank through a full
   sort, as add_div_penalty :1197-1223 does)."""
   c0, h0 = state
@@ -112,6 +112,9 @@ def decoder_beam(first, state, tp, b, cell_w, emb_w, head_w, scene_mean, mask, d
       lp = lp + math.log(gamma) * rank.to(lp.dtype)
     cand = lp.reshape(n, b * v) if time > 1 else lp[:, 0]
     sc, idx = torch.topk(cand, b, dim=-1, sorted=True)
+    if margins is not None:      # [smallest gap between consecutive selected candidates, gap to the best unselected one]
+      top = torch.topk(cand, b + 1, dim=-1, sorted=True).values
+      margins.append(torch.stack([(top[:, :-2] - top[:, 1:-1]).min(-1).values, top[:, -2] - top[:, -1]], -1))
     if time <= fix_num_timestep:
       sc = torch.zeros_like(sc)
     ids, par = idx % v, idx // v
@@ -194,9 +197,11 @@ def _forward(cfg, w, feeds, dtype):
     enc_r = encoder(obs_reg, sw.enc_reg[0], sw.enc_reg[1], cfg.enc_hidden_size)
     scene_mean = convs[i].mean(1)
     if cfg.use_beam_search:
+      margins = []
       lg, ids, sc = decoder_beam(onehot[:, -1], enc, cfg.pred_len, cfg.beam_size, sw.dec_class,
                                  sw.emb_class, sw.head_class, scene_mean, mask, cfg.diverse_beam,
-                                 cfg.diverse_gamma, cfg.fix_num_timestep)
+                                 cfg.diverse_gamma, cfg.fix_num_timestep, margins)
+      out["beam_margins"] = torch.stack(margins, 1).numpy()      # [N, Tp, 2]: test infrastructure (near-tie masks)
       out["beam_outputs"] = [lg.numpy(), ids.numpy().astype(np.int32), sc.numpy()]   # no_grad only
       dec = lg[:, 0].reshape(n, cfg.pred_len, h, ww, 1)
     else:

@@ -82,3 +82,48 @@ ROLLOUTS = {
                            beam_size=5, diverse_beam=False, fix_num_timestep=0), 2),
     "greedy_native_18x32": (dict(batch_size=2, scene_h=36, scene_w=64, use_grids=[True, False]), 3),
 }
+
+
+# At-size rollouts (the shapes bench.py actually runs: CTA-pair cell kernel, x-fold + row_map, fan-out with K = 20).
+# Their goldens hold REDUCED statistics of the fp64 oracle run (tests/golden/make_golden_atsize.py), not the tensors.
+ROLLOUTS_ATSIZE = {
+    "beam_k20_n16": (dict(batch_size=16, use_grids=[True, False], use_beam_search=True, beam_size=20,
+                          diverse_beam=True, diverse_gamma=0.01, fix_num_timestep=1), 21),
+    "greedy_two_scale_n64": (dict(batch_size=64), 22),
+    "beam_k20_native_18x32_n4": (dict(batch_size=4, scene_h=36, scene_w=64, use_grids=[True, False],
+                                      use_beam_search=True, beam_size=20, diverse_beam=True, diverse_gamma=0.01,
+                                      fix_num_timestep=1), 23),
+}
+
+
+def rollout_stats(cfg, out):
+  """Size-reduced view of a forward() result (numpy arrays shaped like the reference fetches): what the at-size
+  goldens store and what the GPU run is reduced to before the comparison."""
+  import numpy as np
+  st = {}
+  n, tp = cfg.batch_size, cfg.pred_len
+  for i, (h, w) in enumerate(cfg.scene_grids):
+    if not cfg.use_grids[i]:
+      continue
+    v = h * w
+    lg = np.asarray(out["grid_pred_decoded"][i], np.float64).reshape(n, tp, v)
+    reg = np.asarray(out["grid_pred_reg_decoded"][i], np.float64).reshape(n, tp, v, 2)
+    am = lg.argmax(-1)
+    srt = np.sort(lg, -1)
+    cells = (np.arange(8) * 79 + 3) % v
+    st["argmax_%d" % i] = am.astype(np.int32)
+    st["margin_%d" % i] = srt[..., -1] - srt[..., -2]
+    st["lg_max_%d" % i] = srt[..., -1]
+    st["lg_mean_%d" % i] = lg.mean(-1)
+    st["lg_at_%d" % i] = lg[..., cells]
+    st["reg_at_argmax_%d" % i] = np.take_along_axis(reg, am[..., None, None], 2)[:, :, 0]
+    st["reg_mean_%d" % i] = reg.mean(2)
+    st["reg_at_%d" % i] = reg[:, :, cells]
+  if out.get("beam_outputs") is not None:
+    blg, ids, lp = out["beam_outputs"]
+    blg = np.asarray(blg, np.float64)
+    st["beam_ids"] = np.asarray(ids, np.int32)
+    st["beam_logprobs"] = np.asarray(lp, np.float64)
+    st["beam_lg_max"] = blg.max(-1)
+    st["beam_lg_mean"] = blg.mean(-1)
+  return st

@@ -21,18 +21,16 @@ kw = dict(use_grids=[False, True], is_train=True, grid_loss_weight=1.0, grid_reg
 w = synthetic.make_weights(synthetic.make_config(batch_size=N, **kw), 3)
 f = synthetic.make_feeds(synthetic.make_config(batch_size=N, **kw), N, 3, with_pred=True)
 g = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-def feeds_of(sl, base):
-  out = dict(scene_feat=g(f["scene_feat"][sl]), obs_scene=g(f["obs_scene"][sl] - base))
-  for k in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
-    out[k] = [g(a[sl]) for a in f[k]]
-  return out
+def feeds_of(r, wsize):
+  sh = synthetic.shard_feeds(f, r, wsize)       # the product's definition of a shard (bench.py uses the same)
+  return {k: ([g(a) for a in v] if isinstance(v, list) else g(v)) for k, v in sh.items() if k != "traj"}
 n_loc = N // world
 eng = TrainEngine(synthetic.make_config(batch_size=n_loc, **kw), {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
-losses, _ = eng.train_step(feeds_of(slice(rank * n_loc, (rank + 1) * n_loc), rank * n_loc), 0.2, dist)
+losses, _ = eng.train_step(feeds_of(rank, world), 0.2, dist)
 ok = True
 if rank == 0:
   full = TrainEngine(synthetic.make_config(batch_size=N, **kw), {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
-  l_full, _ = full.train_step(feeds_of(slice(0, N), 0), 0.2, None)
+  l_full, _ = full.train_step(feeds_of(0, 1), 0.2, None)
   e_loss = float((losses - l_full).abs().max() / l_full.abs().max())
   e_grad = float((eng.flat_grad / world - full.flat_grad).abs().max() / full.flat_grad.abs().max())
   e_w = max(float((eng.params[k] - full.params[k]).abs().max()) for k in eng.names)

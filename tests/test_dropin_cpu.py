@@ -98,6 +98,36 @@ def test_saver_round_trip_and_initializer(dropin, tmp_path):
     assert np.array_equal(v, w0[k])
 
 
+def test_saver_relative_path_round_trip(dropin, tmp_path, monkeypatch):
+  """The published commands pass a RELATIVE output base (`multiverse-models`, TRAINING.md:32-39): the `checkpoint`
+  index must then name the file relative to its own directory, as TF's generate_checkpoint_state_proto does, so
+  that get_checkpoint_state (which joins the directory back, code/pred_utils.py:186-188) finds it - train.py
+  followed by test.py --load_best, and train.py --load."""
+  tf, pm = dropin
+  args, _ = make_args(tmp_path, use_grids=[False, True])
+  model = pm.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  w0 = {k: v.copy() for k, v in model.weights().items()}
+  monkeypatch.chdir(tmp_path)
+  sess = tf.Session()
+  rel = os.path.join("out", "model", "00", "save", "save")
+  path = tf.train.Saver().save(sess, rel, global_step=7)
+  assert path == rel + "-7"
+  state = tf.train.get_checkpoint_state(os.path.join("out", "model", "00", "save"))
+  assert os.path.normpath(state.model_checkpoint_path) == os.path.normpath(path)
+  for v in tf.global_variables():
+    if v.dtype == "float32":
+      v.assign(np.zeros(v.get_shape(), dtype=np.float32))
+  tf.train.Saver([v for v in tf.global_variables() if "global_step" not in v.name]).restore(
+      sess, state.model_checkpoint_path)
+  for k, v in model.weights().items():
+    assert np.array_equal(v, w0[k])
+  # and from another working directory through an absolute directory name
+  monkeypatch.chdir("/")
+  st2 = tf.train.get_checkpoint_state(str(tmp_path / "out" / "model" / "00" / "save"))
+  assert os.path.exists(st2.model_checkpoint_path + ".npz")
+
+
 @pytest.mark.skipif(not have_ref, reason="reference tree not mounted")
 def test_get_feed_dict_equals_the_references(dropin, tmp_path, monkeypatch):
   """Our vectorised Model.get_feed_dict against the reference's own method

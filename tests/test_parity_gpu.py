@@ -328,6 +328,78 @@ def test_rollout_golden(dev, name):
       assert torch.equal(out["grid_pred_reg_decoded"][i], out2["grid_pred_reg_decoded"][i])
 
 
+@pytest.mark.parametrize("name", sorted(cases.ROLLOUTS_ATSIZE))
+def test_rollout_atsize(dev, name):
+  """The paths the benchmark runs, at sizes that select its kernel variants (CTA-pair cell kernel from 54 sample
+  rows of 36x18, f16f8 operands, x-fold + row_map, K = 20 fan-out), against the fp64 oracle's committed statistics:
+  beam ids bit-exact, margin-safe arg-max cells identical, logits / offsets within the 1e-4 bar."""
+  from multiverse_b200 import ops
+  from multiverse_b200.engine import ConvRNNEngine
+  over, seed = cases.ROLLOUTS_ATSIZE[name]
+  cfg = R.default_config(**over)
+  w = R.make_weights(cfg, seed); f = R.make_inputs(cfg, seed)
+  g = gold("atsize_" + name)
+  assert abs(float(g["checksum"]) - (cases.checksum(*w.values()) + cases.checksum(f["scene_feat"], f["traj"]))) < 1e-6
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  ops.cell_variants_seen(reset=True)
+  out = eng.forward(to_dev(f, dev))
+  seen = ops.cell_variants_seen()
+  assert (ops.PLANES_F16F8, True) in seen, "the CTA-pair f16f8 cell kernel did not run: %s" % sorted(seen)
+  res = dict(grid_pred_decoded=[t.cpu().numpy() if torch.is_tensor(t) else t for t in out["grid_pred_decoded"]],
+             grid_pred_reg_decoded=[t.cpu().numpy() if torch.is_tensor(t) else t for t in out["grid_pred_reg_decoded"]],
+             beam_outputs=None if out["beam_outputs"] is None else [t.cpu().numpy() for t in out["beam_outputs"]])
+  st = cases.rollout_stats(cfg, res)
+  worst = {}
+  n = cfg.batch_size
+  # Beam search is discontinuous in its scores, and this model's beams are near-degenerate: children of one parent
+  # that differ only in a far-away input cell carry logits equal to ~1e-9 (the fp64 oracle's own gaps between
+  # consecutive selected candidates are 1e-9..1e-7 in EVERY sample), so the ORDER of such twins inside the beam is
+  # not defined at fp32 accuracy.  What is defined is the SET of K id sequences, as long as the gap between the
+  # K-th selected and the best unselected candidate is well above the kernels' error at every step; samples where
+  # even that gap is a near-tie (known from the oracle, stored in the golden) are excluded from the beam-dependent
+  # comparisons.  The kept fraction is asserted and printed.
+  safe_n = np.ones(n, bool)
+  if cfg.use_beam_search:
+    safe_n = g["beam_margins"][:, :, 1].min(1) > 2e-4
+    assert safe_n.mean() >= 0.75, "too few boundary-safe samples: %.2f" % safe_n.mean()
+  ok_rows = safe_n
+  if cfg.use_beam_search:     # best-beam logits depend on the beam order: compare where the ids agree beam for beam
+    ok_rows = np.array([np.array_equal(st["beam_ids"][j], g["beam_ids"][j]) for j in range(n)])
+  for i in range(len(cfg.scene_grids)):
+    if not cfg.use_grids[i]:
+      continue
+    ls = np.abs(g["lg_max_%d" % i]).max(); rs = np.abs(g["reg_at_%d" % i]).max()
+    for k, scale in (("lg_max", ls), ("lg_mean", ls), ("lg_at", ls), ("reg_at_argmax", rs), ("reg_mean", rs), ("reg_at", rs)):
+      key = "%s_%d" % (k, i)
+      rows = ok_rows if k.startswith("lg") or k == "reg_at_argmax" else np.ones(n, bool)
+      d = np.abs(st[key] - g[key])[rows]
+      if k == "reg_at_argmax":
+        d = d[(st["argmax_%d" % i] == g["argmax_%d" % i])[rows]]
+      worst[key] = float(d.max() / scale)
+      assert worst[key] < TOL, (key, worst[key])
+    if not cfg.use_beam_search:
+      safe = g["margin_%d" % i] > 1e-4
+      assert safe.mean() > 0.9 and np.array_equal(st["argmax_%d" % i][safe], g["argmax_%d" % i][safe])
+  if cfg.use_beam_search:
+    # order-sensitive statistics (per-beam logits, best-beam logits above) are compared on the samples whose ids
+    # agree beam for beam; the id SETS must agree on every boundary-safe sample
+    seqs = lambda a: sorted(map(tuple, a.tolist()))
+    exact = np.array([np.array_equal(st["beam_ids"][j], g["beam_ids"][j]) for j in range(n)])
+    same_set = np.array([seqs(st["beam_ids"][j]) == seqs(g["beam_ids"][j]) for j in range(n)])
+    assert same_set[safe_n].all(), "beam id sets differ from the oracle on boundary-safe samples %s" % np.nonzero(safe_n & ~same_set)[0]
+    assert exact.mean() >= 0.5, "beam order differs from the oracle in most samples: %s" % exact
+    assert np.abs(np.sort(st["beam_logprobs"], 1) - np.sort(g["beam_logprobs"], 1))[safe_n].max() < 1e-3
+    bs = np.abs(g["beam_lg_max"]).max()
+    for k in ("beam_lg_max", "beam_lg_mean"):
+      worst[k] = float(np.abs(st[k] - g[k])[exact].max() / bs)
+      assert worst[k] < TOL, (k, worst[k])
+    print("atsize %s: %d of %d samples boundary-safe (gap to the best unselected candidate > 2e-4), id sets equal on "
+          "all of them; ids equal beam for beam in %d samples; the others' smallest in-beam oracle gaps: %s"
+          % (name, int(safe_n.sum()), n, int(exact.sum()),
+             ["%.1e" % g["beam_margins"][j, :, 0].min() for j in np.nonzero(~exact)[0]]))
+  print("atsize %s: variants %s worst rel errs %s" % (name, sorted(seen), {k: "%.1e" % v for k, v in worst.items()}))
+
+
 def test_full_size_properties(dev):
   """BASELINE-size batch (config 3 shape, N=64 here): size-independent properties - a batch is the
   concatenation of its shards (what multi-GPU sharding relies on), outputs are finite, halos stay

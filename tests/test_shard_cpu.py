@@ -1,7 +1,8 @@
 # coding=utf-8
 """World-size-2 gloo test (CPU) of the multi-GPU host logic: trajectory sharding of the feeds
 (bench.py / SURVEY.md §8e: contiguous split, per-shard scene-frame re-indexing, no data-path
-collective) and the max-over-ranks timing reduction.  The per-shard compute is replaced by a
+collective) and the max-over-ranks timing reduction, through multiverse_b200.synthetic.shard_feeds - the function
+bench.py's inference and training arms and tests/ddp_check.py call.  The per-shard compute is replaced by a
 deterministic row-wise function, so the test checks exactly what the sharding must guarantee:
 concatenating the shards' outputs reproduces the full-batch output, row for row."""
 import os
@@ -16,13 +17,7 @@ import torch.multiprocessing as mp
 from multiverse_b200 import synthetic
 
 
-def shard_feeds(feeds, rank, world):
-  n = feeds["obs_scene"].shape[0]
-  per = n // world
-  sl = slice(rank * per, (rank + 1) * per)
-  return dict(scene_feat=feeds["scene_feat"][sl], obs_scene=feeds["obs_scene"][sl] - rank * per,
-              grid_obs_labels=[a[sl] for a in feeds["grid_obs_labels"]],
-              grid_obs_regress=[a[sl] for a in feeds["grid_obs_regress"]])
+shard_feeds = synthetic.shard_feeds      # the function bench.py and tests/ddp_check.py shard with
 
 
 def rowwise_digest(f):
@@ -68,3 +63,19 @@ def test_shard_frame_indices_are_local():
   for r in range(3):
     sh = shard_feeds(full, r, 3)
     assert sh["obs_scene"].min() == 0 and sh["obs_scene"].max() == sh["scene_feat"].shape[0] - 1
+
+
+def test_shard_recompacts_shared_and_unordered_frames():
+  """Trajectories that share segmentation frames, in any order (the reference reuses one frame for many steps and
+  rows, code/preprocess.py:390-400): a shard carries only the frames it indexes, and every row still sees its own."""
+  cfg = synthetic.make_config(batch_size=8)
+  full = synthetic.make_feeds(cfg, 8, seed=5)
+  rng = np.random.default_rng(0)
+  full["obs_scene"] = rng.integers(0, 8, size=full["obs_scene"].shape).astype(np.int32)
+  want = rowwise_digest(full)
+  for world in (2, 4):
+    got = np.concatenate([rowwise_digest(shard_feeds(full, r, world)) for r in range(world)])
+    assert np.array_equal(got, want)
+    for r in range(world):
+      sh = shard_feeds(full, r, world)
+      assert sh["scene_feat"].shape[0] == len(np.unique(full["obs_scene"][r * (8 // world):(r + 1) * (8 // world)]))
