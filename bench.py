@@ -456,11 +456,18 @@ def run_infer(args, name, ctx, steps, warmup, cpu_baseline=True):
                model.obs_length: np.full((n_local,), cfg.obs_len, dtype="int32"),
                model.pred_length: np.full((n_local,), cfg.pred_len, dtype="int32"), model.is_train: False}
   fetches = []
+  # row f-1: what Model.get_feed_dict feeds for a pred_utils batch - the observed trajectories and the cell centres
+  # instead of the dense [N,T,h,w,2] offsets, which the engine rebuilds on the device (bit-identical)
+  feed_dict[model.obs_traj] = np.ascontiguousarray(host["traj64"][:, :cfg.obs_len])
+  centers = synthetic.grid_centers(cfg)
+  e2e_h2d = [host_pinned["scene_feat"].numpy(), host_pinned["obs_scene"].numpy(), feed_dict[model.obs_traj]]
   for i in range(len(cfg.scene_grids)):
     if cfg.use_grids[i]:
       feed_dict[model.grid_obs_labels[i]] = host_pinned["grid_obs_labels"][i].numpy()
-      feed_dict[model.grid_obs_regress[i]] = host_pinned["grid_obs_regress"][i].numpy()
+      feed_dict[model.grid_centers[i]] = np.asarray(centers[i], dtype=np.float64)
+      e2e_h2d += [feed_dict[model.grid_obs_labels[i]], feed_dict[model.grid_centers[i]]]
       fetches += [model.grid_pred_decoded[i], model.grid_pred_reg_decoded[i]]
+  e2e_h2d_bytes = sum(a.nbytes for a in e2e_h2d)
   if cfg.use_beam_search:
     fetches.append(model.beam_outputs)
 
@@ -542,7 +549,12 @@ def run_infer(args, name, ctx, steps, warmup, cpu_baseline=True):
                              % (rows * (h0 + 1) * (w0 + 1) * 256 * 4 * 3 / 1e9),
                           gflop_per_trajectory=flops_per_trajectory(cfg) / 1e9),
               clocks=clocks, e2e=dict(value=e2e_value, unit="trajectories/s", ms_per_step=ms_e2e / steps,
-                                      h2d_bytes_per_step=h2d_bytes * world, d2h_bytes_per_step=d2h_bytes * world),
+                                      h2d_bytes_per_step=e2e_h2d_bytes * world, d2h_bytes_per_step=d2h_bytes * world,
+                                      h2d_note="segmentation frames %.1f MB + trajectories, labels and cell centres "
+                                               "%.3f MB (dense offsets are rebuilt on the device, row f-1; they were "
+                                               "%.1f MB)" % (host_pinned["scene_feat"].numel() * 4 * world / 1e6,
+                                                            (e2e_h2d_bytes - host_pinned["scene_feat"].numel() * 4) * world / 1e6,
+                                                            sum(t.numel() * 4 for t in host_pinned["grid_obs_regress"]) * world / 1e6)),
               gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
   return line
 

@@ -103,12 +103,13 @@ int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, co
 /* First K-row step of the beam decoder (pred_models.py:611-666 right after the first selection): the K = fanout
  * children of a sample share their parent - the same graph-attended h and the same c - and differ only in the
  * selected cell ids[s*K + k], i.e. in the folded table rows.  The GEMM runs once per PARENT row (xh_planes, c_in:
- * NS sample rows) and the epilogue emits the K children (c_out, h32_out: NS*K sample rows, child-major within a
- * sample): 1/K of the MMAs, identical values. */
+ * NS sample rows; its raw accumulators go to `workspace`, fp32 [NS*S, 1024], caller-allocated) and a second,
+ * HBM-bound kernel emits the K children (c_out, h32_out: NS*K sample rows, child-major within a sample): 1/K of the
+ * MMAs, identical values. */
 int mvb_convlstm_cell_fwd_onehot_fanout(const void* xh_planes, const void* w_planes, const float* table_B,
                                         const float* table_T2, const int32_t* ids, const float* c_in,
-                                        float* c_out, float* h32_out, int64_t NS, int fanout, int H, int W,
-                                        int cpad, int planes, float forget_bias, void* stream);
+                                        float* c_out, float* h32_out, float* workspace, int64_t NS, int fanout,
+                                        int H, int W, int cpad, int planes, float forget_bias, void* stream);
 
 /* ---- a13: BPTT step of the cell (Trainer, pred_models.py:1636-1742; tf.gradients :1698 through
  *      ConvLSTMCell) ------------------------------------------------------------------------ */
@@ -259,6 +260,23 @@ int mvb_emb_dense_fwd(const float* x, const float* We, const float* be, int E, v
 int mvb_beam_step(const float* logits, const float* score_in, float* score_out, int32_t* ids_out,
                   int32_t* parents_out, int32_t* row_map_out, int64_t N, int B, int V,
                   int first_step, int zero_scores, int diverse, float log_gamma, void* stream);
+/* ---- f-3: multi-future evaluation metrics on the device ------------------------------------------------------
+ * minADE / minFDE of code/multifuture_eval_trajs.py:41-78 (get_min :16-21): for every trajectory n and ground-truth
+ * future g (gt_len[n,g] steps, 0 = absent) the prediction k in [0,K) with the smallest left-to-right SUM of per-step
+ * L2 errors (first index on ties) -> its per-step errors ade_err [N,G,Tg] fp64 (0 beyond the length) and index
+ * ade_idx [N,G]; and the smallest final-step error fde [N,G] fp64 with its index.  Double arithmetic on the fp32
+ * inputs, i.e. the reference's numpy float64 results bit for bit.
+ *   pred fp32 [N,K,Tp,2] (mvb_decode_trajectories output), gt fp32 [N,G,Tg,2], Tg <= Tp. */
+int mvb_min_ade_fde(const float* pred, const float* gt, const int32_t* gt_len, double* ade_err, int32_t* ade_idx,
+                    double* fde, int32_t* fde_idx, int64_t N, int G, int K, int Tp, int Tg, void* stream);
+/* NLL of code/multifuture_eval_trajs_prob.py:113-131,170-197: for trajectory n and evaluated step steps[j] the grid
+ * distribution p = sum_b softmax(logprobs[n,:])[b] * softmax(logits[n,b,steps[j],:]) (get_hw_prob) and
+ * nll[n,j] = mean over the present ground-truth cells gt_idx[n,j,g] >= 0 of -log(p[cell] + DBL_EPSILON)
+ * (compute_nll); count[n,j] = number of present cells (0: the reference skips that step).
+ *   logits fp32 [N,K,Tp,V] and logprobs fp32 [N,K] = beam_outputs[0], [2]; gt_idx int32 [N,J,G]; steps int32 [J]. */
+int mvb_beam_nll(const float* logits, const float* logprobs, const int32_t* gt_idx, const int32_t* steps, double* nll,
+                 int32_t* count, int64_t N, int K, int Tp, int V, int J, int G, void* stream);
+
 /* Back-trace (pred_models.py:689-764): step_ids/step_parents int32 [Tp,N,B], step_logits fp32
  * [Tp,N,B,V] -> out_ids int32 [N,B,Tp], out_logits fp32 [N,B,Tp,V]. */
 int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,

@@ -26,7 +26,7 @@ SIGNATURES = {
     "mvb_convlstm_cell_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                               _i, _i, _f, _vp],
     "mvb_cell_xfold_tables": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "mvb_convlstm_cell_fwd_onehot_fanout": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
+    "mvb_convlstm_cell_fwd_onehot_fanout": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "mvb_convlstm_cell_fwd_onehot": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64,
                                      _i, _i, _i, _i, _f, _vp],
     "mvb_convlstm_cell_fwd_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _i, _i,
@@ -61,6 +61,8 @@ SIGNATURES = {
     "mvb_beam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "mvb_traj_to_grid": [_vp, _vp, C.c_double, C.c_double, _vp, _vp, _i64, _i, _i, _vp],
     "mvb_decode_trajectories": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
+    "mvb_min_ade_fde": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "mvb_beam_nll": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "mvb_beam_backtrace": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
 }
 _RESTYPES = {"mvb_last_error": C.c_char_p, "mvb_launch_count": C.c_longlong, "mvb_cell_variants_seen": C.c_longlong,

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmultiverse_b200.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["mvb_api.cu", "mvb_cell.cu", "mvb_layout.cu", "mvb_scene.cu", "mvb_gnn.cu",
-           "mvb_head.cu", "mvb_beam.cu", "mvb_train.cu", "mvb_train2.cu"]
+           "mvb_head.cu", "mvb_beam.cu", "mvb_train.cu", "mvb_train2.cu", "mvb_metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

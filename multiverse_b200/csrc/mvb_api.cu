@@ -112,7 +112,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 6; }
+int mvb_abi_version(void) { return 7; }
 int mvb_cell_last_variant(void) { return cell_last_variant(); }
 long long mvb_cell_variants_seen(int reset) { return (long long)cell_variants_seen(reset); }
 long long mvb_launch_count(void) { return g_launches; }
@@ -149,10 +149,10 @@ int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, co
 }
 int mvb_convlstm_cell_fwd_onehot_fanout(const void* xh_planes, const void* w_planes, const float* table_B,
                                         const float* table_T2, const int32_t* ids, const float* c_in,
-                                        float* c_out, float* h32_out, int64_t NS, int fanout, int H, int W,
-                                        int cpad, int planes, float forget_bias, void* stream) {
+                                        float* c_out, float* h32_out, float* workspace, int64_t NS, int fanout, int H,
+                                        int W, int cpad, int planes, float forget_bias, void* stream) {
   return cell_fwd(xh_planes, w_planes, table_B, c_in, nullptr, c_out, h32_out, nullptr, 0, 0, 0, NS, H, W, cpad,
-                  planes, forget_bias, nullptr, table_B, table_T2, ids, fanout, S(stream));
+                  planes, forget_bias, workspace, table_B, table_T2, ids, fanout, S(stream));
 }
 
 int mvb_convlstm_cell_fwd_train(const void* xh_planes, const void* w_planes,
@@ -310,6 +310,14 @@ int mvb_beam_step(const float* logits, const float* score_in, float* score_out, 
 int mvb_decode_trajectories(const int32_t* ids, const float* offsets, const float* centers, float* out,
                             int64_t N, int K, int Tp, int V, void* stream) {
   return decode_trajectories(ids, offsets, centers, out, N, K, Tp, V, S(stream));
+}
+int mvb_min_ade_fde(const float* pred, const float* gt, const int32_t* gt_len, double* ade_err, int32_t* ade_idx,
+                    double* fde, int32_t* fde_idx, int64_t N, int G, int K, int Tp, int Tg, void* stream) {
+  return min_ade_fde(pred, gt, gt_len, ade_err, ade_idx, fde, fde_idx, N, G, K, Tp, Tg, S(stream));
+}
+int mvb_beam_nll(const float* logits, const float* logprobs, const int32_t* gt_idx, const int32_t* steps, double* nll,
+                 int32_t* count, int64_t N, int K, int Tp, int V, int J, int G, void* stream) {
+  return beam_nll(logits, logprobs, gt_idx, steps, nll, count, N, K, Tp, V, J, G, S(stream));
 }
 int mvb_beam_backtrace(const int32_t* step_ids, const int32_t* step_parents,
                        const float* step_logits, int32_t* out_ids, float* out_logits, int64_t N,

@@ -85,8 +85,8 @@ struct CellParams {
   int order;                // work order, see work_index()
   int abl;                  // debug ablations (MVB_CELL_ABL; results are then WRONG): 1 skip the fp8 MMAs, 2 skip the
                             // 16-bit MMAs, 4 skip the epilogue's math and stores
-  int fanout;               // > 1 (x-fold only): every GEMM row is a parent whose K = fanout children differ only in
-                            // their one-hot input; the epilogue emits sample row smp*K + k for k < K (xf_ids [NS*K])
+  float* preact_out;        // [R, 1024] raw accumulators (packed column order) instead of the state update: first stage of
+                            // the fan-out step (fanout_children_kernel turns every parent row into its K children)
   int hp_mixed;             // hp_out is written in the f16f8 format (else P bf16 planes)
   __nv_bfloat16* hp_out;    // [P][R][cpad_out] plane base or nullptr
   long long hp_plane_stride;  // elements between planes of hp_out
@@ -97,6 +97,23 @@ struct CellParams {
   int cpad;                 // K channels per tap (multiple of 32)
   float forget_bias;
 };
+
+// The state update of one element from its four gate pre-activations, with the roundings spelled out so that the
+// cell epilogue and the fan-out kernel produce the same bits:  c' = sigmoid(f + forget_bias) c + sigmoid(i) tanh(j);
+// h' = tanh(c') sigmoid(o).
+struct GateOut { float ai, aj, af, ao, c, h; };
+__device__ __forceinline__ GateOut lstm_update(float xi, float xj, float xf, float xo, float cprev, float forget_bias) {
+  GateOut r;
+  r.ai = sigmoid_acc(xi); r.aj = tanh_acc(xj); r.af = sigmoid_acc(__fadd_rn(xf, forget_bias)); r.ao = sigmoid_acc(xo);
+  r.c = __fmaf_rn(r.af, cprev, __fmul_rn(r.ai, r.aj));
+  r.h = __fmul_rn(tanh_acc(r.c), r.ao);
+  return r;
+}
+// pre-activation from the accumulator: acc * (column scale, f16f8 only) + (bias + x-fold table row)
+template <int FMT>
+__device__ __forceinline__ float preact(float acc, float scale, float q) {
+  return FMT ? __fmaf_rn(acc, scale, q) : __fadd_rn(acc, q);
+}
 
 // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) |
@@ -364,45 +381,63 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int v = 0; v < 16; ++v) cprev[v] = 0.f;
         }
         tmem_ld_wait();
-        if (valid) {
-         const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
-         if (FMT == 1) {      // the weights were stored times 2^S per column: scale the accumulators back once
-           const float* sp = prm.col_scale + nt * BLOCK_N + j0;
+        if (valid && prm.preact_out) {
+          float* gp = prm.preact_out + row * kGates + nt * BLOCK_N + j0;
 #pragma unroll
-           for (int v = 0; v < 16; ++v) {
-             gi[v] = __float_as_uint(__uint_as_float(gi[v]) * __ldg(sp + 0 * TILE_CH + v));
-             gj[v] = __float_as_uint(__uint_as_float(gj[v]) * __ldg(sp + 1 * TILE_CH + v));
-             gf[v] = __float_as_uint(__uint_as_float(gf[v]) * __ldg(sp + 2 * TILE_CH + v));
-             go[v] = __float_as_uint(__uint_as_float(go[v]) * __ldg(sp + 3 * TILE_CH + v));
-           }
-         }
-#pragma unroll 1
-         for (int k = 0; k < prm.fanout; ++k) {      // 1 pass, or one per child of this parent row
-          const long long osmp = prm.fanout > 1 ? psmp * prm.fanout + k : psmp;
-          const long long orow = prm.fanout > 1 ? osmp * g.S + prem : row;
-          const float* xft = prm.xf_B ? xft_of(prm.xf_ids[osmp]) : nullptr;
+          for (int v = 0; v < 4; ++v) {
+            reinterpret_cast<uint4*>(gp + 0 * TILE_CH)[v] = make_uint4(gi[4 * v], gi[4 * v + 1], gi[4 * v + 2], gi[4 * v + 3]);
+            reinterpret_cast<uint4*>(gp + 1 * TILE_CH)[v] = make_uint4(gj[4 * v], gj[4 * v + 1], gj[4 * v + 2], gj[4 * v + 3]);
+            reinterpret_cast<uint4*>(gp + 2 * TILE_CH)[v] = make_uint4(gf[4 * v], gf[4 * v + 1], gf[4 * v + 2], gf[4 * v + 3]);
+            reinterpret_cast<uint4*>(gp + 3 * TILE_CH)[v] = make_uint4(go[4 * v], go[4 * v + 1], go[4 * v + 2], go[4 * v + 3]);
+          }
+        } else if (valid) {
+          const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
+          const float* xft = prm.xf_B ? xft_of(prm.xf_ids[psmp]) : nullptr;
           const float* tptr = xft ? xft + nt * BLOCK_N + j0 : nullptr;
+          const float* sptr = FMT == 1 ? prm.col_scale + nt * BLOCK_N + j0 : bptr;
           float cn[16], hn[16];
 #pragma unroll
-          for (int v = 0; v < 16; ++v) {
-            float xi = __uint_as_float(gi[v]) + __ldg(bptr + 0 * TILE_CH + v);
-            float xj = __uint_as_float(gj[v]) + __ldg(bptr + 1 * TILE_CH + v);
-            float xf = __uint_as_float(gf[v]) + __ldg(bptr + 2 * TILE_CH + v);
-            float xo = __uint_as_float(go[v]) + __ldg(bptr + 3 * TILE_CH + v);
+          for (int v4 = 0; v4 < 4; ++v4) {
+            // bias (or bias-folded table), the x-fold table row of this cell and the column scales: one 128-bit load
+            // per gate and 4 columns
+            const float4* b4 = reinterpret_cast<const float4*>(bptr) + v4;
+            const float4* s4 = reinterpret_cast<const float4*>(sptr) + v4;
+            float4 qi = __ldg(b4 + 0 * (TILE_CH / 4)), qj = __ldg(b4 + 1 * (TILE_CH / 4)),
+                   qf = __ldg(b4 + 2 * (TILE_CH / 4)), qo = __ldg(b4 + 3 * (TILE_CH / 4));
             if (tptr) {
-              xi += __ldg(tptr + 0 * TILE_CH + v); xj += __ldg(tptr + 1 * TILE_CH + v);
-              xf += __ldg(tptr + 2 * TILE_CH + v); xo += __ldg(tptr + 3 * TILE_CH + v);
+              const float4* t4 = reinterpret_cast<const float4*>(tptr) + v4;
+              const float4 ti = __ldg(t4 + 0 * (TILE_CH / 4)), tj = __ldg(t4 + 1 * (TILE_CH / 4)),
+                           tf = __ldg(t4 + 2 * (TILE_CH / 4)), to = __ldg(t4 + 3 * (TILE_CH / 4));
+              qi.x = __fadd_rn(qi.x, ti.x); qi.y = __fadd_rn(qi.y, ti.y); qi.z = __fadd_rn(qi.z, ti.z); qi.w = __fadd_rn(qi.w, ti.w);
+              qj.x = __fadd_rn(qj.x, tj.x); qj.y = __fadd_rn(qj.y, tj.y); qj.z = __fadd_rn(qj.z, tj.z); qj.w = __fadd_rn(qj.w, tj.w);
+              qf.x = __fadd_rn(qf.x, tf.x); qf.y = __fadd_rn(qf.y, tf.y); qf.z = __fadd_rn(qf.z, tf.z); qf.w = __fadd_rn(qf.w, tf.w);
+              qo.x = __fadd_rn(qo.x, to.x); qo.y = __fadd_rn(qo.y, to.y); qo.z = __fadd_rn(qo.z, to.z); qo.w = __fadd_rn(qo.w, to.w);
             }
-            const float ai = sigmoid_acc(xi), aj = tanh_acc(xj), af = sigmoid_acc(xf + prm.forget_bias),
-                        ao = sigmoid_acc(xo);
-            const float c1 = af * cprev[v] + ai * aj;
-            cn[v] = c1;
-            hn[v] = tanh_acc(c1) * ao;
-            if (prm.gates_out) {   // reuse the accumulator registers as staging for the stores below
-              gi[v] = __float_as_uint(ai); gj[v] = __float_as_uint(aj);
-              gf[v] = __float_as_uint(af); go[v] = __float_as_uint(ao);
+            float4 si = qi, sj = qj, sf = qf, so = qo;
+            if (FMT == 1) {
+              si = __ldg(s4 + 0 * (TILE_CH / 4)); sj = __ldg(s4 + 1 * (TILE_CH / 4));
+              sf = __ldg(s4 + 2 * (TILE_CH / 4)); so = __ldg(s4 + 3 * (TILE_CH / 4));
+            }
+            const float bi[4] = {qi.x, qi.y, qi.z, qi.w}, bj[4] = {qj.x, qj.y, qj.z, qj.w},
+                        bf[4] = {qf.x, qf.y, qf.z, qf.w}, bo[4] = {qo.x, qo.y, qo.z, qo.w};
+            const float ci[4] = {si.x, si.y, si.z, si.w}, cj[4] = {sj.x, sj.y, sj.z, sj.w},
+                        cf[4] = {sf.x, sf.y, sf.z, sf.w}, co4[4] = {so.x, so.y, so.z, so.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int v = 4 * v4 + e;
+              const GateOut r = lstm_update(preact<FMT>(__uint_as_float(gi[v]), ci[e], bi[e]),
+                                            preact<FMT>(__uint_as_float(gj[v]), cj[e], bj[e]),
+                                            preact<FMT>(__uint_as_float(gf[v]), cf[e], bf[e]),
+                                            preact<FMT>(__uint_as_float(go[v]), co4[e], bo[e]), cprev[v], prm.forget_bias);
+              cn[v] = r.c;
+              hn[v] = r.h;
+              if (prm.gates_out) {   // reuse the accumulator registers as staging for the stores below
+                gi[v] = __float_as_uint(r.ai); gj[v] = __float_as_uint(r.aj);
+                gf[v] = __float_as_uint(r.af); go[v] = __float_as_uint(r.ao);
+              }
             }
           }
+          const long long orow = row;
           if (prm.gates_out) {
             float* gp = prm.gates_out + orow * kGates + nt * BLOCK_N + j0;
 #pragma unroll
@@ -444,7 +479,6 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               po[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
             }
           }
-         }
         }
       }
       tc_fence_before();
@@ -457,6 +491,81 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   if (PAIR) cluster_sync_all();     // the peer may still send into this CTA's smem / barriers / TMEM
   if (warp == 2) { if (CG2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+}
+
+// ----------------------------------------------------------------------------------
+// Fan-out step of the beam decoder (the first K-row step: every child's parent is its sample's single t0 row, so the
+// K children share the graph-attended h, the GEMM and c, and differ only in the folded table rows of their selected
+// cell).  Stage 1 = the cell kernel with preact_out (one GEMM per PARENT row, raw accumulators to HBM: 4 KB per cell);
+// stage 2 = this kernel: one warp per parent cell keeps the 1024 accumulators, the bias-folded table row and c in
+// registers and emits the K children (c', h') - HBM-bound on its 2 KB of stores per child cell, where the round-1
+// in-epilogue fan-out ran the K passes on 8 warps per SM (25 ms against a 2.5 ms HBM bound).
+// Bit-identical to the K-times tiled launch: same preact() / lstm_update() roundings.
+// ----------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256)
+fanout_children_kernel(const float* __restrict__ acc, const float* __restrict__ col_scale,
+                       const float* __restrict__ xf_B, const float* __restrict__ xf_T2, const int* __restrict__ ids,
+                       const float* __restrict__ c_in, float* __restrict__ c_out, float* __restrict__ h32_out,
+                       long long NS, int K, Grid g, float forget_bias) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int hw = g.H * g.W;
+  if (wid >= NS * hw) return;
+  const long long smp = wid / hw;
+  const int cell = (int)(wid - smp * hw);
+  const int y = cell / g.W, x = cell - y * g.W;
+  const int rem = y * g.Wp + x;
+  const long long prow = smp * g.S + rem;
+  const int ch0 = lane * 8;                                  // this lane's 8 hidden channels
+  const int col0 = (ch0 / TILE_CH) * BLOCK_N + ch0 % TILE_CH;   // packed column of gate 0 (gate g: + g * 64)
+  const int cy = y == 0 ? 0 : (y == g.H - 1 ? 2 : 1), cx = x == 0 ? 0 : (x == g.W - 1 ? 2 : 1);
+  float a[4][8], q0[4][8], sc[4][8], cp[8];
+#pragma unroll
+  for (int gt = 0; gt < 4; ++gt) {
+    const float4* ap = reinterpret_cast<const float4*>(acc + prow * kGates + col0 + gt * TILE_CH);
+    const float4* bp = reinterpret_cast<const float4*>(xf_B + (cy * 3 + cx) * kGates + col0 + gt * TILE_CH);
+    const float4* sp = reinterpret_cast<const float4*>((FMT ? col_scale : xf_B) + col0 + gt * TILE_CH);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const float4 av = __ldg(ap + v), bv = __ldg(bp + v), sv = __ldg(sp + v);
+      a[gt][4 * v] = av.x; a[gt][4 * v + 1] = av.y; a[gt][4 * v + 2] = av.z; a[gt][4 * v + 3] = av.w;
+      q0[gt][4 * v] = bv.x; q0[gt][4 * v + 1] = bv.y; q0[gt][4 * v + 2] = bv.z; q0[gt][4 * v + 3] = bv.w;
+      sc[gt][4 * v] = sv.x; sc[gt][4 * v + 1] = sv.y; sc[gt][4 * v + 2] = sv.z; sc[gt][4 * v + 3] = sv.w;
+    }
+  }
+  {
+    const float4* cq = reinterpret_cast<const float4*>(c_in + prow * kHidden + ch0);
+    const float4 c0 = __ldg(cq), c1 = __ldg(cq + 1);
+    cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
+  }
+  for (int k = 0; k < K; ++k) {
+    const long long osmp = smp * K + k;
+    const int id = ids[osmp];
+    const int ay = id / g.W, ax = id - ay * g.W;
+    const int ry = y - ay, rx = x - ax;
+    const float* tp = nullptr;      // x-fold table row of this cell for the child's selected cell (inside its 5x5)
+    if (ry >= -2 && ry <= 2 && rx >= -2 && rx <= 2) {
+      const int acy = ay == 0 ? 0 : (ay == g.H - 1 ? 2 : 1), acx = ax == 0 ? 0 : (ax == g.W - 1 ? 2 : 1);
+      tp = xf_T2 + ((long long)(acy * 3 + acx) * 25 + (ry + 2) * 5 + (rx + 2)) * kGates + col0;
+    }
+    float cn[8], hn[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      float q[4];
+#pragma unroll
+      for (int gt = 0; gt < 4; ++gt) q[gt] = tp ? __fadd_rn(q0[gt][v], __ldg(tp + gt * TILE_CH + v)) : q0[gt][v];
+      const GateOut r = lstm_update(preact<FMT>(a[0][v], sc[0][v], q[0]), preact<FMT>(a[1][v], sc[1][v], q[1]),
+                                    preact<FMT>(a[2][v], sc[2][v], q[2]), preact<FMT>(a[3][v], sc[3][v], q[3]),
+                                    cp[v], forget_bias);
+      cn[v] = r.c; hn[v] = r.h;
+    }
+    const long long orow = osmp * g.S + rem;
+    float4* co = reinterpret_cast<float4*>(c_out + orow * kHidden + ch0);
+    co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+    float4* ho = reinterpret_cast<float4*>(h32_out + orow * kHidden + ch0);
+    ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+  }
 }
 
 // ----------------------------------------------------------------------------------
@@ -620,9 +729,9 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   const bool mixed = P == kPlanesF16F8;
   MVB_REQUIRE(P_out == P || P_out == kPlanesF16F8 || (mixed && P_out == 2), "cell_fwd: output planes %d with input planes %d", P_out, P);
   MVB_REQUIRE((P >= 1 && P <= 3) || mixed, "cell_fwd: planes P=%d not in {1,2,3,%d}", P, kPlanesF16F8);
-  MVB_REQUIRE(!mixed || !gates_out, "cell_fwd: the f16f8 format is an inference format (no gates_out)");
-  MVB_REQUIRE(fanout <= 1 || (xf_B && xf_T2 && xf_ids && !gates_out && !row_map && !hp_out),
-              "cell_fwd: fanout=%d needs the x-fold tables and no row_map / gates_out / hp_out", fanout);
+  MVB_REQUIRE(!mixed || !gates_out || fanout > 1, "cell_fwd: the f16f8 format is an inference format (no gates_out)");
+  MVB_REQUIRE(fanout <= 1 || (xf_B && xf_T2 && xf_ids && gates_out && c_in && h32_out && !row_map && !hp_out),
+              "cell_fwd: fanout=%d needs the x-fold tables, c_in, h32_out, a [R,1024] fp32 workspace and no row_map / hp_out", fanout);
   MVB_REQUIRE(cpad == kHidden + XPAD || cpad == kHidden + 2 * XPAD, "cell_fwd: cpad=%d must be 288 or 320 (x block of 32 or 64 channels)", cpad);
   MVB_REQUIRE(NS > 0 && H > 0 && W > 0, "cell_fwd: bad sizes NS=%lld H=%d W=%d", NS, H, W);
   MVB_REQUIRE(xh_planes && w_planes && bias && c_out, "cell_fwd: null pointer");
@@ -665,10 +774,10 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
 
   CellParams prm;
   prm.bias = bias; prm.col_scale = col_scale; prm.c_in = c_in; prm.row_map = row_map; prm.c_out = c_out; prm.h32_out = h32_out;
-  prm.gates_out = gates_out;
+  prm.gates_out = fanout > 1 ? nullptr : gates_out;
+  prm.preact_out = fanout > 1 ? gates_out : nullptr;      // fan-out: stage 1 stores the raw accumulators there
   prm.xf_B = xf_B; prm.xf_T2 = xf_T2; prm.xf_ids = xf_ids;
   prm.skip_x = 0;
-  prm.fanout = fanout > 1 ? fanout : 1;
   // measured on the K=20 beam step: order 1 keeps the DRAM reads at 1.05x algorithmic with the CTA-pair clusters
   // (order 0: 1.39x) and is 3 % faster; MVB_CELL_ORDER=0 selects the strided order for A/B runs.
   static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : 1; }();
@@ -688,11 +797,22 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   MVB_CHECK_CUDA(cudaGetDevice(&dev));
   MVB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   switch (P) {
-    case 1: return launch_cell<1, 0>(tm, prm, num_sms, multicast, stream);
-    case 2: return launch_cell<2, 0>(tm, prm, num_sms, multicast, stream);
-    case kPlanesF16F8: return launch_cell<2, 1>(tm, prm, num_sms, multicast, stream);
-    default: return launch_cell<3, 0>(tm, prm, num_sms, multicast, stream);
+    case 1: rc = launch_cell<1, 0>(tm, prm, num_sms, multicast, stream); break;
+    case 2: rc = launch_cell<2, 0>(tm, prm, num_sms, multicast, stream); break;
+    case kPlanesF16F8: rc = launch_cell<2, 1>(tm, prm, num_sms, multicast, stream); break;
+    default: rc = launch_cell<3, 0>(tm, prm, num_sms, multicast, stream); break;
   }
+  if (rc || fanout <= 1) return rc;
+  // fan-out stage 2: every parent row -> its K children (c_out / h32_out hold NS * fanout sample rows)
+  const long long warps = NS * H * W;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  if (mixed) fanout_children_kernel<1><<<blocks, 256, 0, stream>>>(gates_out, col_scale, xf_B, xf_T2, xf_ids, c_in, c_out,
+                                                                    h32_out, NS, fanout, g, forget_bias);
+  else fanout_children_kernel<0><<<blocks, 256, 0, stream>>>(gates_out, col_scale, xf_B, xf_T2, xf_ids, c_in, c_out,
+                                                             h32_out, NS, fanout, g, forget_bias);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
 }
 
 // ----------------------------------------------------------------------------------

@@ -152,12 +152,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 
 // activations: fp32, ~1e-6 accurate (MUFU.EX2 is 2^-22; tanh.approx at 2^-11 is NOT
 // acceptable for the 1e-4 parity bar, so it is never used)
 // ----------------------------------------------------------------------------------
+// MUFU.RCP (1 ulp) instead of the correctly rounded __frcp_rn (MUFU + Newton fix-up, ~5 instructions): the gate
+// epilogue of the cell evaluates five of these per state element and is co-critical with the f16f8 mainloop
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float sigmoid_acc(float x) {
-  return __frcp_rn(1.0f + __expf(-x));
+  return rcp_fast(1.0f + __expf(-x));
 }
 __device__ __forceinline__ float tanh_acc(float x) {
   // 1 - 2/(exp(2x)+1): exact limits at +-inf, abs error ~1e-7
-  return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
+  return 1.0f - 2.0f * rcp_fast(__expf(2.0f * x) + 1.0f);
 }
 
 // ----------------------------------------------------------------------------------

@@ -63,6 +63,12 @@ int beam_backtrace(const int* step_ids, const int* step_parents, const float* st
                    int* out_ids, float* out_logits, long long N, int B, int Tp, int V,
                    cudaStream_t stream);
 
+// mvb_metrics.cu
+int min_ade_fde(const float* pred, const float* gt, const int* gt_len, double* ade_err, int* ade_idx, double* fde,
+                int* fde_idx, long long N, int G, int K, int Tp, int Tg, cudaStream_t stream);
+int beam_nll(const float* logits, const float* logprobs, const int* gt_idx, const int* steps, double* nll, int* count,
+             long long N, int K, int Tp, int V, int J, int G, cudaStream_t stream);
+
 // mvb_train.cu
 int cell_dgrad(const void* dg_planes, const void* wd_planes, float* dxh, long long NS, int H, int W,
                int cpad, int P, int need_x, cudaStream_t stream);

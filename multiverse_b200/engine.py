@@ -312,8 +312,10 @@ class ConvRNNEngine(object):
         # differ only in the selected cell, i.e. in the folded table rows -> attention and GEMM once per sample,
         # the cell epilogue fans the K children out (ops.cell_fwd_onehot_fanout; 1/K of the step's MMAs)
         ops.gnn_attend_fwd(h32_t0, scene_mean, xh1[1], h, w, n, beam=1, row_map=None)
+        ws = self._buf(("beam_fanout_ws", n, h, w), lambda: torch.empty(
+            (ops.halo_rows(n, h, w), 4 * ops.HIDDEN), dtype=torch.float32, device=dev))
         self._cell_fanout("beam_fanout", xh1[1], sw.dec_class, xf, step_ids[0].view(-1), c_t0, c[1 - cur_c], h32,
-                          h, w, n, b)
+                          h, w, n, b, workspace=ws)
       else:
         ops.gnn_attend_fwd(h_src, scene_mean, nxt, h, w, ns, beam=b, row_map=row_map)
         self._cell_onehot("beam", nxt, sw.dec_class, xf, step_ids[time - 1].view(-1), c_src, c[1 - cur_c], h32,

@@ -168,11 +168,17 @@ def cell_fwd_onehot(xh, packed, xf, ids, c_in, c_out, h32_out, xh_next, h, w, ns
             packed.cpad, _planes_arg(packed, xh_next), float(forget_bias), _stream())
 
 
-def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, fanout, forget_bias=1.0):
-  """First K-row beam step: GEMM on the `ns` parent rows, epilogue emits ns*fanout child rows (ids [ns*fanout])."""
+def cell_fwd_onehot_fanout(xh, packed, xf, ids, c_in, c_out, h32_out, h, w, ns, fanout, forget_bias=1.0,
+                           workspace=None):
+  """First K-row beam step: GEMM on the `ns` parent rows (raw accumulators to `workspace` fp32 [ns*S, 1024]), then
+  the children kernel emits ns*fanout child rows (ids [ns*fanout])."""
   assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
+  if workspace is None:
+    workspace = torch.empty((halo_rows(ns, h, w), 4 * HIDDEN), dtype=torch.float32, device=xh.device)
+  assert workspace.numel() >= halo_rows(ns, h, w) * 4 * HIDDEN and workspace.dtype == torch.float32
   _lib.call("mvb_convlstm_cell_fwd_onehot_fanout", _p(xh), _p(packed.w), _p(xf.B), _p(xf.T2), _p(ids), _p(c_in),
-            _p(c_out), _p(h32_out), ns, fanout, h, w, packed.cpad, packed.planes, float(forget_bias), _stream())
+            _p(c_out), _p(h32_out), _p(workspace), ns, fanout, h, w, packed.cpad, packed.planes, float(forget_bias),
+            _stream())
 
 
 def nhwc_to_planes(src, xh, ch_off, h, w, comp=False):
@@ -372,6 +378,33 @@ def decode_trajectories(ids, offs, centers, out):
   n, k, tp = ids.shape
   _lib.call("mvb_decode_trajectories", _p(ids), _p(offs), _p(centers), _p(out), n, k, tp, offs.shape[2],
             _stream())
+
+
+def min_ade_fde(pred, gt, gt_len):
+  """pred fp32 [N,K,Tp,2], gt fp32 [N,G,Tg,2], gt_len int32 [N,G] -> (ade_err fp64 [N,G,Tg], ade_idx int32 [N,G],
+  fde fp64 [N,G], fde_idx int32 [N,G]): code/multifuture_eval_trajs.py:41-78 on the device."""
+  n, k, tp, _ = pred.shape
+  g, tg = gt.shape[1], gt.shape[2]
+  dev = pred.device
+  ade_err = torch.empty((n, g, tg), dtype=torch.float64, device=dev)
+  ade_idx = torch.empty((n, g), dtype=torch.int32, device=dev)
+  fde = torch.empty((n, g), dtype=torch.float64, device=dev)
+  fde_idx = torch.empty((n, g), dtype=torch.int32, device=dev)
+  _lib.call("mvb_min_ade_fde", _p(pred), _p(gt), _p(gt_len), _p(ade_err), _p(ade_idx), _p(fde), _p(fde_idx), n, g, k,
+            tp, tg, _stream())
+  return ade_err, ade_idx, fde, fde_idx
+
+
+def beam_nll(logits, logprobs, gt_idx, steps):
+  """logits fp32 [N,K,Tp,V], logprobs fp32 [N,K], gt_idx int32 [N,J,G] (-1 = absent), steps int32 [J] ->
+  (nll fp64 [N,J], count int32 [N,J]): code/multifuture_eval_trajs_prob.py:113-131,170-197 on the device."""
+  n, k, tp, v = logits.shape
+  j, g = gt_idx.shape[1], gt_idx.shape[2]
+  nll = torch.empty((n, j), dtype=torch.float64, device=logits.device)
+  cnt = torch.empty((n, j), dtype=torch.int32, device=logits.device)
+  _lib.call("mvb_beam_nll", _p(logits), _p(logprobs), _p(gt_idx), _p(steps), _p(nll), _p(cnt), n, k, tp, v, j, g,
+            _stream())
+  return nll, cnt
 
 
 def traj_to_grid(traj, centers, h_gap, w_gap, labels, regress, h, w):

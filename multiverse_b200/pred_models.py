@@ -103,6 +103,13 @@ class Model(object):
       self.grid_obs_regress.append(ph("grid_obs_regress", i))
       self.grid_pred_labels_T.append(ph("grid_pred_labels_T", i))
       self.grid_pred_regress.append(ph("grid_pred_regress", i))
+    # Extension placeholders: the observed trajectories [N,T,2] float64 and the cell
+    # centres [h,w,2] float64 of a scale.  Fed INSTEAD of grid_obs_regress, they make the engine build the dense
+    # per-cell offsets on the device (mvb_traj_to_grid, bit-identical to get_grid_input,
+    # code/multifuture_inference.py:115-156 == code/preprocess.py:436-475): 128 bytes per trajectory on the PCIe
+    # bus instead of 41 KB per trajectory and scale.  get_feed_dict uses them when the batch carries both.
+    self.obs_traj = ph("obs_traj")
+    self.grid_centers = [ph("grid_centers", i) for i, _ in enumerate(config.scene_grids)]
     self.beam_outputs = None
     self.loss = None
     self.build_forward()
@@ -230,7 +237,46 @@ class Model(object):
     fd[self.obs_scene] = obs_scene
     fd[self.obs_scene_mask] = mask
     fd[self.scene_feat] = data["batch_scene_feat"]
+    self._compact_grid_feeds(fd, batch, n_have, is_train)
     return fd
+
+  def _compact_grid_feeds(self, fd, batch, n_have, is_train):
+    """Row f-1: when the batch carries the observed trajectories and the grid centres the dense offsets were
+    computed from (pred_utils.read_data puts both there: data["obs_traj"], shared["grid_center_<j>"]), feed those
+    instead of the dense [N,T,h,w,2] arrays; the engine regenerates the arrays on the device.  Guarded by a
+    sampled consistency check - dense == float32(trajectory - centre) on 32 random cells per scale - so a batch
+    whose dense targets were edited independently keeps the dense path.  config.device_grid_feeds=False turns it
+    off; training keeps the dense path (its loss also needs the dense prediction targets)."""
+    cfg = self.config
+    if is_train or not getattr(cfg, "device_grid_feeds", True) or not n_have:
+      return
+    data, shared = batch.data, getattr(batch, "shared", None)
+    if shared is None or "obs_traj" not in data:
+      return
+    used = [j for j in range(len(cfg.scene_grids)) if cfg.use_grids[j]]
+    if any(("grid_center_%d" % j) not in shared for j in used):
+      return
+    traj = np.zeros((self.N, cfg.obs_len, 2), dtype=np.float64)
+    try:
+      traj[:n_have] = np.stack([np.asarray(t, dtype=np.float64) for t in data["obs_traj"]])[:, :cfg.obs_len]
+    except Exception:
+      return
+    rng = np.random.default_rng(0)
+    for j in used:
+      h, w = cfg.scene_grids[j]
+      centers = np.asarray(shared["grid_center_%d" % j], dtype=np.float64)
+      if centers.shape != (h, w, 2):
+        return
+      dense = fd[self.grid_obs_regress[j]]
+      ii, tt = rng.integers(0, n_have, 32), rng.integers(0, cfg.obs_len, 32)
+      yy, xx = rng.integers(0, h, 32), rng.integers(0, w, 32)
+      want = (traj[ii, tt] - centers[yy, xx]).astype(np.float32)
+      if not np.array_equal(dense[ii, tt, yy, xx], want):
+        return
+    for j in used:
+      del fd[self.grid_obs_regress[j]]
+      fd[self.grid_centers[j]] = np.asarray(shared["grid_center_%d" % j], dtype=np.float64)
+    fd[self.obs_traj] = traj
 
   # ---------------------------------------------------------------- execution
   def _ensure_engine(self):
@@ -268,10 +314,19 @@ class Model(object):
                obs_scene=up(feed[self.obs_scene], np.int32),
                grid_obs_labels=[None] * len(cfg.scene_grids),
                grid_obs_regress=[None] * len(cfg.scene_grids))
+    regress = None
+    if self.obs_traj in feed:       # row f-1: dense offsets built on the device from the trajectories
+      centers = [feed.get(self.grid_centers[i]) for i in range(len(cfg.scene_grids))]
+      _, regress = eng.grid_feeds_from_traj(np.asarray(feed[self.obs_traj], dtype=np.float64), centers=centers)
     for i in range(len(cfg.scene_grids)):
       if cfg.use_grids[i]:
         out["grid_obs_labels"][i] = up(feed[self.grid_obs_labels[i]], np.int32)
-        out["grid_obs_regress"][i] = up(feed[self.grid_obs_regress[i]], np.float32)
+        if self.grid_obs_regress[i] in feed:
+          out["grid_obs_regress"][i] = up(feed[self.grid_obs_regress[i]], np.float32)
+        elif regress is not None:
+          out["grid_obs_regress"][i] = regress[i]
+        else:
+          raise KeyError("feed neither grid_obs_regress[%d] nor obs_traj + grid_centers[%d]" % (i, i))
     return out
 
   def _run(self, handles, feed):

@@ -101,7 +101,7 @@ def make_feeds(cfg, n=None, seed=20200614, with_pred=False):
                       size=(n, 2))
   traj = np.clip(start[:, None] + np.cumsum(rng.normal(0, 25.0, size=(n, t + tp, 2)), axis=1), 1.0,
                  [cfg.video_w - 1.0, cfg.video_h - 1.0])
-  feeds = dict(scene_feat=scene_feat, obs_scene=obs_scene, traj=traj.astype(np.float32),
+  feeds = dict(scene_feat=scene_feat, obs_scene=obs_scene, traj=traj.astype(np.float32), traj64=traj,
                grid_obs_labels=[], grid_obs_regress=[], grid_pred_labels=[], grid_pred_regress=[])
   for center, (h, w) in zip(grid_centers(cfg), cfg.scene_grids):
     hg, wg = cfg.video_h * 1.0 / h, cfg.video_w * 1.0 / w
@@ -134,8 +134,9 @@ def shard_feeds(feeds, rank, world):
   for k in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
     if k in feeds and len(feeds[k]):
       out[k] = [a[sl] for a in feeds[k]]
-  if "traj" in feeds:
-    out["traj"] = feeds["traj"][sl]
+  for k in ("traj", "traj64"):
+    if k in feeds:
+      out[k] = feeds[k][sl]
   return out
 
 
@@ -146,7 +147,7 @@ def write_npz(path, cfg, n, seed=0):
   t = cfg.obs_len
   ns = len(cfg.scene_grids)
   data = dict(
-      obs_traj=f["traj"][:, :t], pred_traj=f["traj"][:, t:],
+      obs_traj=f["traj64"][:, :t], pred_traj=f["traj64"][:, t:],     # float64, like the reference's preprocess output
       obs_scene=f["obs_scene"][:, :, None].astype(np.int32),
       obs_grid_class=np.stack([np.stack([f["grid_obs_labels"][j][i] for j in range(ns)]) for i in range(n)]),
       pred_grid_class=np.stack([np.stack([f["grid_pred_labels"][j][i] for j in range(ns)]) for i in range(n)]),

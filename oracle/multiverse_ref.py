@@ -5,18 +5,30 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may import it.  The product path (``multiverse_b200``) never routes through it.
 
-PARITY UNPINNED: the reference (JunweiLiang/Multiverse @ c1756f0) ships no unit
-tests, golden vectors or fixtures for this path, and its arithmetic lives in
-TensorFlow 1.15 (``tf.contrib.rnn.ConvLSTMCell``, ``tf.nn.raw_rnn``,
-``tf.nn.dynamic_rnn``, ``tf.nn.conv2d`` ...), which is neither vendored under the
-reference tree nor installable in this image (Python 3.12, no wheel, no network).
-This file therefore *restates* the reference wiring (``code/pred_models.py``) plus
-the published TF-1.15 semantics of the ops it calls (sheet in SURVEY.md §8c).  It
-is cross-checked against independent implementations in ``tests/`` - torch conv2d with
-TF's SAME rule, torch.nn.LSTMCell (the cell on a 1x1 grid), torch.optim.Adadelta, torch's
-Huber / cross-entropy, the literal dense [HW,HW] graph attention, brute-force beam replay,
-a second, independently written torch port of the whole model - but cannot be checked
-against an execution of the reference itself.
+PINNED ON AN EXECUTION OF THE REFERENCE'S OWN GRAPH CODE (round 2).  The reference
+(JunweiLiang/Multiverse @ c1756f0) ships no unit tests, golden vectors or fixtures for this path, and
+its arithmetic lives in TensorFlow 1.15 (``tf.contrib.rnn.ConvLSTMCell``, ``tf.nn.raw_rnn``,
+``tf.nn.dynamic_rnn``, ``tf.nn.conv2d`` ...), which is neither vendored under the reference tree nor
+installable in this image (Python 3.12, no wheel, no network).  So instead of TensorFlow,
+``oracle/tf1_eager`` provides an eager torch-fp64 stand-in for the ~90 ``tf.*`` symbols
+``code/pred_models.py`` touches, and ``oracle/tf1_eager/run_reference.py`` imports the UNMODIFIED
+``/root/reference/code/pred_models.py`` against it and runs ``Model.__init__ / build_forward /
+build_loss`` and ``Trainer.__init__`` line by line: scopes and variable names, both ``raw_rnn`` loop
+functions, the beam bookkeeping and back-trace, ``add_div_penalty`` / ``gather_helper``, the graph
+attention, the loss and ``tf.gradients`` -> clip -> Adadelta are executed reference code.
+``tests/test_reference_exec_cpu.py`` asserts that this execution equals this file to 1e-12 with
+identical beam ids (greedy two-scale, K=5 plain and K=20 diverse beams, use_gnn off, one training
+step incl. every clipped gradient and the Adadelta update), and the committed rollout goldens
+(``tests/golden/rollout_*.npz``, ``source = "reference_exec"``) are outputs of that execution.
+What stays restated - and is what this file's elementary ops and the stand-in's ops both follow -
+are the per-op TensorFlow semantics (SAME padding, ConvLSTMCell gate order and forget bias,
+raw_rnn / dynamic_rnn protocol, top_k / argmax tie-breaking, l2_normalize, Huber, Adadelta; sheet in
+SURVEY.md section 8c).  Those are anchored outside this repo where PyTorch implements the same op:
+torch conv2d with TF's SAME rule, torch.nn.LSTMCell (the cell on a 1x1 grid), torch.optim.Adadelta,
+torch's Huber / cross-entropy (tests/test_oracle_cpu.py); plus the literal dense [HW,HW] graph
+attention, a brute-force beam replay and an independently written torch port of the whole model.
+The evaluation metrics (minADE / minFDE / NLL, row f-3) are pinned directly on the reference's own
+numpy functions (tests/golden/make_golden_metrics.py imports them).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  All functions are dtype-generic: pass float64 arrays for the

