@@ -43,7 +43,19 @@ def sources():
 
 
 def build(force=False, verbose=False):
-  """Compile every .cu into an object and link the shared library (skips if up to date)."""
+  """Compile every .cu into an object and link the shared library (skips if up to date).  Serialised across
+  processes with a lock file: the ranks of a torchrun job all call this."""
+  import fcntl
+  os.makedirs(OBJ, exist_ok=True)
+  with open(os.path.join(OBJ, ".lock"), "w") as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      return _build_locked(force, verbose)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
   srcs = sources()
   deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
   deps.append(os.path.join(HERE, "..", "include", "multiverse_b200.h"))

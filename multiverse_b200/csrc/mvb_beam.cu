@@ -243,7 +243,7 @@ int decode_trajectories(const int* ids, const float* offs, const float* centers,
                         int K, int Tp, int V, cudaStream_t stream) {
   MVB_REQUIRE(ids && offs && centers && out && N > 0 && K > 0 && Tp > 0 && V > 0, "decode_trajectories: bad args");
   const long long total = N * K * Tp;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int blocks = (int)((total + 255) / 256 < sm_count() * 8 ? (total + 255) / 256 : sm_count() * 8);
   decode_traj_kernel<<<blocks, 256, 0, stream>>>(ids, offs, centers, out, N, K, Tp, V);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

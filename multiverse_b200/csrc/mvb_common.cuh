@@ -186,6 +186,20 @@ inline cudaError_t smem_opt_in(SmemOptIn& st, Kernel kernel, size_t bytes) {
   return e;
 }
 
+// Number of SMs of the current device (cached per device; 148 on B200): grid-stride launchers size their grids in
+// multiples of it instead of a hard-coded constant.
+inline int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // Sums each of v[0..7] over the warp with 9 shuffles instead of 8 butterflies (40): at every halving step a lane
 // keeps one half of its values and hands the other half to its partner.  Lane l returns the warp total of value
 // ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1); the four lanes that share l >> 2 hold the same total.

@@ -114,7 +114,7 @@ int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, i
   const Grid g = make_grid(H, W);
   const long long total = NS * H * W * C;
   const int threads = 256;
-  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  const int blocks = (int)((total + threads - 1) / threads < sm_count() * 16 ? (total + threads - 1) / threads : sm_count() * 16);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_planes);
   switch (P) {
     case 1: nhwc_to_planes_kernel<1><<<blocks, threads, 0, stream>>>(src, d, plane_stride, cpad, ch_off, NS, g, C, comp); break;
@@ -157,7 +157,7 @@ int traj_to_grid(const double* traj, const double* centers, double h_gap, double
   MVB_REQUIRE(traj && centers && labels && regress && NT > 0 && H > 0 && W > 0 && h_gap > 0 && w_gap > 0,
               "traj_to_grid: bad args");
   const long long total = NT * H * W;
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const int blocks = (int)((total + 255) / 256 < sm_count() * 16 ? (total + 255) / 256 : sm_count() * 16);
   traj_to_grid_kernel<<<blocks, 256, 0, stream>>>(traj, centers, h_gap, w_gap, labels, regress, NT, H, W);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
@@ -170,7 +170,7 @@ int nhwc_halo_copy(const float* src, float* dst, long long NS, int H, int W, int
   const Grid g = make_grid(H, W);
   const long long total = NS * H * W * (C / 4);
   const int threads = 256;
-  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  const int blocks = (int)((total + threads - 1) / threads < sm_count() * 16 ? (total + threads - 1) / threads : sm_count() * 16);
   nhwc_halo_copy_kernel<<<blocks, threads, 0, stream>>>(src, dst, NS, g, C, to_nhwc);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

@@ -82,7 +82,7 @@ int scene_time_mean(const float* scene_conv, const int* frame_idx, float* out, l
   MVB_REQUIRE(scene_conv && frame_idx && out && N > 0 && T > 0 && HWC > 0, "scene_time_mean: bad args");
   const long long total = N * HWC;
   const int threads = 256;
-  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  const int blocks = (int)((total + threads - 1) / threads < sm_count() * 16 ? (total + threads - 1) / threads : sm_count() * 16);
   scene_time_mean_kernel<<<blocks, threads, 0, stream>>>(scene_conv, frame_idx, out, N, T, HWC);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);

@@ -583,7 +583,7 @@ int lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, 
   MVB_REQUIRE(gates && c_new && dh && dg_planes && dc_prev && dbias_packed && NS > 0, "lstm_gates_bwd: bad args");
   const Grid g = make_grid(H, W);
   const long long pix = NS * H * W;
-  const int blocks = (int)((pix + 7) / 8 < 148 * 8 ? (pix + 7) / 8 : 148 * 8);
+  const int blocks = (int)((pix + 7) / 8 < sm_count() * 8 ? (pix + 7) / 8 : sm_count() * 8);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dg_planes);
   switch (P) {
     case 1: lstm_bwd_kernel<1><<<blocks, 256, 0, stream>>>(gates, c_prev, c_new, dh, dc_in, d, plane_stride, dc_prev, dbias_packed, NS, g); break;

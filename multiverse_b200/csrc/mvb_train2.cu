@@ -52,11 +52,12 @@ ce_loss_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
   s = bc[1];
   const float inv = 1.0f / s;
   const int lab = labels[r];
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  const bool lab_ok = lab >= 0 && lab < V;      // TF's sparse_softmax_cross_entropy yields NaN loss / gradient rows for
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {      // an out-of-range label; never read lg[lab] out of bounds
     const float p = expf(lg[v] - m) * inv;
-    dlogits[r * V + v] = (p - (v == lab ? 1.f : 0.f)) * scale;
+    dlogits[r * V + v] = lab_ok ? (p - (v == lab ? 1.f : 0.f)) * scale : NAN;
   }
-  if (threadIdx.x == 0) atomicAdd(loss_sum, (logf(s) + m - lg[lab]) * scale);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, lab_ok ? (logf(s) + m - lg[lab]) * scale : NAN);
 }
 
 __global__ void __launch_bounds__(256)
@@ -488,7 +489,7 @@ __global__ void clip_adadelta_kernel(float* __restrict__ w, const float* __restr
 // ------------------------------------------------------------------------------ launchers
 static inline int grid_for(long long n, int threads) {
   const long long b = (n + threads - 1) / threads;
-  return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+  return (int)(b < sm_count() * 16 ? (b > 0 ? b : 1) : sm_count() * 16);
 }
 
 int loss_fwd_bwd(const float* logits, const int* labels, float* dlogits, long long rows, int V,
@@ -572,7 +573,7 @@ int scene_conv_bwd(const float* in, const float* W, const float* out, const floa
   const int tot_h = (OH - 1) * 2 + 3 - IH > 0 ? (OH - 1) * 2 + 3 - IH : 0;
   const int tot_w = (OW - 1) * 2 + 3 - IW > 0 ? (OW - 1) * 2 + 3 - IW : 0;
   const long long total_pix = F * OH * OW;
-  const unsigned blocks = (unsigned)(total_pix < 148 * 8 ? total_pix : 148 * 8);
+  const unsigned blocks = (unsigned)(total_pix < sm_count() * 8 ? total_pix : sm_count() * 8);
   if (9 * Cin <= 4 * 25) {
     scene_conv_bwd_kernel<25><<<blocks, 256, sizeof(float) * (100 + 64), stream>>>(
         in, W, out, dout, dW, db, din, F, IH, IW, OH, OW, tot_h / 2, tot_w / 2, Cin, Cout);

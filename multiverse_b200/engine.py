@@ -105,8 +105,9 @@ class ConvRNNEngine(object):
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
     dev = self.device
-    if getattr(self, "_graphs", None):
+    if getattr(self, "_graphs", None) is not None:
       self._graphs.clear()      # captured graphs point at the previous weight buffers
+      self._graph_seen.clear()
     w = {k: (v if torch.is_tensor(v) else torch.as_tensor(v)).to(dev) for k, v in weights.items()}
     self.scene_w = [(w[P_ + "scene_conv%d/W" % (i + 1)].float().contiguous(),
                      w[P_ + "scene_conv%d/b" % (i + 1)].float().contiguous())
@@ -444,11 +445,24 @@ class ConvRNNEngine(object):
     """Feed generation on the device: the observed trajectories fp64 [N,T,2] (frame
     pixels; numpy or tensor) -> (grid_obs_labels, grid_obs_regress) lists per scale, i.e. what get_grid_input
     builds per trajectory on the host (code/multifuture_inference.py:115-156) and what 99 % of the fed bytes are.
-    `centers[i]` fp64 [h,w,2]: the caller's args.scene_grid_centers; default = the reference's formula (:101-113)."""
+    `centers[i]` fp64 [h,w,2]: the caller's args.scene_grid_centers; default = the reference's formula (:101-113).
+    The returned tensors are per-engine buffers, overwritten by the next call with the same shapes."""
     import numpy as np
     cfg = self.cfg
     vh, vw = getattr(cfg, "video_h", video_h), getattr(cfg, "video_w", video_w)
-    traj = torch.as_tensor(obs_traj, dtype=torch.float64).to(self.device).contiguous()
+    if torch.is_tensor(obs_traj):
+      traj = obs_traj.to(self.device, torch.float64).contiguous()
+    else:      # host array: through a pinned staging block, asynchronously on the current stream
+      a = np.ascontiguousarray(obs_traj, dtype=np.float64)
+      stage = self._buf(("traj_stage", a.shape), lambda: torch.empty(a.shape, dtype=torch.float64).pin_memory())
+      ev = self._bufs.get(("traj_stage_event", a.shape))
+      if ev is not None:
+        ev.synchronize()                  # the previous call's copy out of the staging block has finished
+      stage.copy_(torch.from_numpy(a))
+      traj = stage.to(self.device, non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream(self.device))
+      self._bufs[("traj_stage_event", a.shape)] = ev
     n, t = traj.shape[0], traj.shape[1]
     labels, regress = [], []
     for i, (h, w) in enumerate(cfg.scene_grids):
@@ -462,9 +476,12 @@ class ConvRNNEngine(object):
         cx = np.cumsum([w_gap] * w) - w_gap / 2.0
         cy = np.cumsum([h_gap] * h) - h_gap / 2.0
         c = np.stack((np.tile(cx[None], (h, 1)), np.tile(cy[:, None], (1, w))), axis=-1).reshape(h * w, 2)
-      c_dev = torch.from_numpy(np.ascontiguousarray(c)).to(self.device)
-      lab = torch.empty((n, t), dtype=torch.int32, device=self.device)
-      reg = torch.empty((n, t, h, w, 2), dtype=torch.float32, device=self.device)
+      # the centres are a per-model constant: uploaded once per distinct array (keyed by its bytes)
+      ckey = ("centers", i, hash(np.ascontiguousarray(c).tobytes()))
+      c_dev = self._buf(ckey, lambda: torch.from_numpy(np.ascontiguousarray(c)).to(self.device))
+      lab = self._buf(("traj_lab", i, n, t), lambda: torch.empty((n, t), dtype=torch.int32, device=self.device))
+      reg = self._buf(("traj_reg", i, n, t), lambda: torch.empty((n, t, h, w, 2), dtype=torch.float32,
+                                                                  device=self.device))
       ops.traj_to_grid(traj, c_dev, h_gap, w_gap, lab, reg, h, w)
       labels.append(lab); regress.append(reg)
     return labels, regress

@@ -457,7 +457,11 @@ class Model(object):
         feeds["grid_pred_regress"][i] = up(feed[self.grid_pred_regress[i]], np.float32)
     step = int(self.global_step.value)
     if apply:
-      losses, wd = eng.train_step(feeds, self.learning_rate(step))
+      # under torchrun (an initialised NCCL process group) the drop-in train.py is data parallel: every rank feeds its
+      # own batches and the gradients are all-reduced; a single process trains alone
+      import torch.distributed as dist
+      group = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+      losses, wd = eng.train_step(feeds, self.learning_rate(step), group)
       self.global_step.value = np.asarray(step + 1, dtype="int32")
       self._device_newer = True
     else:

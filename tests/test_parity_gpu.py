@@ -389,9 +389,12 @@ def test_rollout_atsize(dev, name):
     assert same_set[safe_n].all(), "beam id sets differ from the oracle on boundary-safe samples %s" % np.nonzero(safe_n & ~same_set)[0]
     assert exact.mean() >= 0.5, "beam order differs from the oracle in most samples: %s" % exact
     assert np.abs(np.sort(st["beam_logprobs"], 1) - np.sort(g["beam_logprobs"], 1))[safe_n].max() < 1e-3
+    # the saved logit rows of a step form the same SET whatever the order of twins inside the beam; which row the
+    # reference's back-trace pairs with which final beam is not (it gathers the row of the slot's PREVIOUS occupant,
+    # code/pred_models.py:738 before :749), so the per-beam statistics are compared sorted over the beam axis
     bs = np.abs(g["beam_lg_max"]).max()
     for k in ("beam_lg_max", "beam_lg_mean"):
-      worst[k] = float(np.abs(st[k] - g[k])[exact].max() / bs)
+      worst[k] = float(np.abs(np.sort(st[k], 1) - np.sort(g[k], 1))[safe_n].max() / bs)
       assert worst[k] < TOL, (k, worst[k])
     print("atsize %s: %d of %d samples boundary-safe (gap to the best unselected candidate > 2e-4), id sets equal on "
           "all of them; ids equal beam for beam in %d samples; the others' smallest in-beam oracle gaps: %s"

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "atsize or metrics or compact" -s 2>&1 | grep -v "^$" | tail -12
+timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^$" | tail -25
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/c12_bench.json 2> gpurun_out/c12_bench.err; tail -3 gpurun_out/c12_bench.err
 python - <<'PY'
