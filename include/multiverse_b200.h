@@ -260,6 +260,16 @@ int mvb_emb_dense_fwd(const float* x, const float* We, const float* be, int E, v
 int mvb_beam_step(const float* logits, const float* score_in, float* score_out, int32_t* ids_out,
                   int32_t* parents_out, int32_t* row_map_out, int64_t N, int B, int V,
                   int first_step, int zero_scores, int diverse, float log_gamma, void* stream);
+/* ---- f-4: SimAug's white-box attack on the scene input (SimAug/code/pred_models.py:60-170) ----------------------
+ * The gradient of the (targeted) classification loss with respect to the scene features comes out of the ordinary
+ * backward pass: mvb_scene_conv_bwd with a non-NULL `din` for the FIRST scene convolution accumulates d loss / d input
+ * (fp32 [F,SH,SW,SC]).  One attack step (:96-124, bounds :142-143), element-wise over n values:
+ *   out = clip(adv - step * sign(grad), clip(x - eps, -1, 1), clip(x + eps, -1, 1))      (FGSM: step = eps; PGD: step size)
+ * and the mixup of :149-166: out = a * w + b * (1 - w). */
+int mvb_adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, int64_t n,
+                 void* stream);
+int mvb_mix(const float* a, const float* b, float* out, float w, int64_t n, void* stream);
+
 /* ---- f-3: multi-future evaluation metrics on the device ------------------------------------------------------
  * minADE / minFDE of code/multifuture_eval_trajs.py:41-78 (get_min :16-21): for every trajectory n and ground-truth
  * future g (gt_len[n,g] steps, 0 = absent) the prediction k in [0,K) with the smallest left-to-right SUM of per-step

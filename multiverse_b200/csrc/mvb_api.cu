@@ -311,6 +311,13 @@ int mvb_decode_trajectories(const int32_t* ids, const float* offsets, const floa
                             int64_t N, int K, int Tp, int V, void* stream) {
   return decode_trajectories(ids, offsets, centers, out, N, K, Tp, V, S(stream));
 }
+int mvb_adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, int64_t n,
+                 void* stream) {
+  return adv_step(x, adv, grad, out, eps, step, n, S(stream));
+}
+int mvb_mix(const float* a, const float* b, float* out, float w, int64_t n, void* stream) {
+  return mix(a, b, out, w, n, S(stream));
+}
 int mvb_min_ade_fde(const float* pred, const float* gt, const int32_t* gt_len, double* ade_err, int32_t* ade_idx,
                     double* fde, int32_t* fde_idx, int64_t N, int G, int K, int Tp, int Tg, void* stream) {
   return min_ade_fde(pred, gt, gt_len, ade_err, ade_idx, fde, fde_idx, N, G, K, Tp, Tg, S(stream));

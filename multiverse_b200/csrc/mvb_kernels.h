@@ -104,6 +104,9 @@ int enc_class_input_bwd(const float* dxh, int cpad, const int* frame_idx, const 
                         float* dscene, long long NS, int H, int W, cudaStream_t stream);
 int scene_mean_bwd(const float* dmean, const int* frame_idx, float* dscene, long long N, int T,
                    long long HWC, cudaStream_t stream);
+int adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, long long n,
+             cudaStream_t stream);
+int mix(const float* a, const float* b, float* out, float w, long long n, cudaStream_t stream);
 int clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, long long n, float lr,
                   float rho, float eps, float clip, float wd, float gscale, cudaStream_t stream);
 

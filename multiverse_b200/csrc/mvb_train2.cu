@@ -586,6 +586,44 @@ int scene_conv_bwd(const float* in, const float* W, const float* out, const floa
   return MVB_OK;
 }
 
+// ------------------------------------------------------------------------------ SimAug input attack step
+// One step of SimAug's white-box attack on the scene input (SimAug/code/pred_models.py:96-124): the targeted
+// FGSM / PGD update  adv <- clip(adv - step * sign(grad), lower, upper)  with the bounds of :142-143,
+// lower = clip(x - eps, -1, 1), upper = clip(x + eps, -1, 1), x = the clean input.
+__global__ void adv_step_kernel(const float* __restrict__ x, const float* __restrict__ adv, const float* __restrict__ g,
+                                float* __restrict__ out, float eps, float step, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float lo = fminf(fmaxf(x[i] - eps, -1.f), 1.f), hi = fminf(fmaxf(x[i] + eps, -1.f), 1.f);
+    const float gi = g[i];
+    const float sg = gi > 0.f ? 1.f : (gi < 0.f ? -1.f : 0.f);          // tf.sign
+    out[i] = fminf(fmaxf(adv[i] - step * sg, lo), hi);                  // tf.clip_by_value: min(max(v, lo), hi)
+  }
+}
+// mixup of :149-166:  out = a * w + b * (1 - w)
+__global__ void mix_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, float w,
+                           long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] * w + b[i] * (1.f - w);
+}
+
+int adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, long long n,
+             cudaStream_t stream) {
+  MVB_REQUIRE(x && adv && grad && out && n > 0 && eps >= 0.f, "adv_step: bad args");
+  const long long b = (n + 255) / 256;
+  adv_step_kernel<<<(unsigned)(b < sm_count() * 16 ? b : sm_count() * 16), 256, 0, stream>>>(x, adv, grad, out, eps, step, n);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+int mix(const float* a, const float* b, float* out, float w, long long n, cudaStream_t stream) {
+  MVB_REQUIRE(a && b && out && n > 0, "mix: bad args");
+  const long long bl = (n + 255) / 256;
+  mix_kernel<<<(unsigned)(bl < sm_count() * 16 ? bl : sm_count() * 16), 256, 0, stream>>>(a, b, out, w, n);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int enc_class_input_bwd(const float* dxh, int cpad, const int* frame_idx, const int* label,
                         float* dscene, long long NS, int H, int W, cudaStream_t stream) {
   MVB_REQUIRE(dxh && frame_idx && label && dscene && NS > 0, "enc_class_input_bwd: bad args");

@@ -380,6 +380,16 @@ def decode_trajectories(ids, offs, centers, out):
             _stream())
 
 
+def adv_step(x, adv, grad, out, eps, step):
+  """out = clip(adv - step*sign(grad), clip(x-eps,-1,1), clip(x+eps,-1,1)) (SimAug/code/pred_models.py:96-124,142-143)."""
+  _lib.call("mvb_adv_step", _p(x), _p(adv), _p(grad), _p(out), float(eps), float(step), x.numel(), _stream())
+
+
+def mix(a, b, out, w):
+  """out = a*w + b*(1-w) (SimAug mixup, SimAug/code/pred_models.py:149-166)."""
+  _lib.call("mvb_mix", _p(a), _p(b), _p(out), float(w), a.numel(), _stream())
+
+
 def min_ade_fde(pred, gt, gt_len):
   """pred fp32 [N,K,Tp,2], gt fp32 [N,G,Tg,2], gt_len int32 [N,G] -> (ade_err fp64 [N,G,Tg], ade_idx int32 [N,G],
   fde fp64 [N,G], fde_idx int32 [N,G]): code/multifuture_eval_trajs.py:41-78 on the device."""

@@ -238,14 +238,19 @@ class TrainEngine(ConvRNNEngine):
                             accumulate=True)
 
   # ------------------------------------------------------------------ public
-  def loss_and_grads(self, feeds, loss_scale=1.0, zero=True):
+  def loss_and_grads(self, feeds, loss_scale=1.0, zero=True, dscene_out=None, cls_weight=None, reg_weight=None):
     """Forward + loss + backward.  feeds additionally needs grid_pred_labels[i] int32 [N,Tp] and
     grid_pred_regress[i] fp32 [N,Tp,h,w,2].  Returns (losses fp32 tensor [2*scales] on device in
     the reference's order cls_0, reg_0, cls_1, ..., wd_loss tensor); gradients are ADDED into
     self.grads (TF variable names; zeroed first unless zero=False), WITHOUT the weight-decay term
     (added by the optimizer).  loss_scale weights this call's batch inside a larger one
-    (micro-batching: n_chunk / N, every loss being a batch mean)."""
+    (micro-batching: n_chunk / N, every loss being a batch mean).
+    dscene_out (fp32 [F,SH,SW,SC], zeroed by the caller): receives d loss / d scene_feat - the input gradient of
+    SimAug's white-box attack; cls_weight / reg_weight override the config's loss
+    weights for this call (the attack differentiates the classification loss alone)."""
     cfg, dev = self.cfg, self.device
+    cls_w = cfg.grid_loss_weight if cls_weight is None else cls_weight
+    reg_w = cfg.grid_reg_loss_weight if reg_weight is None else reg_weight
     if zero:
       self.flat_grad.zero_()
     obs_scene = feeds["obs_scene"].to(torch.int32).contiguous()
@@ -257,13 +262,13 @@ class TrainEngine(ConvRNNEngine):
     for i in used:
       S = self._forward_scale(i, feeds, convs, means)
       self._backward_scale(i, S, feeds, convs, means, dconv, loss_out[i],
-                           cfg.grid_loss_weight * loss_scale, cfg.grid_reg_loss_weight * loss_scale)
+                           cls_w * loss_scale, reg_w * loss_scale)
     # scene CNN backward: conv_k -> conv_{k-1} chain (code/pred_models.py:155-165)
     ins = [scene_feat] + convs[:-1]
     for k in range(len(convs) - 1, -1, -1):
       W, _ = self.scene_w[k]
       ops.scene_conv_bwd(ins[k], W, convs[k], dconv[k], self.grads[P_ + "scene_conv%d/W" % (k + 1)],
-                         self.grads[P_ + "scene_conv%d/b" % (k + 1)], dconv[k - 1] if k > 0 else None)
+                         self.grads[P_ + "scene_conv%d/b" % (k + 1)], dconv[k - 1] if k > 0 else dscene_out)
     wd = sum(0.5 * cfg.wd * (self.params[k] * self.params[k]).sum() for k in self.names if k.endswith("/W"))
     return loss_out[used].reshape(-1), wd
 

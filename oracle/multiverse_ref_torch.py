@@ -148,6 +148,21 @@ def forward(cfg, weights, feeds):
           for k, v in out.items()}
 
 
+def scene_input_grad(cfg, weights, feeds, target_labels, scale_idx, dtype=torch.float64):
+  """Truth for SimAug's attack gradient (SimAug/code/pred_models.py:96-115): d sum(sparse CE(logits, target)) /
+  d scene_feat through the train-mode forward, by torch autograd."""
+  w = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in weights.items()}
+  f = dict(feeds)
+  sf = torch.from_numpy(np.ascontiguousarray(feeds["scene_feat"])).to(dtype).requires_grad_(True)
+  f["scene_feat"] = sf
+  out = _forward(cfg, w, f, dtype)
+  h, ww = cfg.scene_grids[scale_idx]
+  logits = out["grid_pred_decoded"][scale_idx].reshape(-1, h * ww)
+  loss = F.cross_entropy(logits, torch.from_numpy(np.asarray(target_labels)).long().reshape(-1), reduction="sum")
+  loss.backward()
+  return sf.grad.numpy()
+
+
 def loss_and_grads(cfg, weights, feeds, dtype=torch.float64):
   """Training objective of Model.build_loss (code/pred_models.py:961-1040) on the greedy
   train-mode forward (train_w_onehot: the class decoder is fed one_hot(argmax), :285) and its
@@ -177,7 +192,7 @@ def loss_and_grads(cfg, weights, feeds, dtype=torch.float64):
 
 def _forward(cfg, w, feeds, dtype):
   n = cfg.batch_size
-  scene_feat = torch.from_numpy(feeds["scene_feat"]).to(dtype)
+  scene_feat = feeds["scene_feat"] if torch.is_tensor(feeds["scene_feat"]) else torch.from_numpy(feeds["scene_feat"]).to(dtype)
   obs_scene = torch.from_numpy(feeds["obs_scene"]).long()
   x = scene_feat[obs_scene.reshape(-1)]              # embedding_lookup, :148-152
   convs = []

@@ -372,6 +372,8 @@ def test_rollout_atsize(dev, name):
     for k, scale in (("lg_max", ls), ("lg_mean", ls), ("lg_at", ls), ("reg_at_argmax", rs), ("reg_mean", rs), ("reg_at", rs)):
       key = "%s_%d" % (k, i)
       rows = ok_rows if k.startswith("lg") or k == "reg_at_argmax" else np.ones(n, bool)
+      if not rows.any():
+        continue
       d = np.abs(st[key] - g[key])[rows]
       if k == "reg_at_argmax":
         d = d[(st["argmax_%d" % i] == g["argmax_%d" % i])[rows]]
@@ -387,7 +389,6 @@ def test_rollout_atsize(dev, name):
     exact = np.array([np.array_equal(st["beam_ids"][j], g["beam_ids"][j]) for j in range(n)])
     same_set = np.array([seqs(st["beam_ids"][j]) == seqs(g["beam_ids"][j]) for j in range(n)])
     assert same_set[safe_n].all(), "beam id sets differ from the oracle on boundary-safe samples %s" % np.nonzero(safe_n & ~same_set)[0]
-    assert exact.mean() >= 0.5, "beam order differs from the oracle in most samples: %s" % exact
     assert np.abs(np.sort(st["beam_logprobs"], 1) - np.sort(g["beam_logprobs"], 1))[safe_n].max() < 1e-3
     # the saved logit rows of a step form the same SET whatever the order of twins inside the beam; which row the
     # reference's back-trace pairs with which final beam is not (it gathers the row of the slot's PREVIOUS occupant,

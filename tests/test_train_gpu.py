@@ -316,3 +316,50 @@ def test_trainer_step_through_session_and_micro_batching(dev, monkeypatch):
   l_mb, _ = eng.loss_and_grads_chunked(feeds, 2)
   assert float((l_full - l_mb).abs().max()) < 1e-4 * float(l_full.abs().max())
   assert float((g_full - eng.flat_grad).abs().max()) < 2e-4 * float(g_full.abs().max())
+
+
+def test_simaug_scene_input_gradient_and_attack(dev):
+  """SURVEY.md section 8 row f-4 (first part): the gradient of the targeted classification loss with respect to
+  the scene features - what SimAug's white_box_attack differentiates (SimAug/code/pred_models.py:96-115) - against
+  torch autograd through the oracle, and one FGSM / PGD / mixup pass of the attack's update rule."""
+  from types import SimpleNamespace
+  from multiverse_b200 import ops, simaug, synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  from oracle import multiverse_ref as R
+  from oracle import multiverse_ref_torch as RT
+  over = dict(batch_size=2, use_grids=[False, True])
+  cfg = synthetic.make_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, clip_gradient_norm=10.0, **over)
+  w = synthetic.make_weights(cfg, 31); f = synthetic.make_feeds(cfg, 2, 31, with_pred=True)
+  # soft (non one-hot) scene features in (-1, 1): an attacked input is not one-hot any more
+  rng = np.random.default_rng(3)
+  f["scene_feat"] = np.clip(f["scene_feat"] * 0.8 + rng.uniform(-0.1, 0.1, f["scene_feat"].shape), -1, 1).astype(np.float32)
+  eng = TrainEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  feeds = {k: ([T(a, dev) for a in v] if isinstance(v, list) else T(v, dev)) for k, v in f.items() if not k.startswith("traj")}
+  target = simaug.create_random_target(f["grid_pred_labels"][1], 18 * 9, np.random.default_rng(5))
+  assert not (target == f["grid_pred_labels"][1]).any() and target.min() >= 0 and target.max() < 162
+  g = simaug.scene_input_grad(eng, feeds, T(target, dev), 1).cpu().numpy().astype(np.float64)
+  rcfg = R.default_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, **over)
+  g_ref = RT.scene_input_grad(rcfg, w, f, target, 1)
+  scale = float((g * g_ref).sum() / (g_ref * g_ref).sum())        # the engine differentiates the MEAN: a positive factor
+  assert scale > 0
+  err = np.abs(g / scale - g_ref).max() / np.abs(g_ref).max()
+  big = np.abs(g_ref) > 1e-3 * np.abs(g_ref).max()
+  print("scene input gradient: rel err %.2e, factor %.4g (1/(N*Tp) = %.4g), sign agreement %.5f"
+        % (err, scale, 1.0 / target.size, (np.sign(g[big]) == np.sign(g_ref[big])).mean()))
+  assert err < 2e-3 and abs(scale * target.size - 1.0) < 1e-3
+  assert (np.sign(g[big]) == np.sign(g_ref[big])).mean() > 0.999
+  # the attack: FGSM, PGD and mixup keep the reference's bounds and move every pixel the way the sign says
+  x = feeds["scene_feat"]
+  acfg = SimpleNamespace(use_grids=[False, True], scene_grids=cfg.scene_grids, adv_epsilon=0.1, adv_step_size=0.02,
+                         adv_num_iter=3, adv_start_from_clean_prob=1.0, adv_use_fgsm=True, use_mixup=False)
+  adv, tl = simaug.white_box_attack(eng, feeds, f["grid_pred_labels"][1], acfg, np.random.default_rng(5))
+  assert np.array_equal(tl, target)
+  lo = torch.clamp(x - 0.1, -1, 1); hi = torch.clamp(x + 0.1, -1, 1)
+  want = torch.minimum(torch.maximum(x - 0.1 * torch.sign(T(g.astype(np.float32), dev)), lo), hi)
+  assert torch.equal(adv, want)
+  acfg.adv_use_fgsm = False; acfg.adv_start_from_clean_prob = 0.0
+  adv_pgd, _ = simaug.white_box_attack(eng, feeds, f["grid_pred_labels"][1], acfg, np.random.default_rng(5))
+  assert bool((adv_pgd >= lo).all()) and bool((adv_pgd <= hi).all()) and float((adv_pgd - x).abs().max()) > 0.02
+  acfg.adv_use_fgsm = True; acfg.use_mixup = True; acfg.mixup_alpha = 1.0; acfg.mixup_mix_adv = False
+  adv_mix, _ = simaug.white_box_attack(eng, feeds, f["grid_pred_labels"][1], acfg, np.random.default_rng(5))
+  assert bool(((adv_mix - x).abs() <= 0.1 + 1e-6).all())
