@@ -84,7 +84,8 @@ struct CellParams {
   int skip_x;               // x-fold: the x chunk of the K loop is skipped
   int order;                // work order, see work_index()
   int abl;                  // debug ablations (MVB_CELL_ABL; results are then WRONG): 1 skip the fp8 MMAs, 2 skip the
-                            // 16-bit MMAs, 4 skip the epilogue's math and stores
+                            // 16-bit MMAs, 4 skip the epilogue's math and stores, 8 the issuer does not wait for operand
+                            // data, 16 the producer loads nothing (use with 8)
   float* preact_out;        // [R, 1024] raw accumulators (packed column order) instead of the state update: first stage of
                             // the fan-out step (fanout_children_kernel turns every parent row into its K children)
   int hp_mixed;             // hp_out is written in the f16f8 format (else P bf16 planes)
@@ -208,6 +209,7 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // chunk-major K order: the x block - whose terms can be orders of magnitude larger than the h terms (raw
       // pixel offsets in the regression encoder) - is accumulated first, so the small h products are never added
       // onto a large transient partial sum.
+      if (prm.abl & 16) continue;
       for (int q = q_begin; q < NQ; ++q) {
         const int c16 = q == 0 ? 0 : cxp + (q - 1) * CHUNK;              // 16-bit channel coordinate
         const int c8 = q == 0 ? 0 : 2 * cxp + (q - 1) * 2 * CHUNK;       // fp8 byte coordinate
@@ -246,15 +248,16 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1 && lane == 0 && (!CG2 || rank == 0)) {
     // ===================== MMA issuer =====================
+    // One thread; its instruction stream is the critical path at 128 cycles per dispatch (measured with the loads and
+    // the epilogue switched off: the round-2 first draft, with run-time K loops and 64-bit descriptor builds, reached
+    // only 79 % of the dispatch floor).  So: compile-time trip counts for the h chunks, one IADD per operand and
+    // dispatch (umma_lohi), the accumulate flag a compile-time constant except for the first dispatch of a tile.
     constexpr uint32_t kIdM = CG2 ? ((2u * BLOCK_M) >> 4) << 24 : 0u;     // cta_group::2: M = 256
     constexpr uint32_t kIdBf16 = CG2 ? ((kIdesc & 0x00FFFFFFu) | kIdM) : kIdesc;
     constexpr uint32_t kIdF16 = CG2 ? ((kIdescF16 & 0x00FFFFFFu) | kIdM) : kIdescF16;
-    auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-      if (CG2) umma_bf16_2sm(d, a, b, id, acc); else umma_bf16(d, a, b, id, acc);
-    };
-    auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-      if (CG2) umma_f8_2sm(d, a, b, id, acc); else umma_f8(d, a, b, id, acc);
-    };
+    constexpr uint32_t kHi = smem_desc_hi(SW128_SBO, SW128_LAYOUT);
+    const bool do16 = !(prm.abl & 2), do8 = !(prm.abl & 1), wait_data = !(prm.abl & 8);
+    const uint32_t a_plane_lo = (uint32_t)(ra8 * ROW_BYTES) >> 4;
     int slot = 0, astage = 0; uint32_t phase = 0, aphase = 0;
     long long it = 0;
     for (long long t; (t = work_index(it)) < num_tiles; ++it) {
@@ -263,48 +266,77 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tempty_bar[as], tphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      uint32_t first = 0u;
+      bool fresh = true;                     // the tile's first dispatch overwrites the accumulator
       for (int q = q_begin; q < NQ; ++q) {
-        const int ks16 = (q == 0 ? cxp : CHUNK) / UMMA_K;       // K = 16 dispatches per 16-bit plane pair
-        const int ks8 = (q == 0 ? cxp : CHUNK) / 32;            // K = 32 dispatches per fp8 plane
-        const uint32_t poff8 = q == 0 ? (uint32_t)cxp : (uint32_t)CHUNK;   // byte offset of e1 inside an fp8 row
-        mbar_wait(&afull_bar[astage], aphase);
-        const uint32_t sa_base = smem_u32(smem_a + astage * a_stage_bytes);
-        const uint32_t a_plane = (uint32_t)ra8 * ROW_BYTES;
+        if (wait_data) mbar_wait(&afull_bar[astage], aphase);
+        const uint32_t sa_lo = smem_u32(smem_a + astage * a_stage_bytes) >> 4;
         for (int tap = 0; tap < 9; ++tap) {
           // the tap's A tile: the stage's rows starting (dy-1) Wp + (dx-1) + (Wp+1) = dy Wp + dx rows in
-          const uint32_t sa = sa_base + (uint32_t)((tap / 3) * g.Wp + (tap % 3)) * ROW_BYTES;
+          const uint32_t a_lo = sa_lo + (uint32_t)((tap / 3) * g.Wp + (tap % 3)) * (ROW_BYTES >> 4);
 #pragma unroll
           for (int sl = 0; sl < NS; ++sl) {
-            mbar_wait(&full_bar[slot], phase);
+            if (wait_data) mbar_wait(&full_bar[slot], phase);
             tc_fence_after();
-            const uint32_t sb = smem_u32(smem + slot * SLOT_BYTES);
-            if (FMT == 1 && sl == 0) {
-              for (int k = 0; k < ks16; ++k) {                    // a0 * b0, fp16
-                if (prm.abl & 2) break;
-                mma16(d_tmem, make_smem_desc(sa + k * 32, SW128_SBO, SW128_LAYOUT),
-                      make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdF16, first);
-                first = 1u;
+            const uint32_t b_lo = smem_u32(smem + slot * SLOT_BYTES) >> 4;
+            if (q > 0) {
+              // ---- h chunk: 64 channels = 4 K16 steps per 16-bit plane pair, 2 K32 steps per e4m3 plane ----
+              if (FMT == 1 && sl == 0) {
+                if (do16) {
+                  if (fresh) umma_lohi<0, CG2, false>(d_tmem, a_lo, b_lo, kHi, kIdF16);
+                  else umma_lohi<0, CG2, true>(d_tmem, a_lo, b_lo, kHi, kIdF16);
+                  umma_lohi<0, CG2, true>(d_tmem, a_lo + 2, b_lo + 2, kHi, kIdF16);
+                  umma_lohi<0, CG2, true>(d_tmem, a_lo + 4, b_lo + 4, kHi, kIdF16);
+                  umma_lohi<0, CG2, true>(d_tmem, a_lo + 6, b_lo + 6, kHi, kIdF16);
+                  fresh = false;
+                }
+              } else if (FMT == 1) {
+                if (do8) {
+                  const uint32_t a8 = a_lo + a_plane_lo;          // [e0 (64 B) | e1 (64 B)] per row
+                  if (fresh) umma_lohi<1, CG2, false>(d_tmem, a8, b_lo, kHi, kIdF16);
+                  else umma_lohi<1, CG2, true>(d_tmem, a8, b_lo, kHi, kIdF16);
+                  umma_lohi<1, CG2, true>(d_tmem, a8 + 2, b_lo + 2, kHi, kIdF16);
+                  umma_lohi<1, CG2, true>(d_tmem, a8 + 4, b_lo + 4, kHi, kIdF16);
+                  umma_lohi<1, CG2, true>(d_tmem, a8 + 6, b_lo + 6, kHi, kIdF16);
+                  fresh = false;
+                }
+              } else if (do16) {
+                // B plane sl against the A planes pa with pa + sl < P
+#pragma unroll
+                for (int pa = 0; pa < P - sl; ++pa) {
+                  const uint32_t ap = a_lo + pa * a_plane_lo;
+                  if (fresh) umma_lohi<0, CG2, false>(d_tmem, ap, b_lo, kHi, kIdBf16);
+                  else umma_lohi<0, CG2, true>(d_tmem, ap, b_lo, kHi, kIdBf16);
+                  umma_lohi<0, CG2, true>(d_tmem, ap + 2, b_lo + 2, kHi, kIdBf16);
+                  umma_lohi<0, CG2, true>(d_tmem, ap + 4, b_lo + 4, kHi, kIdBf16);
+                  umma_lohi<0, CG2, true>(d_tmem, ap + 6, b_lo + 6, kHi, kIdBf16);
+                  fresh = false;
+                }
               }
-            } else if (FMT == 1) {
-#pragma unroll
-              for (int p = 0; p < 2; ++p)                         // e4m3 cross terms, K = 32 per dispatch
-                for (int k = 0; k < ks8; ++k) {
-                  if (prm.abl & 1) break;
-                  mma8(d_tmem, make_smem_desc(sa + a_plane + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT),
-                       make_smem_desc(sb + p * poff8 + k * 32, SW128_SBO, SW128_LAYOUT), kIdF16, first);
-                  first = 1u;
-                }
             } else {
-              // B plane sl against the A planes pa with pa + sl < P
-#pragma unroll
-              for (int pa = 0; pa < P - sl; ++pa)
-                for (int k = 0; k < ks16; ++k) {
-                  if (prm.abl & 2) break;
-                  mma16(d_tmem, make_smem_desc(sa + pa * a_plane + k * 32, SW128_SBO, SW128_LAYOUT),
-                        make_smem_desc(sb + k * 32, SW128_SBO, SW128_LAYOUT), kIdBf16, first);
-                  first = 1u;
+              // ---- x chunk (only cells whose input is not folded): cxp = 32 or 64 channels, run-time trip counts ----
+              const int ks16 = cxp / UMMA_K, ks8 = cxp / 32;
+              const uint32_t poff = (uint32_t)cxp >> 4;              // e1 sits cxp bytes after e0 in an fp8 row
+              if (FMT == 1 && sl == 0) {
+                for (int k = 0; k < ks16 && do16; ++k) {
+                  if (fresh) umma_lohi<0, CG2, false>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kHi, kIdF16);
+                  else umma_lohi<0, CG2, true>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kHi, kIdF16);
+                  fresh = false;
                 }
+              } else if (FMT == 1) {
+                for (int pk = 0; pk < 2 * ks8 && do8; ++pk) {
+                  const uint32_t o = (pk / ks8) * poff + (pk % ks8) * 2;
+                  if (fresh) umma_lohi<1, CG2, false>(d_tmem, a_lo + a_plane_lo + o, b_lo + o, kHi, kIdF16);
+                  else umma_lohi<1, CG2, true>(d_tmem, a_lo + a_plane_lo + o, b_lo + o, kHi, kIdF16);
+                  fresh = false;
+                }
+              } else {
+                for (int pa = 0; pa < P - sl; ++pa)
+                  for (int k = 0; k < ks16 && do16; ++k) {
+                    if (fresh) umma_lohi<0, CG2, false>(d_tmem, a_lo + pa * a_plane_lo + 2 * k, b_lo + 2 * k, kHi, kIdBf16);
+                    else umma_lohi<0, CG2, true>(d_tmem, a_lo + pa * a_plane_lo + 2 * k, b_lo + 2 * k, kHi, kIdBf16);
+                    fresh = false;
+                  }
+              }
             }
             if (CG2) umma_commit_2sm(&empty_bar[slot]);
             else if (MC) umma_commit_mc(&empty_bar[slot], (uint16_t)3);
@@ -783,7 +815,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : 1; }();
   prm.order = order;
   static const int abl = [] { const char* e = getenv("MVB_CELL_ABL"); return e ? atoi(e) : 0; }();
-  prm.abl = abl;
+  prm.abl = (abl & 16) ? (abl | 8) : abl;      // "load nothing" without "do not wait for data" would hang the issuer
   if (xf_B) {
     MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
     prm.skip_x = 1;

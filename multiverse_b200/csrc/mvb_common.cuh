@@ -432,6 +432,33 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
       : "memory");
 }
 
+// Issue-thread-cheap forms: the MMA issuer is ONE thread and every instruction it executes costs ~4-6 cycles of its
+// dependent-issue latency; with a dispatch due every 128 cycles, descriptor arithmetic must stay at one IADD per operand.
+// A shared-memory descriptor is {lo = (address >> 4) [+ lbo << 16], hi = sbo >> 4 | 1 << 14 | layout << 29}: only `lo`
+// moves along K / rows, by (bytes >> 4).  KIND: 0 = kind::f16, 1 = kind::f8f6f4; CG2: cta_group::2; ACC: accumulate.
+constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+template <int KIND, bool CG2, bool ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  if (KIND == 0 && !CG2)
+    asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi),
+                 "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+  else if (KIND == 0)
+    asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi),
+                 "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+  else if (!CG2)
+    asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], ad, bd, %4, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi),
+                 "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], ad, bd, %4, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi),
+                 "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+
 // mbarrier arrive once all previously issued tcgen05.mma of this thread retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
