@@ -344,7 +344,7 @@ def main():
   if extras:
     # the other two north_star workloads in the same invocation, at the same N and in the same process group
     sub = {}
-    sub["c3"] = run_infer(args, "c3", ctx, max(args.steps, 5), args.warmup, cpu_baseline=False)
+    sub["c3"] = run_infer(args, "c3", ctx, max(args.steps, 10), args.warmup, cpu_baseline=False)
     sub["c5"] = run_train(args, "c5", ctx, max(2, min(args.steps, 3)), args.warmup, cpu_baseline=False)
     chk = ddp_equivalence(ctx) if world > 1 else None
     if rank == 0:
@@ -362,6 +362,9 @@ def run_infer(args, name, ctx, steps, warmup, cpu_baseline=True):
   from multiverse_b200.engine import ConvRNNEngine
   wl = WORKLOADS[name]
   world, rank, local, dev, dist = ctx
+  # the host side of the timed regions is one Python thread issuing launches and copies: keep torch's CPU thread pool
+  # (sized up by a cpu_baseline leg earlier in the same process) from spinning beside it
+  torch.set_num_threads(1)
   gb = args.global_batch or wl["global_batch"]
   assert gb % world == 0
   n_local = gb // world
@@ -458,14 +461,21 @@ def run_infer(args, name, ctx, steps, warmup, cpu_baseline=True):
   fetches = []
   # row f-1: what Model.get_feed_dict feeds for a pred_utils batch - the observed trajectories and the cell centres
   # instead of the dense [N,T,h,w,2] offsets, which the engine rebuilds on the device (bit-identical)
-  feed_dict[model.obs_traj] = np.ascontiguousarray(host["traj64"][:, :cfg.obs_len])
+  dense_feeds = os.environ.get("MVB_BENCH_DENSE_FEEDS", "0") == "1"      # A/B: the reference's dense offset arrays
   centers = synthetic.grid_centers(cfg)
-  e2e_h2d = [host_pinned["scene_feat"].numpy(), host_pinned["obs_scene"].numpy(), feed_dict[model.obs_traj]]
+  e2e_h2d = [host_pinned["scene_feat"].numpy(), host_pinned["obs_scene"].numpy()]
+  if not dense_feeds:
+    feed_dict[model.obs_traj] = np.ascontiguousarray(host["traj64"][:, :cfg.obs_len])
+    e2e_h2d.append(feed_dict[model.obs_traj])
   for i in range(len(cfg.scene_grids)):
     if cfg.use_grids[i]:
       feed_dict[model.grid_obs_labels[i]] = host_pinned["grid_obs_labels"][i].numpy()
-      feed_dict[model.grid_centers[i]] = np.asarray(centers[i], dtype=np.float64)
-      e2e_h2d += [feed_dict[model.grid_obs_labels[i]], feed_dict[model.grid_centers[i]]]
+      if dense_feeds:
+        feed_dict[model.grid_obs_regress[i]] = host_pinned["grid_obs_regress"][i].numpy()
+        e2e_h2d += [feed_dict[model.grid_obs_labels[i]], feed_dict[model.grid_obs_regress[i]]]
+      else:
+        feed_dict[model.grid_centers[i]] = np.asarray(centers[i], dtype=np.float64)
+        e2e_h2d += [feed_dict[model.grid_obs_labels[i]], feed_dict[model.grid_centers[i]]]
       fetches += [model.grid_pred_decoded[i], model.grid_pred_reg_decoded[i]]
   e2e_h2d_bytes = sum(a.nbytes for a in e2e_h2d)
   if cfg.use_beam_search:
