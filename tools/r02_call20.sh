@@ -12,3 +12,4 @@ show("c4", d)
 for k, v in d.get("extra", {}).items(): show(k, v); print(v.get("ddp_equivalence"))
 PY
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 2>/dev/null | tail -1 | cut -c1-300
+timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_parity_gpu.py -q -x -k "cell_f16f8_golden and dec_cx32 or fanout_equals" 2>&1 | tail -6
