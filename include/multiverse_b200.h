@@ -260,6 +260,15 @@ int mvb_emb_dense_fwd(const float* x, const float* We, const float* be, int E, v
 int mvb_beam_step(const float* logits, const float* score_in, float* score_out, int32_t* ids_out,
                   int32_t* parents_out, int32_t* row_map_out, int64_t N, int B, int V,
                   int first_step, int zero_scores, int diverse, float log_gamma, void* stream);
+/* The other optimizers of Trainer (pred_models.py:1667-1681), fused with the same gradient preparation as
+ * mvb_clip_adadelta (g = grad * grad_scale + wd * w, then clip to +-clip if clip > 0):
+ *   kind 1 MomentumOptimizer(lr, p1 = 0.9): slot1 = p1 slot1 + g; w -= lr slot1
+ *   kind 2 AdamOptimizer: slot1 (m), slot2 (v), p1 = beta1, p2 = beta2; `lr` must carry sqrt(1-beta2^t)/(1-beta1^t)
+ *   kind 3 RMSPropOptimizer: slot1 = ms (initialise to ONE like TF), slot2 = mom, p1 = decay 0.9, p2 = momentum 0.0,
+ *          eps 1e-10 */
+int mvb_clip_update(float* w, const float* grad, float* slot1, float* slot2, int64_t n, int kind, float lr, float p1,
+                    float p2, float eps, float clip, float wd, float grad_scale, void* stream);
+
 /* ---- f-4: SimAug's white-box attack on the scene input (SimAug/code/pred_models.py:60-170) ----------------------
  * The gradient of the (targeted) classification loss with respect to the scene features comes out of the ordinary
  * backward pass: mvb_scene_conv_bwd with a non-NULL `din` for the FIRST scene convolution accumulates d loss / d input

@@ -311,6 +311,10 @@ int mvb_decode_trajectories(const int32_t* ids, const float* offsets, const floa
                             int64_t N, int K, int Tp, int V, void* stream) {
   return decode_trajectories(ids, offsets, centers, out, N, K, Tp, V, S(stream));
 }
+int mvb_clip_update(float* w, const float* grad, float* slot1, float* slot2, int64_t n, int kind, float lr, float p1,
+                    float p2, float eps, float clip, float wd, float grad_scale, void* stream) {
+  return clip_update(w, grad, slot1, slot2, n, kind, lr, p1, p2, eps, clip, wd, grad_scale, S(stream));
+}
 int mvb_adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, int64_t n,
                  void* stream) {
   return adv_step(x, adv, grad, out, eps, step, n, S(stream));

@@ -104,6 +104,8 @@ int enc_class_input_bwd(const float* dxh, int cpad, const int* frame_idx, const 
                         float* dscene, long long NS, int H, int W, cudaStream_t stream);
 int scene_mean_bwd(const float* dmean, const int* frame_idx, float* dscene, long long N, int T,
                    long long HWC, cudaStream_t stream);
+int clip_update(float* w, const float* grad, float* s1, float* s2, long long n, int kind, float lr, float p1, float p2,
+                float eps, float clip, float wd, float gscale, cudaStream_t stream);
 int adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, long long n,
              cudaStream_t stream);
 int mix(const float* a, const float* b, float* out, float w, long long n, cudaStream_t stream);

@@ -486,6 +486,38 @@ __global__ void clip_adadelta_kernel(float* __restrict__ w, const float* __restr
   }
 }
 
+// The other three optimizers Trainer offers (code/pred_models.py:1667-1681), same gradient preparation (wd * w added,
+// 1/G scaling, element-wise clip):
+//   kind 1  tf.train.MomentumOptimizer(lr, 0.9):   a = m a + g;  w -= lr a                        (s1 = a)
+//   kind 2  tf.train.AdamOptimizer(lr):            m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//                                                  w -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)   (s1 = m, s2 = v)
+//   kind 3  tf.train.RMSPropOptimizer(lr):         ms = d ms + (1-d) g^2;  mom = mu mom + lr g rsqrt(ms + eps);
+//                                                  w -= mom      (s1 = ms, initialised to ONE by TF; s2 = mom)
+__global__ void clip_update_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ s1,
+                                   float* __restrict__ s2, long long n, int kind, float lr, float p1, float p2,
+                                   float eps, float clip, float wd, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gv = fmaf(wd, w[i], grad[i] * gscale);
+    if (clip > 0.f) gv = fminf(fmaxf(gv, -clip), clip);
+    if (kind == 1) {
+      const float a = p1 * s1[i] + gv;
+      s1[i] = a;
+      w[i] -= lr * a;
+    } else if (kind == 2) {
+      const float m = p1 * s1[i] + (1.f - p1) * gv;
+      const float v = p2 * s2[i] + (1.f - p2) * gv * gv;
+      s1[i] = m; s2[i] = v;
+      w[i] -= lr * m / (sqrtf(v) + eps);          // lr already carries sqrt(1-b2^t)/(1-b1^t)
+    } else {
+      const float ms = p1 * s1[i] + (1.f - p1) * gv * gv;
+      const float mom = p2 * s2[i] + lr * gv * rsqrtf(ms + eps);
+      s1[i] = ms; s2[i] = mom;
+      w[i] -= mom;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ launchers
 static inline int grid_for(long long n, int threads) {
   const long long b = (n + threads - 1) / threads;
@@ -646,6 +678,15 @@ int clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, long 
                   float rho, float eps, float clip, float wd, float gscale, cudaStream_t stream) {
   MVB_REQUIRE(w && grad && acc && acc_upd && n > 0, "clip_adadelta: bad args");
   clip_adadelta_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w, grad, acc, acc_upd, n, lr, rho, eps, clip, wd, gscale);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int clip_update(float* w, const float* grad, float* s1, float* s2, long long n, int kind, float lr, float p1, float p2,
+                float eps, float clip, float wd, float gscale, cudaStream_t stream) {
+  MVB_REQUIRE(w && grad && s1 && n > 0 && kind >= 1 && kind <= 3 && (kind == 1 || s2), "clip_update: bad args (kind %d)", kind);
+  clip_update_kernel<<<grid_for(n, 256), 256, 0, stream>>>(w, grad, s1, s2, n, kind, lr, p1, p2, eps, clip, wd, gscale);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;

@@ -395,12 +395,16 @@ class ConvRNNEngine(object):
           items.append(("%s/%d" % (name, i), t))
     return items
 
-  def forward_graph(self, feeds, pred_len=None):
+  def forward_graph(self, feeds, pred_len=None, on_output=None):
     """forward() captured per feed signature (shapes, dtypes, rollout length) into a CUDA graph and replayed:
     a forward is 120-950 kernel launches with no host-side data dependence (the beam loop has a fixed trip count and
     parents travel as device row maps), so at small batches - where the ~20 us the host spends per launch exceeds
     the kernels' run time - one graph launch replaces them.  Bit-identical to forward().  The returned tensors
-    are the graph's static outputs: they are overwritten by the next replay of the same signature."""
+    are the graph's static outputs: they are overwritten by the next replay of the same signature.
+    The capture is cut into SEGMENTS at the end of every class branch (graphs sharing one memory pool, replayed in
+    order): `on_output(name, index, tensor)` is called after the segment that completes a tensor has been launched,
+    so a caller can start the device->host copy of the beam logits (87 % of the fetched bytes) on another stream
+    while the regression branch still runs - like forward()'s own on_output in eager mode."""
     tp = int(pred_len) if pred_len else self.cfg.pred_len
     # The number of unique scene frames F changes from batch to batch in the reference's loops (scene_feat is
     # re-compacted per batch, code/pred_utils.py:680-704), so the graph is captured for F rounded up to a multiple
@@ -419,7 +423,7 @@ class ConvRNNEngine(object):
         if len(self._graph_seen) >= 64:
           self._graph_seen.clear()
         self._graph_seen.add(key)
-        return self.forward(feeds, tp)
+        return self.forward(feeds, tp, on_output=on_output)
       static = dict(scene_feat=torch.zeros((f_pad,) + tuple(sf.shape[1:]), dtype=sf.dtype, device=sf.device),
                     obs_scene=feeds["obs_scene"].clone(),
                     grid_obs_labels=[None if t is None else t.clone() for t in feeds["grid_obs_labels"]],
@@ -427,18 +431,41 @@ class ConvRNNEngine(object):
       static["scene_feat"][:sf.shape[0]].copy_(sf)
       self.forward(static, tp)        # eager pass: persistent buffers, kernel attributes, lazy caches
       torch.cuda.synchronize(self.device)
-      graph = torch.cuda.CUDAGraph()
       # thread_local: calls made by other threads (NCCL watchdog, profilers) must not invalidate the capture
-      with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-        out = self.forward(static, tp)
-      ent = (graph, static, out)
+      segments, pending = [], []
+      pool = torch.cuda.graph_pool_handle()
+      cap = torch.cuda.Stream(device=self.device)
+      cap.wait_stream(torch.cuda.current_stream(self.device))
+      with torch.cuda.stream(cap):
+        cur = [torch.cuda.CUDAGraph()]
+        cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+
+        def cut(name, index, t):
+          pending.append((name, index, t))
+          if name == "grid_pred_decoded":               # a class branch (and its beam outputs) is complete
+            cur[0].capture_end()
+            segments.append((cur[0], list(pending)))
+            del pending[:]
+            cur[0] = torch.cuda.CUDAGraph()
+            cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+        try:
+          out = self.forward(static, tp, on_output=cut)
+        finally:
+          cur[0].capture_end()
+        segments.append((cur[0], list(pending)))
+      torch.cuda.current_stream(self.device).wait_stream(cap)
+      ent = (segments, static, out)
       while len(self._graphs) >= self.GRAPH_CACHE:
         self._graphs.pop(next(iter(self._graphs)))      # oldest first (dicts keep insertion order)
       self._graphs[key] = ent
-    graph, static, out = ent
+    segments, static, out = ent
     for (name, dst), (_, src) in zip(self._flat_feeds(static), flat):
       (dst[:src.shape[0]] if name == "scene_feat" else dst).copy_(src, non_blocking=True)
-    graph.replay()
+    for graph, done in segments:
+      graph.replay()
+      if on_output is not None:
+        for name, index, t in done:
+          on_output(name, index, t)
     return out
 
   def grid_feeds_from_traj(self, obs_traj, centers=None, video_h=1080, video_w=1920):

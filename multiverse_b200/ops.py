@@ -373,6 +373,12 @@ def clip_adadelta(w, grad, acc, acc_upd, lr, clip, wd, grad_scale=1.0, rho=0.95,
             float(rho), float(eps), float(clip or 0.0), float(wd), float(grad_scale), _stream())
 
 
+def clip_update(w, grad, s1, s2, kind, lr, p1, p2, eps, clip, wd, grad_scale=1.0):
+  """Momentum (kind 1) / Adam (2) / RMSProp (3) update fused with wd, 1/G scaling and the element-wise clip."""
+  _lib.call("mvb_clip_update", _p(w), _p(grad), _p(s1), _p(s2), w.numel(), int(kind), float(lr), float(p1), float(p2),
+            float(eps), float(clip or 0.0), float(wd), float(grad_scale), _stream())
+
+
 def decode_trajectories(ids, offs, centers, out):
   """ids int32 [N,K,Tp], offs fp32 [Tp,N,V,2], centers fp32 [V,2] -> out fp32 [N,K,Tp,2]."""
   n, k, tp = ids.shape

@@ -379,14 +379,10 @@ class Model(object):
     with torch.cuda.device(dev):
       feeds, tp = self._device_feeds(feed), self._fed_pred_len(feed)
       if self._launch_bound(feeds):
-        # small batch: the host cannot launch ~10^3 kernels as fast as the GPU runs them -> one graph replay,
-        # then the copies (the static outputs are consumed before the next replay)
-        out = eng.forward_graph(feeds, pred_len=tp)
-        for i in range(len(self.config.scene_grids)):
-          on_output("grid_pred_decoded", i, out["grid_pred_decoded"][i])
-          on_output("grid_pred_reg_decoded", i, out["grid_pred_reg_decoded"][i])
-        for j, t in enumerate(out["beam_outputs"] or []):
-          on_output("beam_outputs", j, t)
+        # small batch: the host cannot launch ~10^3 kernels as fast as the GPU runs them -> graph replay
+        # (captured in segments cut after every class branch: the fetches of a finished branch travel while the next
+        # segment runs; the static outputs are consumed before the next replay)
+        eng.forward_graph(feeds, pred_len=tp, on_output=on_output)
       else:
         eng.forward(feeds, pred_len=tp, on_output=on_output)
       side.synchronize()
@@ -438,8 +434,8 @@ class Model(object):
     """What sess.run([loss, train_op, wd_loss, pred_grid_loss]) does (Trainer.step, :1719-1742)."""
     import torch
     cfg = self.config
-    if getattr(cfg, "optimizer", "adadelta") != "adadelta":
-      raise NotImplementedError("only the default Adadelta optimizer has a CUDA update kernel")
+    if getattr(cfg, "optimizer", "adadelta") not in ("adadelta", "momentum", "adam", "rmsprop"):
+      raise Exception("Optimizer not implemented")            # code/pred_models.py:1681
     if getattr(cfg, "use_soft_grid_class", False) or getattr(cfg, "mask_grid_regression", False):
       raise NotImplementedError("soft grid labels / masked regression loss are not implemented")
     if not getattr(cfg, "train_w_onehot", False):
@@ -535,7 +531,7 @@ def _engine_config(config):
   d["obs_len"] = getattr(config, "obs_len", None)    # multifuture_inference.py's Namespace has none (:419-452)
   d["activation_func"] = "tanh"
   for k, default in (("grid_loss_weight", 1.0), ("grid_reg_loss_weight", 0.1), ("wd", 0.0),
-                     ("clip_gradient_norm", None), ("is_train", False)):
+                     ("clip_gradient_norm", None), ("is_train", False), ("optimizer", "adadelta")):
     d[k] = getattr(config, k, default)
   for flag in ("use_single_decoder", "use_teacher_forcing"):
     if getattr(config, flag, False):

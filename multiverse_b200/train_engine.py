@@ -12,6 +12,8 @@ MN-major operands read straight from the stored planes);  around it: head_bwd, e
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import ops
@@ -277,9 +279,28 @@ class TrainEngine(ConvRNNEngine):
     variables named .../W (:1033), gradients pre-scaled by 1/world after an all-reduce SUM."""
     cfg = self.cfg
     clip = getattr(cfg, "clip_gradient_norm", None) or 0.0
+    opt = getattr(cfg, "optimizer", "adadelta")
+    if opt != "adadelta" and not getattr(self, "_opt_slots_ready", False):
+      if opt == "rmsprop":                      # TF initialises the RMSProp mean-square slot to ones
+        for k in self.names:
+          self.acc[k].fill_(1.0)
+      self._opt_steps, self._opt_slots_ready = 0, True
+    if opt == "adam":
+      self._opt_steps += 1
+      t = self._opt_steps
+      lr = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
     for k in self.names:
-      ops.clip_adadelta(self.params[k], self.grads[k], self.acc[k], self.acc_upd[k], lr, clip,
-                        cfg.wd if k.endswith("/W") else 0.0, 1.0 / world)
+      wd = cfg.wd if k.endswith("/W") else 0.0
+      if opt == "adadelta":                     # tf.train.AdadeltaOptimizer(lr): rho 0.95, eps 1e-8
+        ops.clip_adadelta(self.params[k], self.grads[k], self.acc[k], self.acc_upd[k], lr, clip, wd, 1.0 / world)
+      elif opt == "momentum":                   # MomentumOptimizer(lr, momentum=0.9), :1668
+        ops.clip_update(self.params[k], self.grads[k], self.acc[k], self.acc_upd[k], 1, lr, 0.9, 0.0, 0.0, clip, wd, 1.0 / world)
+      elif opt == "adam":                       # AdamOptimizer(lr): beta1 .9, beta2 .999, eps 1e-8, :1675
+        ops.clip_update(self.params[k], self.grads[k], self.acc[k], self.acc_upd[k], 2, lr, 0.9, 0.999, 1e-8, clip, wd, 1.0 / world)
+      elif opt == "rmsprop":                    # RMSPropOptimizer(lr): decay .9, momentum 0, eps 1e-10, :1678
+        ops.clip_update(self.params[k], self.grads[k], self.acc[k], self.acc_upd[k], 3, lr, 0.9, 0.0, 1e-10, clip, wd, 1.0 / world)
+      else:
+        raise ValueError("Optimizer not implemented: %r" % (opt,))      # :1681
     self._repack()
 
   def loss_and_grads_chunked(self, feeds, micro_batch):

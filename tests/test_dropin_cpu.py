@@ -422,6 +422,12 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
     replays = 0
     def replay(self):
       FakeGraph.replays += 1
+    def capture_begin(self, **kw): pass
+    def capture_end(self): pass
+
+  class FakeStream(object):
+    def __init__(self, *a, **k): pass
+    def wait_stream(self, other): pass
 
   class FakeCtx(object):
     def __init__(self, g, **kw): pass
@@ -431,6 +437,10 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
   monkeypatch.setattr(torch.cuda, "graph", FakeCtx)
   monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  monkeypatch.setattr(torch.cuda, "graph_pool_handle", lambda: None)
+  monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+  monkeypatch.setattr(torch.cuda, "stream", lambda s: FakeCtx(None))
+  monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
   eng = E.ConvRNNEngine.__new__(E.ConvRNNEngine)
   eng.cfg = types.SimpleNamespace(pred_len=12)
   eng.device, eng.cell_events, eng._graphs, eng._graph_seen = torch.device("cpu"), None, {}, set()

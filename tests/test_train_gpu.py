@@ -1,12 +1,16 @@
 # coding=utf-8
 """GPU parity tests of the backward (BPTT) kernels against torch autograd on the oracle's
 torch-CPU restatement (fp64)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import cases
 from oracle import multiverse_ref_torch as RT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 GTOL = 2e-4   # gradients: relative to the largest entry of each gradient tensor
@@ -363,3 +367,43 @@ def test_simaug_scene_input_gradient_and_attack(dev):
   acfg.adv_use_fgsm = True; acfg.use_mixup = True; acfg.mixup_alpha = 1.0; acfg.mixup_mix_adv = False
   adv_mix, _ = simaug.white_box_attack(eng, feeds, f["grid_pred_labels"][1], acfg, np.random.default_rng(5))
   assert bool(((adv_mix - x).abs() <= 0.1 + 1e-6).all())
+
+
+@pytest.mark.parametrize("opt", ["momentum", "adam", "rmsprop"])
+def test_other_optimizers_match_tf_semantics(dev, opt):
+  """Trainer's non-default optimizers (code/pred_models.py:1667-1681) - MomentumOptimizer(lr, 0.9), AdamOptimizer(lr),
+  RMSPropOptimizer(lr) - fused with weight decay, 1/G scaling and the element-wise clip (mvb_clip_update), three steps
+  against the optimizer classes of the eager TF-1.15 stand-in (oracle/tf1_eager: python/training/{momentum,adam,
+  rmsprop}.py restated) and against closed forms."""
+  import sys
+  from multiverse_b200 import ops
+  sys.path.insert(0, os.path.join(ROOT, "oracle", "tf1_eager"))
+  saved = {k: v for k, v in sys.modules.items() if k == "tensorflow" or k.startswith("tensorflow.")}
+  for k in saved:
+    del sys.modules[k]
+  try:
+    import tensorflow as tfe
+    assert tfe.__version__.endswith("eager-standin")
+  finally:
+    sys.path.remove(os.path.join(ROOT, "oracle", "tf1_eager"))
+    for k in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.")]:
+      del sys.modules[k]
+    sys.modules.update(saved)
+  rng = np.random.default_rng(8)
+  n, lr, clip, wd, gs = 4096, 0.05, 10.0, 0.001, 0.5
+  w0 = rng.standard_normal(n); grads = [rng.standard_normal(n) * 8 for _ in range(3)]
+  tfe.reset_default_graph()
+  var = tfe.Variable(torch.from_numpy(w0.copy()), "w", True)
+  O = dict(momentum=lambda: tfe.train.MomentumOptimizer(lr, momentum=0.9), adam=lambda: tfe.train.AdamOptimizer(lr),
+           rmsprop=lambda: tfe.train.RMSPropOptimizer(lr))[opt]()
+  tw = T(w0.astype(np.float32), dev)
+  s1 = torch.ones_like(tw) if opt == "rmsprop" else torch.zeros_like(tw)
+  s2 = torch.zeros_like(tw)
+  for t, g in enumerate(grads, 1):
+    gg = np.clip(g * gs + wd * var.numpy(), -clip, clip)                    # what Trainer hands to apply_gradients
+    O.apply_gradients([(tfe.Tensor(torch.from_numpy(gg)), var)]).run()
+    kind, p1, p2, eps = dict(momentum=(1, 0.9, 0.0, 0.0), adam=(2, 0.9, 0.999, 1e-8), rmsprop=(3, 0.9, 0.0, 1e-10))[opt]
+    lr_t = lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) if opt == "adam" else lr
+    ops.clip_update(tw, T(g.astype(np.float32), dev), s1, s2, kind, lr_t, p1, p2, eps, clip, wd, grad_scale=gs)
+    err = np.abs(tw.cpu().numpy() - var.numpy()).max() / np.abs(var.numpy()).max()
+    assert err < 2e-5, (opt, t, err)
