@@ -121,24 +121,25 @@ class Session(object):
 
   def run(self, fetches, feed_dict=None):
     flat = []
-
-    def walk(f):
-      if isinstance(f, (list, tuple)):
-        return [walk(x) for x in f]
-      flat.append(f)
-      return len(flat) - 1
-
-    tree = walk(fetches)
+    tree = _flatten_fetches(fetches, flat)
     owners = [getattr(f, "owner", None) for f in flat]
     model = next((o for o in owners if o is not None), None)
     if model is None:
       raise ValueError("Session.run: nothing to fetch from a multiverse_b200 model")
-    vals = model._run(flat, feed_dict or {})
+    return _rebuild_fetches(tree, model._run(flat, feed_dict or {}))
 
-    def build(t):
-      return [build(x) for x in t] if isinstance(t, list) else vals[t]
 
-    return build(tree)
+# Module-level on purpose: as nested recursive closures these two formed reference cycles (function <-> its own
+# closure cell) that kept every fetched array - and its pinned host block - alive until the next cyclic GC pass.
+def _flatten_fetches(f, flat):
+  if isinstance(f, (list, tuple)):
+    return [_flatten_fetches(x, flat) for x in f]
+  flat.append(f)
+  return len(flat) - 1
+
+
+def _rebuild_fetches(t, vals):
+  return [_rebuild_fetches(x, vals) for x in t] if isinstance(t, list) else vals[t]
 
 
 @contextlib.contextmanager

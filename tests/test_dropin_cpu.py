@@ -474,3 +474,33 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   eng.planes = 2
   eng.set_weights({})
   assert not eng._graphs
+
+
+def test_session_run_leaves_no_reference_cycle_on_the_results(monkeypatch):
+  """The fetched arrays must die with the caller's last reference (their pinned blocks are reused then), not at
+  the next cyclic-GC pass."""
+  import gc
+  import weakref
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow",):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+
+  class Owner(object):
+    def _run(self, handles, feed):
+      return [np.zeros(4) + i for i in range(len(handles))]
+
+  class H(object):
+    def __init__(self, owner):
+      self.owner = owner
+
+  owner = Owner()
+  gc.disable()
+  try:
+    out = tf.Session().run([H(owner), [H(owner), H(owner)]], {})
+    assert out[1][1][0] == 2.0
+    refs = [weakref.ref(out[0]), weakref.ref(out[1][0])]
+    del out
+    assert all(r() is None for r in refs)
+  finally:
+    gc.enable()

@@ -149,3 +149,47 @@ def test_compact_grid_feeds_equal_dense_feeds(monkeypatch):
     b = sess.run(fetches, compact_fd)
   for x, y in zip(a, b):
     assert np.array_equal(x, y)
+
+
+def test_fetched_arrays_own_their_pinned_blocks(monkeypatch):
+  """Session.run hands out numpy arrays over pooled pinned blocks: a result the caller still holds is never
+  overwritten by a later run, and a released block is used again instead of a fresh pinned allocation."""
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  for m in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+    monkeypatch.delitem(sys.modules, m, raising=False)
+  import tensorflow as tf
+  import pred_models
+  from multiverse_b200 import synthetic
+  tf.reset_default_graph()
+  cfg = synthetic.make_config(batch_size=2)
+  args = types.SimpleNamespace(**vars(cfg)); args.modelname = "m"; args.use_soft_grid_class = False
+  args.use_gt_grid = False
+  w = synthetic.make_weights(cfg, 5)
+  model = pred_models.get_model(args, gpuid=0)
+  tf.global_variables_initializer().run()
+  for v in tf.global_variables():
+    if v.name.split(":")[0] in w:
+      v.assign(w[v.name.split(":")[0]])
+  fds = []
+  for seed in (5, 6):
+    feeds = synthetic.make_feeds(cfg, 2, seed)
+    fds.append(model.get_feed_dict(make_batch(cfg, feeds, 2)[1]))
+  fetch = [model.grid_pred_decoded[0], model.grid_pred_reg_decoded[0]]
+  with tf.Session() as sess:
+    a = sess.run(fetch, fds[0])
+    keep = [x.copy() for x in a]
+    b = sess.run(fetch, fds[1])                   # `a` is still alive: must land in other blocks
+    assert all(np.array_equal(x, y) for x, y in zip(a, keep))
+    assert not np.array_equal(a[0], b[0])
+    view = a[1][:, 3:]                            # a view keeps its block alive after `a` is gone
+    ref_view = view.copy()
+    del a
+    c = sess.run(fetch, fds[1])
+    assert all(np.array_equal(x, y) for x, y in zip(b, c))
+    assert np.array_equal(view, ref_view)
+    sizes = {k: len(v) for k, v in model._pinned.items()}
+    assert sizes and max(sizes.values()) == 3, sizes      # a's view, b, c
+    del view, b, c
+    for _ in range(6):                            # nothing held: the same blocks serve every run
+      sess.run(fetch, fds[0])
+    assert {k: len(v) for k, v in model._pinned.items()} == sizes

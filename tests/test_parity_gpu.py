@@ -182,6 +182,28 @@ def test_gnn_row_map_and_beam_tiling(dev):
   assert rel(out, ref) < TIGHT
 
 
+@pytest.mark.parametrize("planes", [2, 16])
+@pytest.mark.parametrize("shape", [(3, 36, 18), (2, 18, 9), (2, 18, 32), (1, 4, 48), (2, 1, 5), (2, 5, 1), (1, 7, 3)])
+def test_gnn_shapes_against_dense_oracle(dev, shape, planes):
+  """Both formulations of the attention kernel (shared-memory ring of image rows; one warp per image row for grids
+  wider than the ring allows, here 4x48) against the dense [HW,HW] restatement, incl. odd widths, single rows and
+  single columns, and both operand formats of the output."""
+  from multiverse_b200 import ops
+  ns, h, w = shape
+  rng = np.random.RandomState(h * 100 + w)
+  hs = (rng.standard_normal((ns, h, w, 256)) * 0.5).astype(np.float32)
+  sc = rng.standard_normal((ns, h, w, 64)).astype(np.float32)
+  ref = R.gnn_dense(hs.astype(np.float64), sc.astype(np.float64))
+  h32 = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(hs, dev), h32, h, w)
+  xh = ops.alloc_xh(ns, h, w, 288, planes, dev)
+  ops.gnn_attend_fwd(h32, T(sc, dev), xh, h, w, ns)
+  vals, _ = ops.operand_values(xh)
+  out = vals[:, 32:].view(ns, h + 1, w + 1, 256)
+  assert rel(out[:, :h, :w].cpu().numpy(), ref) < (TIGHT if planes == 2 else 2e-5)
+  assert float(out[:, h].abs().max()) == 0.0 and float(out[:, :, w].abs().max()) == 0.0      # halo stays zero
+  assert float(vals[:, :32].abs().max()) == 0.0
+
+
 def test_heads_and_embeddings_golden(dev):
   from multiverse_b200 import ops
   d = cases.head_case(); g = gold("head")

@@ -24,6 +24,7 @@ fd = {model.scene_feat: pin(f["scene_feat"]), model.obs_scene: pin(f["obs_scene"
       model.obs_traj: np.ascontiguousarray(f["traj64"][:, :8]), model.grid_obs_labels[0]: pin(f["grid_obs_labels"][0]),
       model.grid_centers[0]: np.asarray(synthetic.grid_centers(cfg)[0], np.float64)}
 fetches = [model.grid_pred_decoded[0], model.grid_pred_reg_decoded[0], model.beam_outputs]
+if os.environ.get("PROBE_SMALL_FETCH"): fetches = [model.grid_pred_reg_decoded[0]]
 for _ in range(4): sess.run(fetches, fd)
 T = {}
 def timed(name, fn):
@@ -34,9 +35,33 @@ def timed(name, fn):
 model._device_feeds = timed("device_feeds", model._device_feeds)
 eng = model._engine
 eng.forward_graph = timed("forward_graph", eng.forward_graph)
+eng.forward = timed("forward", eng.forward)
+_empty = torch.empty
+def empty_timed(*a, **k):
+  t0 = time.perf_counter(); r = _empty(*a, **k)
+  if k.get("pin_memory") and r.numel() > 1e5: T.setdefault("pinned_empty %s" % (tuple(r.shape),), []).append((time.perf_counter() - t0,) * 2)
+  return r
+torch.empty = empty_timed
+_contig = torch.Tensor.contiguous
+def contig_timed(self, *a, **k):
+  t0 = time.perf_counter(); r = _contig(self, *a, **k)
+  if self.is_cuda and self.numel() > 1e6: T.setdefault("contiguous %s same=%s" % (tuple(r.shape), r is self), []).append((time.perf_counter() - t0,) * 2)
+  return r
+torch.Tensor.contiguous = contig_timed
 t0 = time.perf_counter()
 for _ in range(10): sess.run(fetches, fd)
 tot = (time.perf_counter() - t0) / 10
 print("n=%d total per run %.2f ms" % (n, tot * 1e3))
 for k, v in T.items():
   print("  %-14s host %.2f ms, until device idle %.2f ms" % (k, 1e3 * np.mean([a for a, _ in v]), 1e3 * np.mean([b for _, b in v])))
+
+# device-resident forward of the same feeds, eager and graph, no fetch
+torch.empty = _empty; torch.Tensor.contiguous = _contig
+T.clear()
+with torch.cuda.device(eng.device):
+  feeds = model._device_feeds(fd)
+  for _ in range(5): eng.forward(feeds, 12)
+  if os.environ.get("MVB_CUDA_GRAPH") != "0":
+    for _ in range(5): eng.forward_graph(feeds, 12)
+for k, v in T.items():
+  print("  resident %-14s host %.2f ms, until device idle %.2f ms" % (k, 1e3 * np.mean([a for a, _ in v][-3:]), 1e3 * np.mean([b for _, b in v][-3:])))

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+echo "== graph auto"; timeout 300 python tools/gpu_probe_e2e.py 64 2>&1 | tail -12
+echo "== eager";      MVB_CUDA_GRAPH=0 timeout 300 python tools/gpu_probe_e2e.py 64 2>&1 | tail -12
