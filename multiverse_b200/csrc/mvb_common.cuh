@@ -105,17 +105,25 @@ __host__ __device__ __forceinline__ int f8_off(int c, int p, int cpad) {
 __device__ __forceinline__ uint8_t to_e4m3(float v) {
   return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
 }
+// two values -> their fp16 pair, the e4m3 pair of the fp16 values and the e4m3 pair of the scaled residuals
+// (packed conversions: 1 + 1 + 1 cvt for two values; low half / low byte = the first value)
+__device__ __forceinline__ void split_f16f8_x2(float v0, float v1, uint32_t& h2, uint32_t& e0, uint32_t& e1) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  h2 = *reinterpret_cast<const uint32_t*>(&h);
+  e0 = (uint32_t)__nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(h), __NV_SATFINITE, __NV_E4M3);
+  const float2 f = __half22float2(h);
+  e1 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((v0 - f.x) * kF8ResidualScale, (v1 - f.y) * kF8ResidualScale),
+                                          __NV_SATFINITE, __NV_E4M3);
+}
 // 8 consecutive channels -> 16 B of fp16 and 8 B of each fp8 plane
 __device__ __forceinline__ void split_f16f8_x8(const float (&v)[8], uint4& f16, uint2& p0, uint2& p1) {
   uint32_t hw[4], b0[2] = {0u, 0u}, b1[2] = {0u, 0u};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half lo = __float2half_rn(v[2 * i]), hi = __float2half_rn(v[2 * i + 1]);
-    const float flo = __half2float(lo), fhi = __half2float(hi);
-    hw[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
-    b0[i >> 1] |= ((uint32_t)to_e4m3(flo) | ((uint32_t)to_e4m3(fhi) << 8)) << (16 * (i & 1));
-    b1[i >> 1] |= ((uint32_t)to_e4m3((v[2 * i] - flo) * kF8ResidualScale) |
-                   ((uint32_t)to_e4m3((v[2 * i + 1] - fhi) * kF8ResidualScale) << 8)) << (16 * (i & 1));
+    uint32_t e0, e1;
+    split_f16f8_x2(v[2 * i], v[2 * i + 1], hw[i], e0, e1);
+    b0[i >> 1] |= e0 << (16 * (i & 1));
+    b1[i >> 1] |= e1 << (16 * (i & 1));
   }
   f16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   p0 = make_uint2(b0[0], b0[1]);

@@ -166,23 +166,23 @@ gnn_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
     }
     const float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
     const long long orow = s * g.S + (long long)y * g.Wp + x;
-    if (MIX) {
+    if constexpr (MIX) {
       store_f16f8_x8(hp_out, plane_stride, orow, ch_off + lane * 8, cpad_out, o);
-      return;
-    }
-    uint32_t pk[P][4];
+    } else {
+      uint32_t pk[P][4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      __nv_bfloat16 a[P], b[P];
-      split_planes<P>(o[2 * v], a);
-      split_planes<P>(o[2 * v + 1], b);
+      for (int v = 0; v < 4; ++v) {
+        __nv_bfloat16 a[P], b[P];
+        split_planes<P>(o[2 * v], a);
+        split_planes<P>(o[2 * v + 1], b);
 #pragma unroll
-      for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
-    }
+        for (int p = 0; p < P; ++p) pk[p][v] = pack_bf16x2(a[p], b[p]);
+      }
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
-      *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+      for (int p = 0; p < P; ++p) {
+        uint4* po = reinterpret_cast<uint4*>(hp_out + p * plane_stride + orow * cpad_out + ch_off + lane * 8);
+        *po = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+      }
     }
   };
   for (int x = 0; x < g.W; x += 4) {
@@ -235,16 +235,14 @@ __device__ __forceinline__ void dot_acc(float2& acc, const float4& a, const floa
 template <int P, bool MIX>
 __device__ __forceinline__ void store_operand_x4(__nv_bfloat16* hp_out, long long plane_stride, long long row,
                                                  int ch, int cpad, const float (&v)[4]) {
-  if (MIX) {
+  if constexpr (MIX) {
     uint32_t hw[2], b0 = 0u, b1 = 0u;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const __half lo = __float2half_rn(v[2 * i]), hi = __float2half_rn(v[2 * i + 1]);
-      const float flo = __half2float(lo), fhi = __half2float(hi);
-      hw[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
-      b0 |= ((uint32_t)to_e4m3(flo) | ((uint32_t)to_e4m3(fhi) << 8)) << (16 * i);
-      b1 |= ((uint32_t)to_e4m3((v[2 * i] - flo) * kF8ResidualScale) |
-             ((uint32_t)to_e4m3((v[2 * i + 1] - fhi) * kF8ResidualScale) << 8)) << (16 * i);
+      uint32_t e0, e1;
+      split_f16f8_x2(v[2 * i], v[2 * i + 1], hw[i], e0, e1);
+      b0 |= e0 << (16 * i);
+      b1 |= e1 << (16 * i);
     }
     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hp_out) + row * cpad + ch) = make_uint2(hw[0], hw[1]);
     uint8_t* b8 = reinterpret_cast<uint8_t*>(hp_out) + 2 * plane_stride + row * 2 * cpad;

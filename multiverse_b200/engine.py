@@ -330,7 +330,12 @@ class ConvRNNEngine(object):
                                                            logits=step_logits)
 
   # ------------------------------------------------------------------ whole forward
-  def forward(self, feeds, pred_len=None, on_output=None):
+  def branches(self):
+    """The independent chains of one forward: ("class", i) and ("reg", i) per used scale (they share only the feeds;
+    the scene CNN belongs to the class chains)."""
+    return [(kind, i) for i in range(len(self.cfg.scene_grids)) if self.cfg.use_grids[i] for kind in ("class", "reg")]
+
+  def forward(self, feeds, pred_len=None, on_output=None, branches=None):
     """feeds: device tensors
          scene_feat fp32 [F,SH,SW,SC], obs_scene int32 [N,T],
          grid_obs_labels[i] int32 [N,T], grid_obs_regress[i] fp32 [N,T,h,w,2]
@@ -338,16 +343,21 @@ class ConvRNNEngine(object):
     grid_pred_reg_decoded[i] [N,Tp,h,w,2] ([] for unused scales, :170-171) and
     beam_outputs = [logits [N,B,Tp,V], ids [N,B,Tp], logprobs [N,B]] or None (:276).
     on_output(name, index, tensor) is called as soon as a fetched tensor is complete on the current stream, so a
-    caller can start its device->host copy on another stream while the remaining branches still run."""
+    caller can start its device->host copy on another stream while the remaining branches still run.
+    `branches`: subset of self.branches() to run (forward_graph captures one graph per chain); the outputs of the
+    others are None."""
     cfg = self.cfg
     emit = on_output if on_output is not None else (lambda *a: None)
+    run = set(self.branches() if branches is None else branches)
     # raw_rnn runs until `time >= pred_length` (code/pred_models.py:347,:520): the rollout length is the
     # FED pred_length (multifuture_inference.py feeds max_pred_lengths[idx], :311), not config.pred_len
     tp = int(pred_len) if pred_len else cfg.pred_len
     obs_scene = feeds["obs_scene"].to(torch.int32).contiguous()
     obs_scene_t = obs_scene.t().contiguous()
     n = obs_scene.shape[0]
-    convs, means = self.scene_cnn(feeds["scene_feat"].float().contiguous(), obs_scene)
+    convs = means = None
+    if any(kind == "class" for kind, _ in run):
+      convs, means = self.scene_cnn(feeds["scene_feat"].float().contiguous(), obs_scene)
     out = dict(grid_pred_decoded=[], grid_pred_reg_decoded=[], beam_outputs=None)
     for i, (h, w) in enumerate(cfg.scene_grids):
       if not cfg.use_grids[i]:
@@ -355,34 +365,35 @@ class ConvRNNEngine(object):
         out["grid_pred_reg_decoded"].append([])
         continue
       sw = self.scales[i]
-      labels = feeds["grid_obs_labels"][i].to(torch.int32)
-      labels_t = labels.t().contiguous()
-      obs_reg = feeds["grid_obs_regress"][i].float()
-      obs_reg_t = obs_reg.transpose(0, 1).contiguous()
-      # class branch
-      xh_dec = self._xh("dec_class", n, h, w, sw.dec_class.cpad, self.class_planes)
-      c_e, h_e = self.encode_class(i, convs[i], obs_scene_t, labels_t,
-                                   None if cfg.use_gnn else xh_dec[0])
-      if cfg.use_beam_search:
-        logits, ids, logprobs, _ = self.decode_class_beam(i, c_e, h_e, labels_t[-1].contiguous(),
-                                                          means[i], tp)
-        out["beam_outputs"] = [logits, ids, logprobs]
-        dec = logits[:, 0].reshape(n, tp, h, w, 1)                      # :799-803
-        for j, t in enumerate(out["beam_outputs"]):
-          emit("beam_outputs", j, t)
-      else:
-        lg, _ = self.decode_class_greedy(i, c_e, h_e, labels_t[-1].contiguous(), means[i], tp)
-        dec = lg.permute(1, 0, 2).reshape(n, tp, h, w, 1)
-      emit("grid_pred_decoded", i, dec)
-      # regression branch
-      xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad, self.fast_planes)
-      c_r, _ = self.encode_reg(i, obs_reg_t, xh_reg[0])
-      offs = self.decode_reg(i, c_r, obs_reg_t[-1], tp, xh_reg)
-      reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)
-      emit("grid_pred_reg_decoded", i, reg)
+      dec = reg = None
+      if ("class", i) in run:
+        labels = feeds["grid_obs_labels"][i].to(torch.int32)
+        labels_t = labels.t().contiguous()
+        xh_dec = self._xh("dec_class", n, h, w, sw.dec_class.cpad, self.class_planes)
+        c_e, h_e = self.encode_class(i, convs[i], obs_scene_t, labels_t,
+                                     None if cfg.use_gnn else xh_dec[0])
+        if cfg.use_beam_search:
+          logits, ids, logprobs, _ = self.decode_class_beam(i, c_e, h_e, labels_t[-1].contiguous(),
+                                                            means[i], tp)
+          out["beam_outputs"] = [logits, ids, logprobs]
+          dec = logits[:, 0].reshape(n, tp, h, w, 1)                      # :799-803
+          for j, t in enumerate(out["beam_outputs"]):
+            emit("beam_outputs", j, t)
+        else:
+          lg, _ = self.decode_class_greedy(i, c_e, h_e, labels_t[-1].contiguous(), means[i], tp)
+          dec = lg.permute(1, 0, 2).reshape(n, tp, h, w, 1)
+        emit("grid_pred_decoded", i, dec)
+      if ("reg", i) in run:
+        obs_reg = feeds["grid_obs_regress"][i].float()
+        obs_reg_t = obs_reg.transpose(0, 1).contiguous()
+        xh_reg = self._xh("dec_reg", n, h, w, sw.dec_reg.cpad, self.fast_planes)
+        c_r, _ = self.encode_reg(i, obs_reg_t, xh_reg[0])
+        offs = self.decode_reg(i, c_r, obs_reg_t[-1], tp, xh_reg)
+        reg = offs.permute(1, 0, 2, 3).reshape(n, tp, h, w, 2)
+        emit("grid_pred_reg_decoded", i, reg)
+        out.setdefault("_offs", {})[i] = offs           # engine layout [Tp,N,HW,2], for decode_trajectories
       out["grid_pred_decoded"].append(dec)
       out["grid_pred_reg_decoded"].append(reg)
-      out.setdefault("_offs", {})[i] = offs           # engine layout [Tp,N,HW,2], for decode_trajectories
     return out
 
   # ------------------------------------------------------------------ CUDA-graph replay of forward()
@@ -396,15 +407,16 @@ class ConvRNNEngine(object):
     return items
 
   def forward_graph(self, feeds, pred_len=None, on_output=None):
-    """forward() captured per feed signature (shapes, dtypes, rollout length) into a CUDA graph and replayed:
+    """forward() captured per feed signature (shapes, dtypes, rollout length) into CUDA graphs and replayed:
     a forward is 120-950 kernel launches with no host-side data dependence (the beam loop has a fixed trip count and
     parents travel as device row maps), so at small batches - where the ~20 us the host spends per launch exceeds
-    the kernels' run time - one graph launch replaces them.  Bit-identical to forward().  The returned tensors
-    are the graph's static outputs: they are overwritten by the next replay of the same signature.
-    The capture is cut into SEGMENTS at the end of every class branch (graphs sharing one memory pool, replayed in
-    order): `on_output(name, index, tensor)` is called after the segment that completes a tensor has been launched,
-    so a caller can start the device->host copy of the beam logits (87 % of the fetched bytes) on another stream
-    while the regression branch still runs - like forward()'s own on_output in eager mode."""
+    the kernels' run time - graph launches replace them.  Bit-identical to forward().  The returned tensors
+    are the graphs' static outputs: they are overwritten by the next replay of the same signature.
+    ONE GRAPH PER CHAIN (self.branches(): class / regression x scale), each with its own memory pool, replayed on
+    its own stream: the chains share nothing but the feeds, and at these batch sizes a launch of one chain leaves SMs
+    idle (64 rows of 36x18 = 2.4 waves of tiles) that the launches of another chain fill.  `on_output(name, index,
+    tensor)` is called inside the chain's stream right after its graph has been launched, so a caller can start the
+    device->host copy of the beam logits (87 % of the fetched bytes) while the other chains still run."""
     tp = int(pred_len) if pred_len else self.cfg.pred_len
     # The number of unique scene frames F changes from batch to batch in the reference's loops (scene_feat is
     # re-compacted per batch, code/pred_utils.py:680-704), so the graph is captured for F rounded up to a multiple
@@ -414,6 +426,7 @@ class ConvRNNEngine(object):
     flat = self._flat_feeds(feeds)
     key = (tp, f_pad) + tuple((k, tuple(t.shape[1:] if k == "scene_feat" else t.shape), t.dtype) for k, t in flat)
     ent = self._graphs.get(key)
+    main = torch.cuda.current_stream(self.device)
     if ent is None:
       if self.cell_events is not None:
         raise RuntimeError("forward_graph: per-launch event recording (cell_events) is an eager-mode feature")
@@ -431,41 +444,51 @@ class ConvRNNEngine(object):
       static["scene_feat"][:sf.shape[0]].copy_(sf)
       self.forward(static, tp)        # eager pass: persistent buffers, kernel attributes, lazy caches
       torch.cuda.synchronize(self.device)
-      # thread_local: calls made by other threads (NCCL watchdog, profilers) must not invalidate the capture
-      segments, pending = [], []
-      pool = torch.cuda.graph_pool_handle()
-      cap = torch.cuda.Stream(device=self.device)
-      cap.wait_stream(torch.cuda.current_stream(self.device))
-      with torch.cuda.stream(cap):
-        cur = [torch.cuda.CUDAGraph()]
-        cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
-
-        def cut(name, index, t):
-          pending.append((name, index, t))
-          if name == "grid_pred_decoded":               # a class branch (and its beam outputs) is complete
-            cur[0].capture_end()
-            segments.append((cur[0], list(pending)))
-            del pending[:]
-            cur[0] = torch.cuda.CUDAGraph()
-            cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
-        try:
-          out = self.forward(static, tp, on_output=cut)
-        finally:
-          cur[0].capture_end()
-        segments.append((cur[0], list(pending)))
-      torch.cuda.current_stream(self.device).wait_stream(cap)
-      ent = (segments, static, out)
+      chains = []
+      for bi, br in enumerate(self.branches()):
+        # the class chains are the long ones: their stream gets the higher priority (lower number)
+        stream = self._buf(("graph_stream", bi), lambda: torch.cuda.Stream(device=self.device,
+                                                                          priority=-1 if br[0] == "class" else 0))
+        done = []
+        stream.wait_stream(main)
+        with torch.cuda.stream(stream):
+          graph = torch.cuda.CUDAGraph()
+          # thread_local: calls made by other threads (NCCL watchdog, profilers) must not invalidate the capture
+          graph.capture_begin(capture_error_mode="thread_local")
+          try:
+            part = self.forward(static, tp, branches=[br], on_output=lambda *a: done.append(a))
+          finally:
+            graph.capture_end()
+        main.wait_stream(stream)
+        chains.append((br, stream, graph, done, part))
+      out = dict(grid_pred_decoded=[[] for _ in self.cfg.scene_grids],
+                 grid_pred_reg_decoded=[[] for _ in self.cfg.scene_grids], beam_outputs=None)
+      for (kind, i), _, _, _, part in chains:
+        if kind == "class":
+          out["grid_pred_decoded"][i] = part["grid_pred_decoded"][i]
+          if part["beam_outputs"] is not None:
+            out["beam_outputs"] = part["beam_outputs"]
+        else:
+          out["grid_pred_reg_decoded"][i] = part["grid_pred_reg_decoded"][i]
+          out.setdefault("_offs", {})[i] = part["_offs"][i]
+      ent = (chains, static, out)
       while len(self._graphs) >= self.GRAPH_CACHE:
         self._graphs.pop(next(iter(self._graphs)))      # oldest first (dicts keep insertion order)
       self._graphs[key] = ent
-    segments, static, out = ent
+    chains, static, out = ent
     for (name, dst), (_, src) in zip(self._flat_feeds(static), flat):
       (dst[:src.shape[0]] if name == "scene_feat" else dst).copy_(src, non_blocking=True)
-    for graph, done in segments:
-      graph.replay()
-      if on_output is not None:
-        for name, index, t in done:
-          on_output(name, index, t)
+    fed = main.record_event()
+    # short chains first: their launches are in flight when the long chain starts and fill its partial waves
+    for br, stream, graph, done, _ in sorted(chains, key=lambda c: c[0][0] != "reg"):
+      stream.wait_event(fed)
+      with torch.cuda.stream(stream):
+        graph.replay()
+        if on_output is not None:
+          for name, index, t in done:
+            on_output(name, index, t)
+    for _, stream, _, _, _ in chains:
+      main.wait_stream(stream)
     return out
 
   def grid_feeds_from_traj(self, obs_traj, centers=None, video_h=1080, video_w=1920):

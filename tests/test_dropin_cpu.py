@@ -413,7 +413,7 @@ def test_tf_checkpoint_bundle_reader(dropin, tmp_path):
 
 def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   """Host logic of ConvRNNEngine.forward_graph with the CUDA pieces stubbed: a signature runs eagerly the first
-  time, is captured the second time and replayed afterwards; at most GRAPH_CACHE graphs are kept (oldest evicted);
+  time, is captured the second time (one graph per independent chain) and replayed afterwards; at most GRAPH_CACHE graphs are kept (oldest evicted);
   replacing the weights drops them all."""
   import torch
   from multiverse_b200 import engine as E
@@ -428,6 +428,8 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   class FakeStream(object):
     def __init__(self, *a, **k): pass
     def wait_stream(self, other): pass
+    def wait_event(self, ev): pass
+    def record_event(self): return object()
 
   class FakeCtx(object):
     def __init__(self, g, **kw): pass
@@ -437,15 +439,26 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
   monkeypatch.setattr(torch.cuda, "graph", FakeCtx)
   monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-  monkeypatch.setattr(torch.cuda, "graph_pool_handle", lambda: None)
   monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
   monkeypatch.setattr(torch.cuda, "stream", lambda s: FakeCtx(None))
   monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
   eng = E.ConvRNNEngine.__new__(E.ConvRNNEngine)
-  eng.cfg = types.SimpleNamespace(pred_len=12)
-  eng.device, eng.cell_events, eng._graphs, eng._graph_seen = torch.device("cpu"), None, {}, set()
+  eng.cfg = types.SimpleNamespace(pred_len=12, scene_grids=[(2, 2), (1, 1)], use_grids=[True, False])
+  eng.device, eng.cell_events, eng._graphs, eng._graph_seen, eng._bufs = torch.device("cpu"), None, {}, set(), {}
   calls = []
-  eng.forward = lambda feeds, tp, on_output=None: calls.append((tuple(feeds["obs_scene"].shape), tp)) or dict(tag=len(calls))
+
+  def fake_forward(feeds, tp, on_output=None, branches=None):
+    calls.append((tuple(feeds["obs_scene"].shape), tp, None if branches is None else tuple(branches)))
+    out = dict(grid_pred_decoded=[None, []], grid_pred_reg_decoded=[None, []], beam_outputs=None)
+    if branches is None or ("class", 0) in branches:
+      out["grid_pred_decoded"][0] = ("class", len(calls))
+      if on_output: on_output("grid_pred_decoded", 0, out["grid_pred_decoded"][0])
+    if branches is None or ("reg", 0) in branches:
+      out["grid_pred_reg_decoded"][0] = ("reg", len(calls))
+      out["_offs"] = {0: "offs"}
+      if on_output: on_output("grid_pred_reg_decoded", 0, out["grid_pred_reg_decoded"][0])
+    return out
+  eng.forward = fake_forward
 
   def feeds(n):
     return dict(scene_feat=torch.zeros(3, 4, 4, 11), obs_scene=torch.zeros(n, 8, dtype=torch.int32),
@@ -454,15 +467,20 @@ def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
 
   eng.forward_graph(feeds(2))                      # first sight: eager
   assert len(calls) == 1 and not eng._graphs and FakeGraph.replays == 0
-  out = eng.forward_graph(feeds(2))                # second sight: eager warm-up + capture, then replay
-  assert len(calls) == 3 and len(eng._graphs) == 1 and FakeGraph.replays == 1 and out["tag"] == 3
+  seen = []
+  out = eng.forward_graph(feeds(2), on_output=lambda name, i, t: seen.append(name))
+  # second sight: eager warm-up, then one capture per chain (class, regression), then one replay per chain
+  assert [c[2] for c in calls[1:]] == [None, (("class", 0),), (("reg", 0),)]
+  assert len(eng._graphs) == 1 and FakeGraph.replays == 2
+  assert out["grid_pred_decoded"] == [("class", 3), []] and out["grid_pred_reg_decoded"] == [("reg", 4), []]
+  assert out["_offs"] == {0: "offs"} and sorted(seen) == ["grid_pred_decoded", "grid_pred_reg_decoded"]
   eng.forward_graph(feeds(2)); eng.forward_graph(feeds(2), pred_len=12)
-  assert len(calls) == 3 and FakeGraph.replays == 3              # pure replays (pred_len default == 12)
+  assert len(calls) == 4 and FakeGraph.replays == 6              # pure replays (pred_len default == 12)
   eng.forward_graph(feeds(2), pred_len=17)         # another rollout length is another signature
-  assert len(calls) == 4 and len(eng._graphs) == 1
+  assert len(calls) == 5 and len(eng._graphs) == 1
   f5 = feeds(2); f5["scene_feat"] = torch.ones(5, 4, 4, 11)       # another frame count, same 64-frame bucket
   eng.forward_graph(f5)
-  assert len(calls) == 4 and FakeGraph.replays == 4
+  assert len(calls) == 5 and FakeGraph.replays == 8
   static_sf = next(iter(eng._graphs.values()))[1]["scene_feat"]
   assert static_sf.shape[0] == 64 and bool((static_sf[:5] == 1).all()) and bool((static_sf[5:] == 0).all())
   for n in range(3, 3 + eng.GRAPH_CACHE + 1):      # more signatures than the cache holds
