@@ -283,14 +283,21 @@ def run_train(args, name, ctx, steps, warmup, cpu_baseline=True):
   clocks = sampler.stop() if rank == 0 else None
   ar = None
   if ar_events:
-    # the one collective of the path (85 MB fp32 gradient bucket): device time per step, max over ranks, and the
-    # bus bandwidth 2 (G-1)/G * bytes / time (the NCCL convention; 725 GB/s measured at 1 GiB on this pool)
-    ar_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ar_events]))], device=dev, dtype=torch.float64)
-    dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
+    # the one collective of the path (85 MB fp32 gradient bucket), device time per step.  A rank that arrives early
+    # waits inside the collective for its peers (the ranks' fwd+bwd times differ by 1-2 % under the power cap), so
+    # the MAX over ranks measures skew + transfer and the MIN - the last arriver's - the transfer itself: bus
+    # bandwidth 2 (G-1)/G * bytes / min time (the NCCL convention; 725 GB/s measured at 1 GiB on this pool).
+    mine = float(np.mean([a.elapsed_time(b) for a, b in ar_events]))
+    ar_max = torch.tensor([mine], device=dev, dtype=torch.float64)
+    ar_min = torch.tensor([mine], device=dev, dtype=torch.float64)
+    dist.all_reduce(ar_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ar_min, op=dist.ReduceOp.MIN)
     nbytes = eng.flat_grad.numel() * 4
-    ar = dict(ms_per_step=float(ar_ms.item()), bytes=nbytes,
-              bus_gbs=2.0 * (world - 1) / world * nbytes / (float(ar_ms.item()) * 1e-3) / 1e9,
-              share_of_step=float(ar_ms.item()) / (ms_total / steps))
+    ar = dict(ms_per_step=float(ar_max.item()), ms_per_step_last_arriver=float(ar_min.item()), bytes=nbytes,
+              bus_gbs=2.0 * (world - 1) / world * nbytes / (float(ar_min.item()) * 1e-3) / 1e9,
+              share_of_step=float(ar_max.item()) / (ms_total / steps),
+              note="ms_per_step = max over ranks (includes waiting for the slowest rank's backward pass); "
+                   "bus_gbs from the last arriver's time")
   host_loss = torch.empty(2 * sum(cfg.use_grids), dtype=torch.float32).pin_memory()
 
   def e2e_step():

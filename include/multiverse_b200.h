@@ -278,6 +278,10 @@ int mvb_clip_update(float* w, const float* grad, float* slot1, float* slot2, int
 int mvb_adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, int64_t n,
                  void* stream);
 int mvb_mix(const float* a, const float* b, float* out, float w, int64_t n, void* stream);
+/* Per-row sparse softmax cross entropy without gradient, loss[r] = logsumexp(logits[r,:]) - logits[r, labels[r]] (NaN
+ * for a label outside [0,V), as TensorFlow): what SimAug's multi-view augmentation ranks the M views of a sample by
+ * (mean over the predicted steps, SimAug/code/pred_models.py:386-392, :413-416, :465-470).  logits fp32 [rows,V]. */
+int mvb_ce_rows(const float* logits, const int32_t* labels, float* loss, int64_t rows, int V, void* stream);
 
 /* ---- f-3: multi-future evaluation metrics on the device ------------------------------------------------------
  * minADE / minFDE of code/multifuture_eval_trajs.py:41-78 (get_min :16-21): for every trajectory n and ground-truth

@@ -109,6 +109,7 @@ int clip_update(float* w, const float* grad, float* s1, float* s2, long long n, 
 int adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, long long n,
              cudaStream_t stream);
 int mix(const float* a, const float* b, float* out, float w, long long n, cudaStream_t stream);
+int ce_rows(const float* logits, const int* labels, float* loss, long long rows, int V, cudaStream_t stream);
 int clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, long long n, float lr,
                   float rho, float eps, float clip, float wd, float gscale, cudaStream_t stream);
 

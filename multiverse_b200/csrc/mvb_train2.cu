@@ -638,6 +638,38 @@ __global__ void mix_kernel(const float* __restrict__ a, const float* __restrict_
     out[i] = a[i] * w + b[i] * (1.f - w);
 }
 
+// per-row sparse softmax cross entropy, no gradient: SimAug's multi-view selection ranks the M views of a sample by
+// the mean of these over the predicted steps (SimAug/code/pred_models.py:386-392, :413-416)
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const float* __restrict__ logits, const int* __restrict__ labels, float* __restrict__ loss, int V) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const long long r = blockIdx.x;
+  const float* lg = logits + r * V;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, lg[v]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = red[0]; for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]); bc = t; }
+  __syncthreads();
+  m = bc;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(lg[v] - m);
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) {
+    const int lab = labels[r];
+    loss[r] = (lab >= 0 && lab < V) ? logf(s) + m - lg[lab] : NAN;      // TF: NaN for an out-of-range label
+  }
+}
+int ce_rows(const float* logits, const int* labels, float* loss, long long rows, int V, cudaStream_t stream) {
+  MVB_REQUIRE(logits && labels && loss && rows > 0 && V > 0, "ce_rows: bad args");
+  ce_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(logits, labels, loss, V);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int adv_step(const float* x, const float* adv, const float* grad, float* out, float eps, float step, long long n,
              cudaStream_t stream) {
   MVB_REQUIRE(x && adv && grad && out && n > 0 && eps >= 0.f, "adv_step: bad args");

@@ -396,6 +396,15 @@ def mix(a, b, out, w):
   _lib.call("mvb_mix", _p(a), _p(b), _p(out), float(w), a.numel(), _stream())
 
 
+def ce_rows(logits, labels):
+  """Per-row sparse softmax cross entropy [rows] of logits fp32 [..., V] and labels int32 [...] (no gradient)."""
+  v = logits.shape[-1]
+  rows = logits.numel() // v
+  out = torch.empty(logits.shape[:-1], dtype=torch.float32, device=logits.device)
+  _lib.call("mvb_ce_rows", _p(logits), _p(labels), _p(out), rows, v, _stream())
+  return out
+
+
 def min_ade_fde(pred, gt, gt_len):
   """pred fp32 [N,K,Tp,2], gt fp32 [N,G,Tg,2], gt_len int32 [N,G] -> (ade_err fp64 [N,G,Tg], ade_idx int32 [N,G],
   fde fp64 [N,G], fde_idx int32 [N,G]): code/multifuture_eval_trajs.py:41-78 on the device."""

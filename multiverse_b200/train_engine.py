@@ -261,8 +261,10 @@ class TrainEngine(ConvRNNEngine):
     used = [i for i in range(len(cfg.scene_grids)) if cfg.use_grids[i]]
     loss_out = torch.zeros((len(cfg.scene_grids), 2), dtype=torch.float32, device=dev)
     dconv = [torch.zeros_like(c) for c in convs]
+    self.last_logits = {}      # scale -> class logits [Tp,N,HW] of this call's train-mode forward (engine buffers)
     for i in used:
       S = self._forward_scale(i, feeds, convs, means)
+      self.last_logits[i] = S["logits"]
       self._backward_scale(i, S, feeds, convs, means, dconv, loss_out[i],
                            cls_w * loss_scale, reg_w * loss_scale)
     # scene CNN backward: conv_k -> conv_{k-1} chain (code/pred_models.py:155-165)

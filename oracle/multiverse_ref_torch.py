@@ -148,9 +148,10 @@ def forward(cfg, weights, feeds):
           for k, v in out.items()}
 
 
-def scene_input_grad(cfg, weights, feeds, target_labels, scale_idx, dtype=torch.float64):
+def scene_input_grad(cfg, weights, feeds, target_labels, scale_idx, dtype=torch.float64, per_sample=False):
   """Truth for SimAug's attack gradient (SimAug/code/pred_models.py:96-115): d sum(sparse CE(logits, target)) /
-  d scene_feat through the train-mode forward, by torch autograd."""
+  d scene_feat through the train-mode forward, by torch autograd.  per_sample=True also returns the per-sample mean
+  over the predicted steps of that cross entropy [N] - what multiview_augmentation ranks the views by (:394-397)."""
   w = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in weights.items()}
   f = dict(feeds)
   sf = torch.from_numpy(np.ascontiguousarray(feeds["scene_feat"])).to(dtype).requires_grad_(True)
@@ -158,8 +159,11 @@ def scene_input_grad(cfg, weights, feeds, target_labels, scale_idx, dtype=torch.
   out = _forward(cfg, w, f, dtype)
   h, ww = cfg.scene_grids[scale_idx]
   logits = out["grid_pred_decoded"][scale_idx].reshape(-1, h * ww)
-  loss = F.cross_entropy(logits, torch.from_numpy(np.asarray(target_labels)).long().reshape(-1), reduction="sum")
-  loss.backward()
+  rows = F.cross_entropy(logits, torch.from_numpy(np.asarray(target_labels)).long().reshape(-1), reduction="none")
+  rows.sum().backward()
+  if per_sample:
+    n = np.asarray(target_labels).shape[0]
+    return sf.grad.numpy(), rows.detach().reshape(n, -1).mean(1).numpy()
   return sf.grad.numpy()
 
 

@@ -369,6 +369,85 @@ def test_simaug_scene_input_gradient_and_attack(dev):
   assert bool(((adv_mix - x).abs() <= 0.1 + 1e-6).all())
 
 
+@pytest.mark.parametrize("exp", [1, 4, 2, 3])
+def test_simaug_multiview_augmentation(dev, exp):
+  """Row f-4, second part: SimAug's multiview_augmentation (SimAug/code/pred_models.py:346-541) - the batch tiled over
+  M camera views, one FGSM step per view against that view's labels, views ranked by their per-sample classification
+  loss, two picked per multiview_exp and mixed - against the same pipeline written with the oracle's autograd
+  gradient and per-sample losses."""
+  from types import SimpleNamespace
+  from multiverse_b200 import simaug, synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  from oracle import multiverse_ref as R
+  from oracle import multiverse_ref_torch as RT
+  n, m = 2, 3
+  over = dict(use_grids=[False, True])
+  cfg = synthetic.make_config(batch_size=n, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+                              clip_gradient_norm=10.0, **over)
+  w = synthetic.make_weights(cfg, 41); f = synthetic.make_feeds(cfg, n, 41, with_pred=True)
+  rng = np.random.default_rng(9)
+  f["scene_feat"] = np.clip(f["scene_feat"] * 0.8 + rng.uniform(-0.1, 0.1, f["scene_feat"].shape), -1, 1).astype(np.float32)
+  t_obs, tp, hw = cfg.obs_len, cfg.pred_len, 18 * 9
+  extra_labels = rng.integers(0, hw, size=(n, m, tp)).astype(np.int32)
+  extra_scene = rng.integers(0, f["scene_feat"].shape[0], size=(n, m, t_obs)).astype(np.int32)
+  eng = TrainEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  feeds = {k: ([T(a, dev) for a in v] if isinstance(v, list) else T(v, dev)) for k, v in f.items() if not k.startswith("traj")}
+  feeds["grid_pred_labels_extra"] = [None, extra_labels]
+  feeds["obs_scene_extra"] = extra_scene
+  eps = 0.1
+  acfg = SimpleNamespace(use_grids=[False, True], scene_grids=cfg.scene_grids, adv_epsilon=eps,
+                         adv_start_from_clean_prob=1.0, multiview_max_num=m, multiview_exp=exp,
+                         multiview_use_adv_for_loss=False, multiview_random=False, fl_gamma=2.0, mixup_alpha=1.0,
+                         multiview_max_weight_for_first=True)
+  out, info = simaug.multiview_augmentation(eng, feeds, acfg, np.random.default_rng(17))
+  # ---- the same pipeline on the oracle: tiled feeds, autograd gradient, per-sample losses
+  tile = lambda a: np.repeat(np.asarray(a), m, axis=0)
+  clean = f["scene_feat"][f["obs_scene"]]                                   # [N,T,SH,SW,SC]
+  tf = dict(scene_feat=tile(clean).reshape((n * m * t_obs,) + clean.shape[2:]),
+            obs_scene=np.arange(n * m * t_obs, dtype=np.int32).reshape(n * m, t_obs))
+  for key in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
+    tf[key] = [None if a is None else tile(a) for a in f[key]]
+  target = extra_labels.reshape(n * m, tp)
+  rcfg = R.default_config(batch_size=n * m, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, **over)
+  g_ref, loss_ref = RT.scene_input_grad(rcfg, w, tf, target, 1, per_sample=True)
+  loss_ref = loss_ref.reshape(n, m)
+  got_loss = info["adv_loss"].cpu().numpy()
+  assert np.abs(got_loss - loss_ref).max() / np.abs(loss_ref).max() < 1e-4
+  order_ref = np.argsort(-loss_ref, axis=1, kind="stable")
+  gaps = np.abs(np.diff(np.sort(loss_ref, axis=1), axis=1)).min()
+  assert gaps > 1e-3, "degenerate test data: view losses too close to rank"
+  assert np.array_equal(info["loss_indices"].cpu().numpy(), order_ref)
+  x = tf["scene_feat"].astype(np.float32)
+  lo, hi = np.clip(x - np.float32(eps), -1, 1), np.clip(x + np.float32(eps), -1, 1)
+  adv_ref = np.minimum(np.maximum(x - np.float32(eps) * np.sign(g_ref).astype(np.float32), lo), hi)
+  adv_ref = adv_ref.reshape((n, m, t_obs) + clean.shape[2:])
+  rows = np.arange(n)
+  r2 = np.random.default_rng(17)
+  if exp == 1:
+    f1, f2 = adv_ref[rows, order_ref[:, 0]], adv_ref[rows, order_ref[:, 1]]
+  elif exp == 4:
+    f1, f2 = adv_ref[rows, order_ref[:, m - 1]], adv_ref[rows, order_ref[:, m - 2]]
+  elif exp == 2:
+    a = r2.integers(0, m, size=n); b = (a + r2.integers(1, m, size=n)) % m
+    assert (a != b).all()
+    f1, f2 = adv_ref[rows, a], adv_ref[rows, b]
+  else:
+    f1 = adv_ref[rows, order_ref[:, 0]]
+    f2 = f["scene_feat"][extra_scene[rows, order_ref[:, 0]]]
+    assert np.array_equal(info["selected_extra_indices"].cpu().numpy(), order_ref[:, 0])
+    fl = (1.0 - np.exp(-np.sort(loss_ref, axis=1)[:, -1])) ** 2.0
+    assert np.abs(info["focal_loss_weight"].cpu().numpy() - fl).max() < 1e-4
+  wgt = r2.beta(1.0, 1.0); wgt = max(wgt, 1.0 - wgt)
+  assert abs(info["beta_weight"] - wgt) < 1e-12 and wgt >= 0.5
+  want = (f1 * np.float32(wgt) + f2 * (np.float32(1.0) - np.float32(wgt))).reshape((n * t_obs,) + clean.shape[2:])
+  got = out.cpu().numpy()
+  assert got.shape == want.shape
+  # the sign of a gradient entry that is ~0 next to the others may differ between fp32 BPTT and fp64 autograd
+  close = np.abs(got - want) <= 1e-6
+  print("multiview exp %d: %.5f of the pixels equal, max diff %.3g" % (exp, close.mean(), np.abs(got - want).max()))
+  assert close.mean() > 0.999 and np.abs(got - want).max() <= 2 * eps + 1e-6
+
+
 @pytest.mark.parametrize("opt", ["momentum", "adam", "rmsprop"])
 def test_other_optimizers_match_tf_semantics(dev, opt):
   """Trainer's non-default optimizers (code/pred_models.py:1667-1681) - MomentumOptimizer(lr, 0.9), AdamOptimizer(lr),
