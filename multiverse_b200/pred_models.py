@@ -110,6 +110,13 @@ class Model(object):
     # bus instead of 41 KB per trajectory and scale.  get_feed_dict uses them when the batch carries both.
     self.obs_traj = ph("obs_traj")
     self.grid_centers = [ph("grid_centers", i) for i, _ in enumerate(config.scene_grids)]
+    # SimAug's Model (SimAug/code/pred_models.py:225-267): the other camera views of every sample
+    if getattr(config, "multiview_train", False):
+      self.obs_scene_extra = ph("obs_scene_extra")
+      self.grid_obs_labels_extra = [ph("grid_obs_labels_extra", i) for i, _ in enumerate(config.scene_grids)]
+      self.grid_pred_labels_T_extra = [ph("grid_pred_labels_T_extra", i) for i, _ in enumerate(config.scene_grids)]
+      self.grid_pred_regress_extra = [ph("grid_pred_regress_extra", i) for i, _ in enumerate(config.scene_grids)]
+      self.grid_obs_regress_extra = [ph("grid_obs_regress_extra", i) for i, _ in enumerate(config.scene_grids)]
     self.beam_outputs = None
     self.loss = None
     self.build_forward()
@@ -237,6 +244,27 @@ class Model(object):
     fd[self.obs_scene] = obs_scene
     fd[self.obs_scene_mask] = mask
     fd[self.scene_feat] = data["batch_scene_feat"]
+    if is_train and getattr(cfg, "multiview_train", False):
+      # SimAug/code/pred_models.py:1517-1541, :1553-1555: the M other camera views of every sample
+      M = cfg.multiview_max_num
+      for j, (h, w) in enumerate(cfg.scene_grids):
+        if not cfg.use_grids[j]:
+          continue
+        obs_lab = np.zeros((N, M, T_in), dtype="int32")
+        pred_lab = np.zeros((N, M, T_pred), dtype="float32")
+        obs_reg = np.zeros((N, M, T_in, h, w, 2), dtype="float32")
+        pred_reg = np.zeros((N, M, T_pred, h, w, 2), dtype="float32")
+        for i, ex in enumerate(data["extra"]):
+          for k in range(len(ex["obs_grid_class"])):
+            obs_lab[i, k] = np.asarray(ex["obs_grid_class"][k])[j, :]
+            pred_lab[i, k] = np.asarray(ex["pred_grid_class"][k])[j, :]
+            obs_reg[i, k] = ex["obs_grid_target_all_%d" % j][k]
+            pred_reg[i, k] = ex["pred_grid_target_all_%d" % j][k]
+        fd[self.grid_obs_labels_extra[j]] = obs_lab
+        fd[self.grid_pred_labels_T_extra[j]] = pred_lab
+        fd[self.grid_pred_regress_extra[j]] = pred_reg
+        fd[self.grid_obs_regress_extra[j]] = obs_reg
+      fd[self.obs_scene_extra] = np.squeeze(data["batch_extra_obs_scene"])
     self._compact_grid_feeds(fd, batch, n_have, is_train)
     return fd
 
@@ -310,7 +338,10 @@ class Model(object):
     dev = eng.device
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=True)
     cfg = self.config
-    out = dict(scene_feat=up(feed[self.scene_feat], np.float32),
+    scene = up(feed[self.scene_feat], np.float32)
+    if getattr(cfg, "norm_input", False):      # SimAug/code/pred_models.py:282-284: features to [-1, 1]
+      scene = scene * 2.0 - 1.0
+    out = dict(scene_feat=scene,
                obs_scene=up(feed[self.obs_scene], np.int32),
                grid_obs_labels=[None] * len(cfg.scene_grids),
                grid_obs_regress=[None] * len(cfg.scene_grids))
@@ -476,6 +507,7 @@ class Model(object):
       if cfg.use_grids[i]:
         feeds["grid_pred_labels"][i] = up(feed[self.grid_pred_labels_T[i]], np.int32)
         feeds["grid_pred_regress"][i] = up(feed[self.grid_pred_regress[i]], np.float32)
+    feeds = self._simaug_feeds(eng, feeds, feed)
     step = int(self.global_step.value)
     if apply:
       # under torchrun (an initialised NCCL process group) the drop-in train.py is data parallel: every rank feeds its
@@ -496,6 +528,51 @@ class Model(object):
       cls[i], reg[i] = losses[2 * j], losses[2 * j + 1]
     return dict(loss=np.float32(losses.sum() + wd), wd_loss=np.float32(wd), train_op=None,
                 classification_loss=cls, regression_loss=reg)
+
+  def _simaug_feeds(self, eng, feeds, feed):
+    """The training-time input augmentations of SimAug's Model (SimAug/code/pred_models.py:286-325), applied to the
+    scene semantics before the training tower runs: `adv_train` (white_box_attack, :289-301), `multiview_train`
+    (multiview_augmentation, :304-310) and `standard_aug` (uniform pixel jitter, :312-325).  Like the reference they
+    work on one private frame per (sample, step) row: the batch's unique frames are expanded first."""
+    import torch
+    cfg = self.config
+    adv = getattr(cfg, "adv_train", False)
+    multi = getattr(cfg, "multiview_train", False)
+    jitter = getattr(cfg, "standard_aug", False)
+    if not (adv or multi or jitter):
+      return feeds
+    from . import simaug
+    if getattr(self, "_aug_rng", None) is None:
+      self._aug_rng = np.random.default_rng(getattr(cfg, "seed", None))
+    dev = eng.device
+    n, t_obs = feeds["obs_scene"].shape
+    rows = dict(feeds)
+    rows["scene_feat"] = feeds["scene_feat"].float()[feeds["obs_scene"].long()].reshape(
+        (n * t_obs,) + tuple(feeds["scene_feat"].shape[1:])).contiguous()
+    rows["obs_scene"] = torch.arange(n * t_obs, device=dev, dtype=torch.int32).reshape(n, t_obs)
+    if adv or multi:
+      assert sum(cfg.use_grids) == 1, "only one scale for adv / multiview train"        # :290, :305
+      i = list(cfg.use_grids).index(True)
+    if adv:
+      label = np.asarray(feed[self.grid_pred_labels_T[i]]).astype(np.int64)
+      rows["scene_feat"], _ = simaug.white_box_attack(eng, rows, label, cfg, self._aug_rng,
+                                                      norm_feat=getattr(cfg, "norm_feat", False))
+    elif multi:
+      if int(cfg.multiview_exp) == 3:
+        raise NotImplementedError("multiview_exp 3 also mixes the observed grid classes and the loss labels of two "
+                                  "views (SimAug/code/pred_models.py:616-635, :1371-1405): not built; the "
+                                  "augmentation itself is simaug.multiview_augmentation")
+      src = dict(feeds)       # the unique frames: obs_scene_extra indexes them
+      src["grid_pred_labels_extra"] = [None if not cfg.use_grids[j] else
+                                       np.asarray(feed[self.grid_pred_labels_T_extra[j]]).astype(np.int32)
+                                       for j in range(len(cfg.scene_grids))]
+      src["obs_scene_extra"] = np.asarray(feed[self.obs_scene_extra]).astype(np.int32)
+      rows["scene_feat"], self.multiview_info = simaug.multiview_augmentation(eng, src, cfg, self._aug_rng)
+    if jitter:
+      eps = float(cfg.adv_epsilon)
+      noise = self._aug_rng.uniform(-eps, eps, size=tuple(rows["scene_feat"].shape)).astype(np.float32)
+      rows["scene_feat"] = rows["scene_feat"] + torch.from_numpy(noise).to(dev)
+    return rows
 
   # ---------------------------------------------------------------- unit-test surface
   def enc_cell(self, x, state, scale=0, kind="class"):

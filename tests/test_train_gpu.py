@@ -369,6 +369,81 @@ def test_simaug_scene_input_gradient_and_attack(dev):
   assert bool(((adv_mix - x).abs() <= 0.1 + 1e-6).all())
 
 
+@pytest.mark.parametrize("mode", ["adv_train", "multiview_train", "standard_aug"])
+def test_simaug_training_variants_through_the_dropin_trainer(dev, monkeypatch, mode):
+  """SimAug's training-time augmentations behind the reference-facing surface (SimAug/code/pred_models.py:286-325,
+  feeds :1517-1555): Trainer.step on a Model whose config switches adv_train / multiview_train / standard_aug on.
+  With epsilon = 0 every augmentation is the identity, so the step must reproduce the plain step's losses; with
+  epsilon > 0 the losses change, stay finite and the variables move."""
+  import sys, types
+  from multiverse_b200 import synthetic
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "multiverse_b200", "dropin"))
+  n, m = 2, 3
+  over = dict(batch_size=n, use_grids=[False, True])
+  cfg = synthetic.make_config(is_train=True, grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+                              clip_gradient_norm=10.0, **over)
+  w = synthetic.make_weights(cfg, 6); f = synthetic.make_feeds(cfg, n, 6, with_pred=True)
+  rng = np.random.default_rng(2)
+  ns = 2
+  data = dict(obs_grid_class=[np.stack([f["grid_obs_labels"][j][i] for j in range(ns)]) for i in range(n)],
+              pred_grid_class=[np.stack([f["grid_pred_labels"][j][i] for j in range(ns)]) for i in range(n)],
+              batch_scene_feat=f["scene_feat"], batch_obs_scene=f["obs_scene"][:, :, None])
+  for j in range(ns):
+    data["obs_grid_target_all_%d" % j] = list(f["grid_obs_regress"][j])
+    data["pred_grid_target_all_%d" % j] = list(f["grid_pred_regress"][j])
+  # the other camera views: same geometry, labels of their own, frames drawn from the batch's frame set
+  data["extra"] = []
+  for i in range(n):
+    ex = dict(obs_grid_class=[], pred_grid_class=[])
+    for j, (h, ww) in enumerate(cfg.scene_grids):
+      ex["obs_grid_target_all_%d" % j] = [f["grid_obs_regress"][j][i]] * m
+      ex["pred_grid_target_all_%d" % j] = [f["grid_pred_regress"][j][i]] * m
+    for k in range(m):
+      ex["obs_grid_class"].append(np.stack([rng.integers(0, h * ww, cfg.obs_len) for (h, ww) in cfg.scene_grids]))
+      ex["pred_grid_class"].append(np.stack([rng.integers(0, h * ww, cfg.pred_len) for (h, ww) in cfg.scene_grids]))
+    data["extra"].append(ex)
+  data["batch_extra_obs_scene"] = rng.integers(0, f["scene_feat"].shape[0], size=(n, m, cfg.obs_len, 1))
+  batch = (tuple(range(n)), types.SimpleNamespace(data=data))
+
+  def run(eps, **flags):
+    for mod in ("tensorflow", "pred_models", "multiverse_b200.pred_models"):
+      sys.modules.pop(mod, None)
+    import tensorflow as tf
+    import pred_models
+    tf.reset_default_graph()
+    args = types.SimpleNamespace(**vars(cfg))
+    args.modelname = "m"; args.use_soft_grid_class = False; args.use_gt_grid = False; args.train_w_onehot = True
+    args.optimizer = "adadelta"; args.init_lr = 0.2; args.emb_lr = 1.0; args.learning_rate_decay = 0.95
+    args.num_epoch_per_decay = 2.0; args.train_num_examples = 100; args.use_cosine_lr = False
+    args.mask_grid_regression = False
+    args.adv_epsilon, args.adv_step_size, args.adv_num_iter, args.adv_use_fgsm = eps, eps / 4, 2, True
+    args.adv_start_from_clean_prob, args.use_mixup, args.mixup_alpha, args.norm_feat = 0.0, False, 1.0, False
+    args.multiview_max_num, args.multiview_exp, args.multiview_max_weight_for_first, args.seed = m, 1, True, 11
+    for k, v in flags.items():
+      setattr(args, k, v)
+    model = pred_models.get_model(args, gpuid=0)
+    tf.global_variables_initializer().run()
+    for v in tf.global_variables():
+      if v.name.split(":")[0] in w:
+        v.assign(w[v.name.split(":")[0]])
+    with tf.Session() as sess:
+      trainer = pred_models.Trainer(model, args)
+      loss, _, wd_loss, pgl = trainer.step(sess, batch)
+      k = "person_pred/decoder_grid_class_1/decoder_rnn/dec_grid_1/kernel"
+      new = [v for v in tf.global_variables() if v.name == k + ":0"][0].eval()
+    return float(loss), np.array(pgl, dtype=np.float64), new
+
+  plain = run(0.0)
+  same = run(0.0, **{mode: True})
+  assert abs(same[0] - plain[0]) < 1e-6 * abs(plain[0]) and np.allclose(same[1], plain[1], rtol=1e-6)
+  aug = run(0.1, **{mode: True})
+  assert np.isfinite(aug[0]) and np.isfinite(aug[1]).all() and abs(aug[0] - plain[0]) > 1e-6
+  assert np.abs(aug[2] - w["person_pred/decoder_grid_class_1/decoder_rnn/dec_grid_1/kernel"]).max() > 0
+  if mode == "multiview_train":
+    with pytest.raises(NotImplementedError):
+      run(0.1, multiview_train=True, multiview_exp=3)
+
+
 @pytest.mark.parametrize("exp", [1, 4, 2, 3])
 def test_simaug_multiview_augmentation(dev, exp):
   """Row f-4, second part: SimAug's multiview_augmentation (SimAug/code/pred_models.py:346-541) - the batch tiled over
