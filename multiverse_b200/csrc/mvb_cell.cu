@@ -713,9 +713,22 @@ static void note_variant(int planes, int pair) {
 
 struct CellMaps { CUtensorMap A, B, Bh, A8, B8, B8h; };
 
+// Work order of a launch (CellParams::order, work_index()).  1: the four N tiles of an M tile (pair) run back to back
+// on the same CTA (pair) - measured on the K=20 beam step: DRAM reads 1.05x algorithmic instead of 1.39x, 3 % faster.
+// 0: work items strided over the CTAs.  A launch of few M tiles (the encoders and the greedy decoders of a small
+// shard: 32 trajectories of 36x18 = 176 M tiles on 148 CTAs) is bound by its longest CTA instead: back to back the
+// busiest CTA runs 2 x 4 items, strided ceil(704 / 148) = 5.  Strided whenever that makespan is shorter and the
+// launch is small enough for its operands to stay in L2.
+static int pick_order(int forced, long long units, long long ctas) {
+  if (forced == 0 || forced == 1) return forced;
+  const long long back_to_back = ((units + ctas - 1) / ctas) * N_TILES, strided = (units * N_TILES + ctas - 1) / ctas;
+  return (strided < back_to_back && units < 4 * ctas) ? 0 : 1;
+}
+
 template <int P, int FMT>
-static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, bool multicast, cudaStream_t stream) {
+static int launch_cell(const CellMaps& tm, const CellParams& prm_in, int num_sms, bool multicast, cudaStream_t stream) {
   using Cfg = CellCfg<P>;
+  CellParams prm = prm_in;
   static SmemOptIn opt_plain, opt_mc;
   const int ra8 = (BLOCK_M + 2 * (prm.W + 2) + 7) & ~7;
   const int smem_bytes = Cfg::smem_bytes(ra8);
@@ -728,6 +741,7 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
   static const int pair_mode = [] { const char* e = getenv("MVB_CELL_PAIR"); return e ? atoi(e) : 2; }();
   const long long m_tiles = (prm.R + BLOCK_M - 1) / BLOCK_M;
   if (multicast && m_tiles >= 2 * (long long)num_sms) {
+    prm.order = pick_order(prm_in.order, (m_tiles + 1) / 2, num_sms / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(num_sms / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
@@ -743,6 +757,7 @@ static int launch_cell(const CellMaps& tm, const CellParams& prm, int num_sms, b
   }
   const long long num_tiles = m_tiles * N_TILES;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  prm.order = pick_order(prm_in.order, m_tiles, grid);
   cell_fwd_kernel<P, 0, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm.A, tm.B, tm.A8, tm.B8, prm);
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
@@ -810,9 +825,8 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   prm.preact_out = fanout > 1 ? gates_out : nullptr;      // fan-out: stage 1 stores the raw accumulators there
   prm.xf_B = xf_B; prm.xf_T2 = xf_T2; prm.xf_ids = xf_ids;
   prm.skip_x = 0;
-  // measured on the K=20 beam step: order 1 keeps the DRAM reads at 1.05x algorithmic with the CTA-pair clusters
-  // (order 0: 1.39x) and is 3 % faster; MVB_CELL_ORDER=0 selects the strided order for A/B runs.
-  static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : 1; }();
+  // work order: chosen per launch in launch_cell (MVB_CELL_ORDER=0|1 forces one)
+  static const int order = [] { const char* e = getenv("MVB_CELL_ORDER"); return e ? atoi(e) : -1; }();
   prm.order = order;
   static const int abl = [] { const char* e = getenv("MVB_CELL_ABL"); return e ? atoi(e) : 0; }();
   prm.abl = (abl & 16) ? (abl | 8) : abl;      // "load nothing" without "do not wait for data" would hang the issuer
