@@ -21,23 +21,6 @@ namespace mvb {
 
 constexpr int GNN_WARPS = 4;
 
-// Packed fp32 pairs: sm_100 issues two FMAs per lane from one instruction (SASS FFMA2).  The kernel is bound by
-// instruction issue, not by the FMA pipe, so every dot product, norm and weighted sum below works on float2.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-
 struct GnnCol {         // one window column: rows y-1, y, y+1
   float2 h[3][4];
   float2 s[3];
@@ -331,6 +314,8 @@ gnn_rows_kernel(const float* __restrict__ h32, const int* __restrict__ row_map,
       float d[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) d[k] = acc[k].x + acc[k].y;
+      // (a transposed reduction - 11 shuffles instead of 40, every lane storing its own sum - was measured and is no
+      // faster: the kernel is not bound by these instructions)
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll

@@ -103,43 +103,57 @@ head_kernel(const float* __restrict__ h32, const float* __restrict__ Wo, float* 
 
   // phase 1: per-pixel, per-tap partial dot products.  The class head (POUT == 1) keeps its 72
   // weights in registers; the 2-output head reads them as 128-bit shared-memory words.
-  float wr[POUT == 1 ? 9 : 1][8];
+  // (packed fp32 pairs: one FFMA2 per two channels - the loop is bound by instruction issue, not by the FMA pipe)
+  float2 wr[POUT == 1 ? 9 : 1][4];
   if (POUT == 1) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 a = *reinterpret_cast<const float4*>(w_s + t * kHidden + lane * 8);
       const float4 b = *reinterpret_cast<const float4*>(w_s + t * kHidden + lane * 8 + 4);
-      wr[t][0] = a.x; wr[t][1] = a.y; wr[t][2] = a.z; wr[t][3] = a.w;
-      wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
+      wr[t][0] = make_float2(a.x, a.y); wr[t][1] = make_float2(a.z, a.w);
+      wr[t][2] = make_float2(b.x, b.y); wr[t][3] = make_float2(b.z, b.w);
     }
   }
-  // the row of the next iteration is requested before the current one is consumed (load latency, not bandwidth,
-  // bounds this loop)
-  auto row_ptr = [&](int q) {
-    return reinterpret_cast<const float4*>(h32 + (s * g.S + (long long)(q / g.W) * g.Wp + q % g.W) * kHidden + lane * 8);
+  // the rows of the next TWO iterations are requested before the current one is consumed (load latency, not
+  // bandwidth, bounds this loop)
+  // (the pixel coordinates of the prefetched row advance incrementally: no division per iteration)
+  constexpr int STEP = HEAD_THREADS / 32;
+  const float* hbase = h32 + s * g.S * kHidden + lane * 8;
+  int py = warp / g.W, px = warp % g.W;          // pixel of the row requested next
+  auto fetch = [&](float4& lo, float4& hi) {
+    const float4* p4 = reinterpret_cast<const float4*>(hbase + ((long long)py * g.Wp + px) * kHidden);
+    lo = __ldg(p4); hi = __ldg(p4 + 1);
+    px += STEP;
+    while (px >= g.W) { px -= g.W; ++py; }
   };
-  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-  if (warp < hw) { na = __ldg(row_ptr(warp)); nb = __ldg(row_ptr(warp) + 1); }
-  for (int q = warp; q < hw; q += HEAD_THREADS / 32) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 na = z4, nb = z4, ma = z4, mb = z4;
+  if (warp < hw) fetch(na, nb);
+  if (warp + STEP < hw) fetch(ma, mb);
+  for (int q = warp; q < hw; q += STEP) {
     const float4 a = na, b = nb;
-    if (q + HEAD_THREADS / 32 < hw) { na = __ldg(row_ptr(q + HEAD_THREADS / 32)); nb = __ldg(row_ptr(q + HEAD_THREADS / 32) + 1); }
-    const float hv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    na = ma; nb = mb;
+    if (q + 2 * STEP < hw) fetch(ma, mb);
+    const float2 hv[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
     float part[9 * POUT];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
 #pragma unroll
       for (int po = 0; po < POUT; ++po) {
-        float acc = 0.f;
+        float2 acc;
         if (POUT == 1) {
+          acc = fmul2(hv[0], wr[t][0]);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc = fmaf(hv[c], wr[t][c], acc);
+          for (int c = 1; c < 4; ++c) acc = ffma2(hv[c], wr[t][c], acc);
         } else {
           const float4 wa = *reinterpret_cast<const float4*>(w_s + (t * POUT + po) * kHidden + lane * 8);
           const float4 wb = *reinterpret_cast<const float4*>(w_s + (t * POUT + po) * kHidden + lane * 8 + 4);
-          acc = fmaf(hv[0], wa.x, acc); acc = fmaf(hv[1], wa.y, acc); acc = fmaf(hv[2], wa.z, acc); acc = fmaf(hv[3], wa.w, acc);
-          acc = fmaf(hv[4], wb.x, acc); acc = fmaf(hv[5], wb.y, acc); acc = fmaf(hv[6], wb.z, acc); acc = fmaf(hv[7], wb.w, acc);
+          acc = fmul2(hv[0], make_float2(wa.x, wa.y));
+          acc = ffma2(hv[1], make_float2(wa.z, wa.w), acc);
+          acc = ffma2(hv[2], make_float2(wb.x, wb.y), acc);
+          acc = ffma2(hv[3], make_float2(wb.z, wb.w), acc);
         }
-        part[t * POUT + po] = acc;
+        part[t * POUT + po] = acc.x + acc.y;
       }
     }
     // warp totals: groups of 8 values by the folding reduction (9 shuffles per 8 values), the rest by butterflies
