@@ -282,6 +282,16 @@ int mvb_mix(const float* a, const float* b, float* out, float w, int64_t n, void
  * for a label outside [0,V), as TensorFlow): what SimAug's multi-view augmentation ranks the M views of a sample by
  * (mean over the predicted steps, SimAug/code/pred_models.py:386-392, :413-416, :465-470).  logits fp32 [rows,V]. */
 int mvb_ce_rows(const float* logits, const int32_t* labels, float* loss, int64_t rows, int V, void* stream);
+/* multiview_exp 3 (SimAug/code/pred_models.py:616-638): the class encoder's input with the observed grid class mixed
+ * from two views, scene_conv (.) (beta * one_hot(label) + one_hot(label2) * (1 - beta)): two weighted feature pixels
+ * per sample row (one, weighted beta + (1 - beta) in fp32, when the labels coincide) into an x block that is zero on
+ * entry; and its backward (x-block gradient -> d scene_conv, atomically added).  Shapes as mvb_enc_class_input. */
+int mvb_enc_class_input_mix(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                            const int32_t* label2, float beta, void* xh_planes, int64_t plane_stride, int cpad,
+                            int64_t NS, int H, int W, int planes, void* stream);
+int mvb_enc_class_input_mix_bwd(const float* dxh, int cpad, const int32_t* frame_idx, const int32_t* label,
+                                const int32_t* label2, float beta, float* dscene, int64_t NS, int H, int W,
+                                void* stream);
 
 /* ---- f-3: multi-future evaluation metrics on the device ------------------------------------------------------
  * minADE / minFDE of code/multifuture_eval_trajs.py:41-78 (get_min :16-21): for every trajectory n and ground-truth

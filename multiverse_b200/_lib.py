@@ -64,6 +64,8 @@ SIGNATURES = {
     "mvb_clip_update": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _f, _f, _f, _f, _f, _vp],
     "mvb_adv_step": [_vp, _vp, _vp, _vp, _f, _f, _i64, _vp],
     "mvb_ce_rows": [_vp, _vp, _vp, _i64, _i, _vp],
+    "mvb_enc_class_input_mix": [_vp, _vp, _vp, _vp, _f, _vp, _i64, _i, _i64, _i, _i, _i, _vp],
+    "mvb_enc_class_input_mix_bwd": [_vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _i, _i, _vp],
     "mvb_mix": [_vp, _vp, _vp, _f, _i64, _vp],
     "mvb_min_ade_fde": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "mvb_beam_nll": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],

@@ -112,7 +112,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 8; }
+int mvb_abi_version(void) { return 9; }
 int mvb_cell_last_variant(void) { return cell_last_variant(); }
 long long mvb_cell_variants_seen(int reset) { return (long long)cell_variants_seen(reset); }
 long long mvb_launch_count(void) { return g_launches; }
@@ -324,6 +324,17 @@ int mvb_mix(const float* a, const float* b, float* out, float w, int64_t n, void
 }
 int mvb_ce_rows(const float* logits, const int32_t* labels, float* loss, int64_t rows, int V, void* stream) {
   return ce_rows(logits, labels, loss, rows, V, S(stream));
+}
+int mvb_enc_class_input_mix(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                            const int32_t* label2, float beta, void* xh_planes, int64_t plane_stride, int cpad,
+                            int64_t NS, int H, int W, int planes, void* stream) {
+  return enc_class_input_mix(scene_conv, frame_idx, label, label2, beta, xh_planes, plane_stride, cpad, NS, H, W,
+                             planes, S(stream));
+}
+int mvb_enc_class_input_mix_bwd(const float* dxh, int cpad, const int32_t* frame_idx, const int32_t* label,
+                                const int32_t* label2, float beta, float* dscene, int64_t NS, int H, int W,
+                                void* stream) {
+  return enc_class_input_mix_bwd(dxh, cpad, frame_idx, label, label2, beta, dscene, NS, H, W, S(stream));
 }
 int mvb_min_ade_fde(const float* pred, const float* gt, const int32_t* gt_len, double* ade_err, int32_t* ade_idx,
                     double* fde, int32_t* fde_idx, int64_t N, int G, int K, int Tp, int Tg, void* stream) {

@@ -110,6 +110,11 @@ int adv_step(const float* x, const float* adv, const float* grad, float* out, fl
              cudaStream_t stream);
 int mix(const float* a, const float* b, float* out, float w, long long n, cudaStream_t stream);
 int ce_rows(const float* logits, const int* labels, float* loss, long long rows, int V, cudaStream_t stream);
+int enc_class_input_mix(const float* scene_conv, const int* frame_idx, const int* label, const int* label2, float beta,
+                        void* xh_planes, long long plane_stride, int cpad, long long NS, int H, int W, int P,
+                        cudaStream_t stream);
+int enc_class_input_mix_bwd(const float* dxh, int cpad, const int* frame_idx, const int* label, const int* label2,
+                            float beta, float* dscene, long long NS, int H, int W, cudaStream_t stream);
 int clip_adadelta(float* w, const float* grad, float* acc, float* acc_upd, long long n, float lr,
                   float rho, float eps, float clip, float wd, float gscale, cudaStream_t stream);
 

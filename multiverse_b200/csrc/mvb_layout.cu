@@ -106,6 +106,54 @@ __global__ void enc_class_input_kernel(const float* __restrict__ scene_conv,
   }
 }
 
+// SimAug multiview_exp 3 (SimAug/code/pred_models.py:616-638): the observed grid class is a mix of two one-hot maps,
+// beta * one_hot(label) + one_hot(label2) * (1 - beta), so two pixels of the x block carry scene features (one, with the
+// fp32 sum of the two weights, when both labels name the same cell).  The x block must be zero on entry.
+template <int P>
+__global__ void enc_class_input_mix_kernel(const float* __restrict__ scene_conv, const int* __restrict__ frame_idx,
+                                           const int* __restrict__ label, const int* __restrict__ label2, float beta,
+                                           __nv_bfloat16* __restrict__ xh, long long plane_stride, int cpad, Grid g) {
+  const long long s = blockIdx.x;
+  const int c = threadIdx.x;  // 0..63
+  const int hw = g.H * g.W;
+  const int l1 = label[s], l2 = label2[s];
+  const float w1 = beta, w2 = 1.0f - beta;
+  auto put = [&](int lb, float wgt) {
+    if (lb < 0 || lb >= hw) return;
+    const long long row = s * g.S + (long long)(lb / g.W) * g.Wp + (lb % g.W);
+    const float v = scene_conv[((long long)frame_idx[s] * hw + lb) * 64 + c] * wgt;
+    if (P == kPlanesF16F8) { store_f16f8(xh, plane_stride, row, c, cpad, v); return; }
+    __nv_bfloat16 pl[P];
+    split_planes<P>(v, pl);
+#pragma unroll
+    for (int p = 0; p < P; ++p) xh[p * plane_stride + row * cpad + c] = pl[p];
+  };
+  if (l1 == l2) {
+    put(l1, w1 + w2);
+  } else {
+    put(l1, w1);
+    put(l2, w2);
+  }
+}
+
+int enc_class_input_mix(const float* scene_conv, const int* frame_idx, const int* label, const int* label2, float beta,
+                        void* xh_planes, long long plane_stride, int cpad, long long NS, int H, int W, int P,
+                        cudaStream_t stream) {
+  MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "enc_class_input_mix: planes P=%d", P);
+  MVB_REQUIRE(scene_conv && frame_idx && label && label2 && xh_planes && NS > 0, "enc_class_input_mix: bad args");
+  const Grid g = make_grid(H, W);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(xh_planes);
+  switch (P) {
+    case 1: enc_class_input_mix_kernel<1><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, label2, beta, d, plane_stride, cpad, g); break;
+    case 2: enc_class_input_mix_kernel<2><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, label2, beta, d, plane_stride, cpad, g); break;
+    case kPlanesF16F8: enc_class_input_mix_kernel<kPlanesF16F8><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, label2, beta, d, plane_stride, cpad, g); break;
+    default: enc_class_input_mix_kernel<3><<<(unsigned)NS, 64, 0, stream>>>(scene_conv, frame_idx, label, label2, beta, d, plane_stride, cpad, g); break;
+  }
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int nhwc_to_planes(const float* src, void* dst_planes, long long plane_stride, int cpad, int ch_off,
                    long long NS, int H, int W, int C, int P, int comp, cudaStream_t stream) {
   MVB_REQUIRE((P >= 1 && P <= 3) || P == kPlanesF16F8, "nhwc_to_planes: planes P=%d", P);

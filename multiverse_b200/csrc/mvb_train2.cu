@@ -454,6 +454,28 @@ __global__ void enc_class_input_bwd_kernel(const float* __restrict__ dxh, int cp
   atomicAdd(dscene + ((long long)frame_idx[s] * hw + lb) * 64 + c, dxh[row * cpad + c]);
 }
 
+// backward of enc_class_input_mix: the x-block gradient of the two weighted pixels goes to the scene features
+__global__ void enc_class_input_mix_bwd_kernel(const float* __restrict__ dxh, int cpad, const int* __restrict__ frame_idx,
+                                               const int* __restrict__ label, const int* __restrict__ label2, float beta,
+                                               float* __restrict__ dscene, Grid g) {
+  const long long s = blockIdx.x;
+  const int c = threadIdx.x;
+  const int hw = g.H * g.W;
+  const int l1 = label[s], l2 = label2[s];
+  const float w1 = beta, w2 = 1.0f - beta;
+  auto add = [&](int lb, float wgt) {
+    if (lb < 0 || lb >= hw) return;
+    const long long row = s * g.S + (long long)(lb / g.W) * g.Wp + (lb % g.W);
+    atomicAdd(dscene + ((long long)frame_idx[s] * hw + lb) * 64 + c, dxh[row * cpad + c] * wgt);
+  };
+  if (l1 == l2) {
+    add(l1, w1 + w2);
+  } else {
+    add(l1, w1);
+    add(l2, w2);
+  }
+}
+
 __global__ void scene_mean_bwd_kernel(const float* __restrict__ dmean, const int* __restrict__ fidx,
                                       float* __restrict__ dscene, long long N, int T, long long HWC) {
   const long long total = N * HWC;
@@ -692,6 +714,15 @@ int enc_class_input_bwd(const float* dxh, int cpad, const int* frame_idx, const 
                         float* dscene, long long NS, int H, int W, cudaStream_t stream) {
   MVB_REQUIRE(dxh && frame_idx && label && dscene && NS > 0, "enc_class_input_bwd: bad args");
   enc_class_input_bwd_kernel<<<(unsigned)NS, 64, 0, stream>>>(dxh, cpad, frame_idx, label, dscene, make_grid(H, W));
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+int enc_class_input_mix_bwd(const float* dxh, int cpad, const int* frame_idx, const int* label, const int* label2,
+                            float beta, float* dscene, long long NS, int H, int W, cudaStream_t stream) {
+  MVB_REQUIRE(dxh && frame_idx && label && label2 && dscene && NS > 0, "enc_class_input_mix_bwd: bad args");
+  enc_class_input_mix_bwd_kernel<<<(unsigned)NS, 64, 0, stream>>>(dxh, cpad, frame_idx, label, label2, beta, dscene, make_grid(H, W));
   MVB_CHECK_CUDA(cudaGetLastError());
   count_launch(1);
   return MVB_OK;

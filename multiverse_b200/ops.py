@@ -200,6 +200,12 @@ def enc_class_input(scene_conv, frame_idx, label, prev_label, xh, h, w):
             _p(xh), xh.stride(0), xh.shape[2], label.shape[0], h, w, planes_of(xh), _stream())
 
 
+def enc_class_input_mix(scene_conv, frame_idx, label, label2, beta, xh, h, w):
+  """scene_conv (.) (beta one_hot(label) + (1 - beta) one_hot(label2)) into the (zeroed) x block of xh."""
+  _lib.call("mvb_enc_class_input_mix", _p(scene_conv), _p(frame_idx), _p(label), _p(label2), float(beta),
+            _p(xh), xh.stride(0), xh.shape[2], label.shape[0], h, w, planes_of(xh), _stream())
+
+
 def scene_conv_fwd(x, W, b):
   f, ih, iw, cin = x.shape
   cout = W.shape[3]
@@ -360,6 +366,11 @@ def scene_conv_bwd(x, W, out, dout, dW, db, din):
 def enc_class_input_bwd(dxh, frame_idx, label, dscene, h, w):
   _lib.call("mvb_enc_class_input_bwd", _p(dxh), dxh.shape[1], _p(frame_idx), _p(label), _p(dscene),
             label.shape[0], h, w, _stream())
+
+
+def enc_class_input_mix_bwd(dxh, frame_idx, label, label2, beta, dscene, h, w):
+  _lib.call("mvb_enc_class_input_mix_bwd", _p(dxh), dxh.shape[1], _p(frame_idx), _p(label), _p(label2), float(beta),
+            _p(dscene), label.shape[0], h, w, _stream())
 
 
 def scene_time_mean_bwd(dmean, frame_idx, dscene):

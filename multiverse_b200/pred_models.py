@@ -558,16 +558,25 @@ class Model(object):
       rows["scene_feat"], _ = simaug.white_box_attack(eng, rows, label, cfg, self._aug_rng,
                                                       norm_feat=getattr(cfg, "norm_feat", False))
     elif multi:
-      if int(cfg.multiview_exp) == 3:
-        raise NotImplementedError("multiview_exp 3 also mixes the observed grid classes and the loss labels of two "
-                                  "views (SimAug/code/pred_models.py:616-635, :1371-1405): not built; the "
-                                  "augmentation itself is simaug.multiview_augmentation")
       src = dict(feeds)       # the unique frames: obs_scene_extra indexes them
       src["grid_pred_labels_extra"] = [None if not cfg.use_grids[j] else
                                        np.asarray(feed[self.grid_pred_labels_T_extra[j]]).astype(np.int32)
                                        for j in range(len(cfg.scene_grids))]
       src["obs_scene_extra"] = np.asarray(feed[self.obs_scene_extra]).astype(np.int32)
       rows["scene_feat"], self.multiview_info = simaug.multiview_augmentation(eng, src, cfg, self._aug_rng)
+      if int(cfg.multiview_exp) == 3:
+        # the label side of experiment 3 (SimAug/code/pred_models.py:616-638, :1371-1405): the observed class maps
+        # and the loss labels are mixed with those of the selected other view, weight beta; the per-sample focal
+        # weights multiply the classification loss under --double_weighting
+        info = self.multiview_info
+        sel = info["selected_extra_indices"].long()
+        pick = lambda a: torch.as_tensor(np.asarray(a), device=dev).to(torch.int32)[torch.arange(n, device=dev), sel]
+        ns = len(cfg.scene_grids)
+        rows["mixup"] = dict(
+            beta=float(info["beta_weight"]),
+            obs_labels2=[pick(feed[self.grid_obs_labels_extra[j]]) if cfg.use_grids[j] else None for j in range(ns)],
+            pred_labels2=[pick(feed[self.grid_pred_labels_T_extra[j]]) if cfg.use_grids[j] else None for j in range(ns)],
+            focal=info["focal_loss_weight"] if getattr(cfg, "double_weighting", False) else None)
     if jitter:
       eps = float(cfg.adv_epsilon)
       noise = self._aug_rng.uniform(-eps, eps, size=tuple(rows["scene_feat"].shape)).astype(np.float32)

@@ -12,7 +12,9 @@ offsets, the Beta mixup weight) come from a numpy Generator - TensorFlow's rando
 ``multiview_augmentation`` (:346-541; second part of row f-4) runs the same one-step attack on the batch tiled
 over the M camera views - the role of the reference's ``build_tower`` (:544, the forward of the model on given scene
 semantics and tiled feeds) is played by ``TrainEngine.loss_and_grads`` on the tiled feed dict - ranks the views by
-their per-sample classification loss (``mvb_ce_rows``), picks two per ``config.multiview_exp`` and mixes them.
+their per-sample classification loss (``mvb_ce_rows``), picks two per ``config.multiview_exp`` and mixes them.  The
+label side of experiment 3 (mixed observed class maps and loss labels, focal weights; :616-638, :1371-1405) lives in
+``TrainEngine`` (``feeds["mixup"]``) and is wired up by the drop-in ``Model._simaug_feeds``.
 """
 from __future__ import annotations
 

@@ -90,6 +90,8 @@ class TrainEngine(ConvRNNEngine):
     obs_scene_t = feeds["obs_scene"].to(torch.int32).t().contiguous()
     obs_reg_t = feeds["grid_obs_regress"][i].float().transpose(0, 1).contiguous()
     n = labels_t.shape[1]
+    mix = feeds.get("mixup")
+    labels2_t = mix["obs_labels2"][i].to(torch.int32).t().contiguous() if mix is not None else None
     R = ops.halo_rows(n, h, w)
     st = lambda tag, cnt: self._steps((tag, i, n), cnt, lambda: ops.alloc_state(n, h, w, dev))
     gt = lambda tag, cnt: self._steps((tag, i, n), cnt, lambda: torch.zeros((R, 4 * HID), device=dev))
@@ -103,7 +105,10 @@ class TrainEngine(ConvRNNEngine):
       xh[t][:, :, :sw.enc_class.cxp].zero_()
       if t == 0:
         xh[0][:, :, sw.enc_class.cxp:].zero_()
-      ops.enc_class_input(convs[i], obs_scene_t[t], labels_t[t], None, xh[t], h, w)
+      if mix is None:
+        ops.enc_class_input(convs[i], obs_scene_t[t], labels_t[t], None, xh[t], h, w)
+      else:          # SimAug multiview_exp 3: the observed class map is a mix of two views' one-hot maps
+        ops.enc_class_input_mix(convs[i], obs_scene_t[t], labels_t[t], labels2_t[t], mix["beta"], xh[t], h, w)
       last = t == T - 1
       nxt = xh[t + 1] if not last else (None if cfg.use_gnn else xh_dc[0])
       ops.cell_fwd_train(xh[t], sw.enc_class, None if t == 0 else c[t - 1], c[t],
@@ -115,7 +120,20 @@ class TrainEngine(ConvRNNEngine):
     ids = self._one(("ids", i, n), lambda: torch.empty((Tp, n), dtype=torch.int32, device=dev))
     We, be = sw.emb_class
     first_ids = labels_t[-1].contiguous()
-    ops.emb_onehot_fwd(first_ids, We, be, xh_dc[0], h, w)
+    first_map = We_pad = None
+    if mix is None:
+      ops.emb_onehot_fwd(first_ids, We, be, xh_dc[0], h, w)
+    else:
+      # the decoder's first input is the MIXED last observed class map (obs_grid_class[:, -1], :690): a two-cell
+      # dense map, embedded by the dense-input kernel with the class embedding padded to two input channels
+      beta = float(mix["beta"])
+      first_map = torch.zeros((n, h * w, 2), dtype=torch.float32, device=dev)
+      rows = torch.arange(n, device=dev)
+      first_map[:, :, 0].index_put_((rows, first_ids.long()), torch.full((n,), beta, device=dev), accumulate=True)
+      first_map[:, :, 0].index_put_((rows, labels2_t[-1].long()), torch.full((n,), 1.0 - beta, device=dev,
+                                                                                dtype=torch.float32), accumulate=True)
+      We_pad = torch.cat([We, torch.zeros_like(We)], dim=2).contiguous()
+      ops.emb_dense_fwd(first_map, We_pad, be, xh_dc[0], h, w)
     for t in range(Tp):
       h_prev = h32_last if t == 0 else h32[t - 1]
       c_prev = S["c_ec"][T - 1] if t == 0 else c[t - 1]
@@ -126,7 +144,8 @@ class TrainEngine(ConvRNNEngine):
                          None if (cfg.use_gnn or last) else xh_dc[t + 1], g[t], h, w, n)
       ops.head_class_fwd(h32[t], sw.head_class, logits[t], ids[t], None if last else We,
                          None if last else be, None if last else xh_dc[t + 1], h, w, n, planes=P)
-    S.update(xh_dc=xh_dc, c_dc=c, g_dc=g, h32_dc=h32, logits=logits, ids=ids, first_ids=first_ids)
+    S.update(xh_dc=xh_dc, c_dc=c, g_dc=g, h32_dc=h32, logits=logits, ids=ids, first_ids=first_ids,
+             first_map=first_map, We_pad=We_pad, labels2_t=labels2_t, mix=mix)
     # ---- regression encoder
     xh = xs("xh_er", T, sw.enc_reg.cpad); c = st("c_er", T); g = gt("g_er", T)
     xh_dr = xs("xh_dr", Tp, sw.dec_reg.cpad)
@@ -186,7 +205,27 @@ class TrainEngine(ConvRNNEngine):
     tgt = feeds["grid_pred_regress"][i].float().transpose(0, 1).reshape(Tp, n, h * w, 2).contiguous()
     dlogits = self._one(("dlogits", i, n), lambda: torch.empty_like(S["logits"]))
     doffs = self._one(("doffs", i, n), lambda: torch.empty_like(S["offs"]))
-    ops.loss_fwd_bwd(S["logits"], lab, dlogits, cw, S["offs"], tgt, doffs, rw, loss_out)
+    mix = S["mix"]
+    if mix is None:
+      ops.loss_fwd_bwd(S["logits"], lab, dlogits, cw, S["offs"], tgt, doffs, rw, loss_out)
+    else:
+      # mixed labels (SimAug/code/pred_models.py:1371-1405): softmax CE against beta one_hot(l1) + (1-beta) one_hot(l2)
+      # = beta CE(l1) + (1-beta) CE(l2), optionally times the per-sample focal weight (double_weighting)
+      beta = float(mix["beta"])
+      lab2 = mix["pred_labels2"][i].to(torch.int32).t().contiguous()             # [Tp,N]
+      focal = mix.get("focal")
+      rowl = beta * ops.ce_rows(S["logits"], lab) + (1.0 - beta) * ops.ce_rows(S["logits"], lab2)
+      if focal is not None:
+        rowl = rowl * focal.float()[None, :]
+      loss_out[0] += rowl.mean() * cw
+      scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+      dl2 = self._one(("dlogits2", i, n), lambda: torch.empty_like(S["logits"]))
+      ops.loss_fwd_bwd(S["logits"], lab, dlogits, cw * beta, None, None, None, 0.0, scratch)
+      ops.loss_fwd_bwd(S["logits"], lab2, dl2, cw * (1.0 - beta), None, None, None, 0.0, scratch)
+      dlogits += dl2
+      if focal is not None:
+        dlogits *= focal.float()[None, :, None]
+      ops.loss_fwd_bwd(None, None, None, 0.0, S["offs"], tgt, doffs, rw, loss_out)
     # ---- class decoder
     dsm = self._one(("dsm", i, n), lambda: torch.zeros_like(means[i]))
     dsm.zero_()
@@ -199,7 +238,12 @@ class TrainEngine(ConvRNNEngine):
       dxh, dc = self._cell_bwd(S, i, sw.dec_class, cgr["dec_class"], S["xh_dc"][t], S["g_dc"][t], c_prev,
                                S["c_dc"][t], dh, dc)
       ids_prev = S["first_ids"] if t == 0 else S["ids"][t - 1]
-      ops.emb_bwd(dxh, ids_prev, None, We, be, G[nm["emb_class"][0]], G[nm["emb_class"][1]], None, False, h, w, n)
+      if t == 0 and mix is not None:       # the mixed two-cell first input: dense path, padded embedding
+        dWe_pad = torch.zeros_like(S["We_pad"])
+        ops.emb_bwd(dxh, None, S["first_map"], S["We_pad"], be, dWe_pad, G[nm["emb_class"][1]], None, False, h, w, n)
+        G[nm["emb_class"][0]] += dWe_pad[:, :, :1]
+      else:
+        ops.emb_bwd(dxh, ids_prev, None, We, be, G[nm["emb_class"][0]], G[nm["emb_class"][1]], None, False, h, w, n)
       gout = dxh[:, sw.dec_class.cxp:].contiguous()
       if cfg.use_gnn:
         h_prev = S["h32_ec"] if t == 0 else S["h32_dc"][t - 1]
@@ -210,7 +254,11 @@ class TrainEngine(ConvRNNEngine):
     for t in range(T - 1, -1, -1):
       dxh, dc = self._cell_bwd(S, i, sw.enc_class, cgr["enc_class"], S["xh_ec"][t], S["g_ec"][t],
                                None if t == 0 else S["c_ec"][t - 1], S["c_ec"][t], dh, dc)
-      ops.enc_class_input_bwd(dxh, S["obs_scene_t"][t], S["labels_t"][t], dconv[i], h, w)
+      if mix is None:
+        ops.enc_class_input_bwd(dxh, S["obs_scene_t"][t], S["labels_t"][t], dconv[i], h, w)
+      else:
+        ops.enc_class_input_mix_bwd(dxh, S["obs_scene_t"][t], S["labels_t"][t], S["labels2_t"][t], mix["beta"],
+                                    dconv[i], h, w)
       if t > 0:
         dh.copy_(dxh[:, sw.enc_class.cxp:])
     ops.scene_time_mean_bwd(dsm, feeds["obs_scene"].to(torch.int32).contiguous(), dconv[i])
@@ -249,7 +297,11 @@ class TrainEngine(ConvRNNEngine):
     (micro-batching: n_chunk / N, every loss being a batch mean).
     dscene_out (fp32 [F,SH,SW,SC], zeroed by the caller): receives d loss / d scene_feat - the input gradient of
     SimAug's white-box attack; cls_weight / reg_weight override the config's loss
-    weights for this call (the attack differentiates the classification loss alone)."""
+    weights for this call (the attack differentiates the classification loss alone).
+    feeds["mixup"] (optional; SimAug multiview_exp 3, SimAug/code/pred_models.py:616-638, :1371-1405) =
+    dict(beta, obs_labels2[i] int [N,T], pred_labels2[i] int [N,Tp], focal fp32 [N] or None): the observed class
+    maps (encoder input and the decoder's first input) and the loss labels become beta * view 1 + (1 - beta) * view 2,
+    the per-sample classification losses are weighted by `focal`."""
     cfg, dev = self.cfg, self.device
     cls_w = cfg.grid_loss_weight if cls_weight is None else cls_weight
     reg_w = cfg.grid_reg_loss_weight if reg_weight is None else reg_weight
@@ -319,6 +371,11 @@ class TrainEngine(ConvRNNEngine):
       part = dict(scene_feat=feeds["scene_feat"][uniq.long()].contiguous(), obs_scene=inv.to(torch.int32))
       for key in ("grid_obs_labels", "grid_obs_regress", "grid_pred_labels", "grid_pred_regress"):
         part[key] = [None if a is None else a[sl] for a in feeds[key]]
+      if feeds.get("mixup") is not None:
+        mx = feeds["mixup"]
+        part["mixup"] = dict(beta=mx["beta"], obs_labels2=[None if a is None else a[sl] for a in mx["obs_labels2"]],
+                             pred_labels2=[None if a is None else a[sl] for a in mx["pred_labels2"]],
+                             focal=None if mx.get("focal") is None else mx["focal"][sl])
       losses, wd = self.loss_and_grads(part, loss_scale=micro_batch / float(n), zero=(lo == 0))
       total = losses if total is None else total + losses
     return total, wd

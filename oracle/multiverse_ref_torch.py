@@ -182,7 +182,20 @@ def loss_and_grads(cfg, weights, feeds, dtype=torch.float64):
       continue
     logits = out["grid_pred_decoded"][i].reshape(-1, h * ww)
     labels = torch.from_numpy(feeds["grid_pred_labels"][i]).long().reshape(-1)
-    cls = F.cross_entropy(logits, labels) * cfg.grid_loss_weight          # :991-995, :1024
+    mixup = feeds.get("mixup")
+    if mixup is None:
+      cls = F.cross_entropy(logits, labels) * cfg.grid_loss_weight        # :991-995, :1024
+    else:
+      # SimAug multiview_exp 3 (SimAug/code/pred_models.py:1371-1405): softmax CE against the mixed labels, per-row
+      # focal weights under double_weighting, then the mean
+      beta = torch.tensor(np.float32(mixup["beta"])).to(dtype)
+      l2 = torch.from_numpy(np.asarray(mixup["pred_labels2"][i])).long().reshape(-1)
+      soft = F.one_hot(labels, h * ww).to(dtype) * beta + F.one_hot(l2, h * ww).to(dtype) * (1 - beta)
+      rows = -(soft * F.log_softmax(logits, dim=1)).sum(1)
+      if mixup.get("focal") is not None:
+        fw = torch.from_numpy(np.asarray(mixup["focal"])).to(dtype)
+        rows = rows * fw[:, None].expand(n, cfg.pred_len).reshape(-1)
+      cls = rows.mean() * cfg.grid_loss_weight
     tgt = torch.from_numpy(feeds["grid_pred_regress"][i]).to(dtype)
     reg = F.huber_loss(out["grid_pred_reg_decoded"][i], tgt, delta=1.0) * cfg.grid_reg_loss_weight
     losses += [cls, reg]
@@ -212,6 +225,11 @@ def _forward(cfg, w, feeds, dtype):
     sw = R.scale_weights(w, i)
     labels = torch.from_numpy(feeds["grid_obs_labels"][i]).long()
     onehot = F.one_hot(labels, h * ww).to(dtype).reshape(n, -1, h, ww, 1)
+    mixup = feeds.get("mixup")
+    if mixup is not None:      # SimAug multiview_exp 3 (SimAug/code/pred_models.py:616-635): mixed observed class maps
+      beta = torch.tensor(np.float32(mixup["beta"])).to(dtype)
+      other = F.one_hot(torch.from_numpy(np.asarray(mixup["obs_labels2"][i])).long(), h * ww).to(dtype)
+      onehot = beta * onehot + other.reshape(n, -1, h, ww, 1) * (1 - beta)
     obs_reg = torch.from_numpy(feeds["grid_obs_regress"][i]).to(dtype)
     mask = neighbour_mask(h, ww, dtype)
     enc = encoder(convs[i] * onehot, sw.enc_class[0], sw.enc_class[1], cfg.enc_hidden_size)

@@ -369,6 +369,56 @@ def test_simaug_scene_input_gradient_and_attack(dev):
   assert bool(((adv_mix - x).abs() <= 0.1 + 1e-6).all())
 
 
+@pytest.mark.parametrize("focal", [False, True])
+def test_mixup_of_two_views_loss_and_gradients(dev, focal):
+  """The label side of SimAug's multiview_exp 3 (SimAug/code/pred_models.py:616-638, :1371-1405): observed class maps
+  (encoder input, decoder's first input) and loss labels mixed from two views with weight beta, optional per-sample
+  focal weights - loss and every variable gradient against torch autograd on the oracle with the same mix.  One
+  sample's two views share a cell at some steps (the single-pixel case of the mixed input)."""
+  from multiverse_b200 import synthetic
+  from multiverse_b200.train_engine import TrainEngine
+  from oracle import multiverse_ref as R
+  from oracle import multiverse_ref_torch as RT
+  n = 3
+  over = dict(batch_size=n, use_grids=[False, True])
+  cfg = synthetic.make_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, clip_gradient_norm=10.0, **over)
+  w = synthetic.make_weights(cfg, 23); f = synthetic.make_feeds(cfg, n, 23, with_pred=True)
+  rng = np.random.default_rng(4)
+  hw = 18 * 9
+  obs2 = rng.integers(0, hw, size=(n, cfg.obs_len)).astype(np.int32)
+  pred2 = rng.integers(0, hw, size=(n, cfg.pred_len)).astype(np.int32)
+  obs2[0] = f["grid_obs_labels"][1][0]                 # sample 0: both views in the same cells
+  pred2[0, ::2] = f["grid_pred_labels"][1][0, ::2]
+  mix = dict(beta=0.7, obs_labels2=[None, obs2], pred_labels2=[None, pred2],
+             focal=(rng.uniform(0.2, 1.0, n).astype(np.float32) if focal else None))
+  eng = TrainEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  feeds = {k: ([T(a, dev) for a in v] if isinstance(v, list) else T(v, dev)) for k, v in f.items() if not k.startswith("traj")}
+  feeds["mixup"] = dict(beta=0.7, obs_labels2=[None, T(obs2, dev)], pred_labels2=[None, T(pred2, dev)],
+                        focal=None if not focal else T(mix["focal"], dev))
+  losses, wd = eng.loss_and_grads(feeds)
+  rcfg = R.default_config(grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001, **over)
+  tot, ref_losses, ref_wd, grads = RT.loss_and_grads(rcfg, w, dict(f, mixup=mix))
+  plain = RT.loss_and_grads(rcfg, w, f)[1]
+  assert abs(ref_losses[0] - plain[0]) > 1e-3            # the mix changes the objective
+  got = losses.cpu().numpy()
+  assert np.abs(got - np.array(ref_losses)).max() < 1e-4 * max(ref_losses)
+  worst = {}
+  for k in eng.names:
+    ref = grads[k] - (cfg.wd * w[k] if k.endswith("/W") else 0.0)
+    if np.abs(ref).max() == 0:
+      assert float(eng.grads[k].abs().max()) == 0
+      continue
+    worst[k] = rel(eng.grads[k].cpu().numpy(), ref)
+  bad = {k: v for k, v in worst.items() if v > 1e-3}
+  print("mixup (focal=%s): worst gradient errors %s" % (focal, sorted(worst.items(), key=lambda kv: -kv[1])[:3]))
+  assert not bad, bad
+  # micro-batched == full batch with the mix sliced along
+  g_full = eng.flat_grad.clone()
+  l_mb, _ = eng.loss_and_grads_chunked(feeds, 1)
+  assert float((losses - l_mb).abs().max()) < 1e-4 * float(losses.abs().max())
+  assert float((g_full - eng.flat_grad).abs().max()) < 2e-4 * float(g_full.abs().max())
+
+
 @pytest.mark.parametrize("mode", ["adv_train", "multiview_train", "standard_aug"])
 def test_simaug_training_variants_through_the_dropin_trainer(dev, monkeypatch, mode):
   """SimAug's training-time augmentations behind the reference-facing surface (SimAug/code/pred_models.py:286-325,
@@ -439,9 +489,10 @@ def test_simaug_training_variants_through_the_dropin_trainer(dev, monkeypatch, m
   aug = run(0.1, **{mode: True})
   assert np.isfinite(aug[0]) and np.isfinite(aug[1]).all() and abs(aug[0] - plain[0]) > 1e-6
   assert np.abs(aug[2] - w["person_pred/decoder_grid_class_1/decoder_rnn/dec_grid_1/kernel"]).max() > 0
-  if mode == "multiview_train":
-    with pytest.raises(NotImplementedError):
-      run(0.1, multiview_train=True, multiview_exp=3)
+  if mode == "multiview_train":      # experiment 3: label mixing and focal weights on top of the feature mix
+    exp3 = run(0.1, multiview_train=True, multiview_exp=3, double_weighting=True, fl_gamma=2.0,
+               multiview_use_adv_for_loss=False, multiview_random=False)
+    assert np.isfinite(exp3[0]) and abs(exp3[0] - aug[0]) > 1e-6
 
 
 @pytest.mark.parametrize("exp", [1, 4, 2, 3])
