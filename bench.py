@@ -88,17 +88,21 @@ class ClockSampler(object):
     if self.proc is None:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
     self.proc.terminate()
-    sm, mx, reasons = [], None, set()
+    sm, mx, reasons, watts = [], None, set(), []
     for r in self.rows:
       try:
         sm.append(float(r[1])); mx = float(r[2])
       except Exception:
         continue
+      try:
+        watts.append(float(r[3]))
+      except Exception:
+        pass
       for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
         if v.lower().startswith("active"):
           reasons.add(name)
     return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, samples=len(sm),
-                reasons=sorted(reasons))
+                reasons=sorted(reasons), power_w=float(np.median(watts)) if watts else None)
 
 
 def load_peaks():

@@ -411,6 +411,93 @@ def test_tf_checkpoint_bundle_reader(dropin, tmp_path):
     _bundle.read_index(prefix)
 
 
+def test_tf_checkpoint_bundle_reader_on_hand_assembled_bytes(dropin, tmp_path):
+  """The reader against files assembled here byte by byte from the published formats - not by the writer in
+  tensorflow/_bundle.py: a LevelDB-format table (leveldb doc/table_format.md: prefix-compressed entries
+  `varint shared | varint non_shared | varint value_len | key delta | value`, a restart array + count, a 5-byte
+  block trailer = compression type 0 + masked CRC-32C, metaindex block, index block of BlockHandles, 48-byte footer
+  ending in the magic 0xdb4775248b80fb57) holding tensor_bundle.proto messages typed out field by field
+  (BundleHeaderProto under the empty key; BundleEntryProto: 1 dtype, 2 shape{2 dim{1 size}}, 4 offset, 5 size,
+  6 fixed32 crc32c).  CRC and varints come from the independent implementations below."""
+  tf, pm = dropin
+  from tensorflow import _bundle
+
+  def crc32c(data):                       # bitwise Castagnoli CRC, reflected polynomial 0x82F63B78
+    crc = 0xFFFFFFFF
+    for byte in data:
+      crc ^= byte
+      for _ in range(8):
+        crc = (crc >> 1) ^ (0x82F63B78 if crc & 1 else 0)
+    return crc ^ 0xFFFFFFFF
+
+  assert crc32c(b"123456789") == 0xE3069283
+  masked = lambda c: ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+  def varint(v):
+    out = bytearray()
+    while v >= 0x80:
+      out.append((v & 0x7F) | 0x80); v >>= 7
+    out.append(v)
+    return bytes(out)
+
+  le32 = lambda v: int(v).to_bytes(4, "little")
+  # ---- the data file: two tensors back to back
+  a = np.arange(6, dtype=np.float32).reshape(2, 3) * 0.5 - 1.0          # "a/kernel"  DT_FLOAT [2,3] at offset 0
+  step = np.asarray(4321, dtype=np.int64)                               # "global_step"  DT_INT64 [] at offset 24
+  data = a.tobytes() + step.tobytes()
+  # ---- protos, typed out (field tags: (field << 3) | wire type)
+  header = bytes([0x08, 0x01,                     # num_shards = 1
+                  0x1A, 0x02, 0x08, 0x01])        # version { producer = 1 }        (endianness LITTLE = 0: absent)
+  entry_a = (bytes([0x08, 0x01,                   # dtype = DT_FLOAT (1)
+                    0x12, 0x08, 0x12, 0x02, 0x08, 0x02, 0x12, 0x02, 0x08, 0x03,     # shape { dim{size 2} dim{size 3} }
+                    0x28, 0x18,                   # size = 24                        (shard_id 0, offset 0: absent)
+                    0x35]) + le32(masked(crc32c(a.tobytes()))))                     # crc32c, fixed32
+  entry_s = (bytes([0x08, 0x09,                   # dtype = DT_INT64 (9)
+                    0x12, 0x00,                   # shape {}  (scalar)
+                    0x20, 0x18,                   # offset = 24
+                    0x28, 0x08,                   # size = 8
+                    0x35]) + le32(masked(crc32c(step.tobytes()))))
+
+  def block(entries):
+    body, prev = bytearray(), b""
+    for key, value in entries:                    # one restart point at 0: keys after it are prefix-compressed
+      shared = 0
+      while shared < min(len(prev), len(key)) and prev[shared] == key[shared]:
+        shared += 1
+      body += varint(shared) + varint(len(key) - shared) + varint(len(value)) + key[shared:] + value
+      prev = key
+    body += le32(0) + le32(1)                     # restart offsets, number of restarts
+    return bytes(body)
+
+  def with_trailer(blk):
+    return blk + b"\x00" + le32(masked(crc32c(blk + b"\x00")))
+
+  # keys in bytewise order: "" < "a/kernel" < "global_step"
+  data_block = block([(b"", header), (b"a/kernel", entry_a), (b"global_step", entry_s)])
+  meta_block = block([])
+  off_meta = len(data_block) + 5
+  index_block = block([(b"h", varint(0) + varint(len(data_block)))])    # separator key >= "global_step"
+  off_index = off_meta + len(meta_block) + 5
+  footer = varint(off_meta) + varint(len(meta_block)) + varint(off_index) + varint(len(index_block))
+  footer += b"\x00" * (40 - len(footer)) + (0xDB4775248B80FB57).to_bytes(8, "little")
+  table = with_trailer(data_block) + with_trailer(meta_block) + with_trailer(index_block) + footer
+  prefix = str(tmp_path / "hand" / "model.ckpt-4321")
+  os.makedirs(os.path.dirname(prefix))
+  open(prefix + ".index", "wb").write(table)
+  open(prefix + ".data-00000-of-00001", "wb").write(data)
+  assert _bundle.is_bundle(prefix)
+  hdr, entries = _bundle.read_index(prefix)
+  assert hdr["num_shards"] == 1 and set(entries) == {"a/kernel", "global_step"}
+  assert entries["a/kernel"]["shape"] == (2, 3) and entries["global_step"]["shape"] == ()
+  back = _bundle.read_bundle(prefix)
+  assert back["a/kernel"].dtype == np.float32 and np.array_equal(back["a/kernel"], a)
+  assert back["global_step"].dtype == np.int64 and int(back["global_step"]) == 4321
+  # and the other way round: what the module's writer produces parses with the spec-level walk used above
+  _bundle.write_bundle(str(tmp_path / "hand" / "w"), {"a/kernel": a})
+  raw = open(str(tmp_path / "hand" / "w") + ".index", "rb").read()
+  assert raw[-8:] == (0xDB4775248B80FB57).to_bytes(8, "little") and len(raw) >= 48
+
+
 def test_forward_graph_cache_policy_without_a_gpu(monkeypatch):
   """Host logic of ConvRNNEngine.forward_graph with the CUDA pieces stubbed: a signature runs eagerly the first
   time, is captured the second time (one graph per independent chain) and replayed afterwards; at most GRAPH_CACHE graphs are kept (oldest evicted);
