@@ -100,6 +100,19 @@ int mvb_convlstm_cell_fwd_onehot(const void* xh_planes, const void* w_planes, co
                                  const int32_t* row_map, float* c_out, float* h32_out, void* hp_out,
                                  int64_t hp_plane_stride, int cpad_out, int ch_off_out, int64_t NS, int H,
                                  int W, int cpad, int planes, float forget_bias, void* stream);
+/* The cell of the regression encoder (code/pred_models.py:196-202, :232-234), whose 2-channel input holds raw pixel
+ * offsets of up to +-1.9e3: the h block goes through the tensor cores (any operand format, normally f16f8), the x block
+ * is added in fp32 in the gate epilogue, sum over the 9 taps and the 2 channels of x_in[p + off(tap)][ch] *
+ * x_weights[tap * 2 + ch][column] (zero outside the image) - every bit of the input counts, at 2 instead of 3 tensor
+ * passes.  x_in fp32 [NS,H,W,2] NHWC without halo; x_weights fp32 [18][1024] from mvb_cell_xdense_weights (rows
+ * (tap, channel) of the TF kernel [3,3,2+256,1024] in the packed column order); the x block of xh_planes is not read.
+ * Other arguments as mvb_convlstm_cell_fwd. */
+int mvb_convlstm_cell_fwd_xdense(const void* xh_planes, const void* w_planes, const float* bias_packed,
+                                 const float* x_in, const float* x_weights, const float* c_in, float* c_out,
+                                 float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
+                                 int64_t NS, int H, int W, int cpad, int planes, float forget_bias, void* stream);
+int mvb_cell_xdense_weights(const float* kernel_tf, float* x_weights, void* stream);
+
 /* First K-row step of the beam decoder (pred_models.py:611-666 right after the first selection): the K = fanout
  * children of a sample share their parent - the same graph-attended h and the same c - and differ only in the
  * selected cell ids[s*K + k], i.e. in the folded table rows.  The GEMM runs once per PARENT row (xh_planes, c_in:

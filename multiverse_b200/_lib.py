@@ -26,6 +26,9 @@ SIGNATURES = {
     "mvb_convlstm_cell_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                               _i, _i, _f, _vp],
     "mvb_cell_xfold_tables": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "mvb_convlstm_cell_fwd_xdense": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
+                                     _i, _i, _f, _vp],
+    "mvb_cell_xdense_weights": [_vp, _vp, _vp],
     "mvb_convlstm_cell_fwd_onehot_fanout": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "mvb_convlstm_cell_fwd_onehot": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64,
                                      _i, _i, _i, _i, _f, _vp],

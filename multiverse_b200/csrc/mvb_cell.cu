@@ -82,6 +82,10 @@ struct CellParams {
   const float* xf_T2;       // [9][25][1024]
   const int* xf_ids;        // [NS] arg-max cell of every sample row
   int skip_x;               // x-fold: the x chunk of the K loop is skipped
+  // dense raw x block of two channels, added in fp32 in the epilogue instead of going through the tensor cores
+  // (regression encoder: the +-1.9e3 pixel offsets need all 24 bits, which neither operand format carries in 2 passes):
+  const float* xr_in;       // [NS, H, W, 2] fp32 NHWC (no halo), or nullptr
+  const float* xr_W;        // [9 taps * 2 channels][1024] fp32, packed column order
   int order;                // work order, see work_index()
   int abl;                  // debug ablations (MVB_CELL_ABL; results are then WRONG): 1 skip the fp8 MMAs, 2 skip the
                             // 16-bit MMAs, 4 skip the epilogue's math and stores, 8 the issuer does not wait for operand
@@ -387,6 +391,17 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int acy = ay == 0 ? 0 : (ay == g.H - 1 ? 2 : 1), acx = ax == 0 ? 0 : (ax == g.W - 1 ? 2 : 1);
         return prm.xf_T2 + ((long long)(acy * 3 + acx) * 25 + (ry + 2) * 5 + (rx + 2)) * kGates;
       };
+      float xv[18];                    // dense x path: the 3x3 neighbourhood of this cell's two raw input channels
+      if (prm.xr_W) {
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          const int yy = py + tp / 3 - 1, xx = px + tp % 3 - 1;
+          const bool ok = valid && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
+          const float2 v = ok ? __ldg(reinterpret_cast<const float2*>(prm.xr_in + ((psmp * g.H + yy) * g.W + xx) * 2))
+                              : make_float2(0.f, 0.f);
+          xv[2 * tp] = v.x; xv[2 * tp + 1] = v.y;
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       if (prm.abl & 4) valid = false;
@@ -444,6 +459,21 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               qj.x = __fadd_rn(qj.x, tj.x); qj.y = __fadd_rn(qj.y, tj.y); qj.z = __fadd_rn(qj.z, tj.z); qj.w = __fadd_rn(qj.w, tj.w);
               qf.x = __fadd_rn(qf.x, tf.x); qf.y = __fadd_rn(qf.y, tf.y); qf.z = __fadd_rn(qf.z, tf.z); qf.w = __fadd_rn(qf.w, tf.w);
               qo.x = __fadd_rn(qo.x, to.x); qo.y = __fadd_rn(qo.y, to.y); qo.z = __fadd_rn(qo.z, to.z); qo.w = __fadd_rn(qo.w, to.w);
+            }
+            if (prm.xr_W) {           // + sum over taps and the two channels of x * W, fp32 (warp-uniform weight loads)
+              const float* wb = prm.xr_W + nt * BLOCK_N + j0 + 4 * v4;
+#pragma unroll
+              for (int k = 0; k < 18; ++k) {
+                const float4 wi = __ldg(reinterpret_cast<const float4*>(wb + k * kGates + 0 * TILE_CH)),
+                             wj = __ldg(reinterpret_cast<const float4*>(wb + k * kGates + 1 * TILE_CH)),
+                             wf = __ldg(reinterpret_cast<const float4*>(wb + k * kGates + 2 * TILE_CH)),
+                             wo = __ldg(reinterpret_cast<const float4*>(wb + k * kGates + 3 * TILE_CH));
+                const float xk = xv[k];
+                qi.x = __fmaf_rn(xk, wi.x, qi.x); qi.y = __fmaf_rn(xk, wi.y, qi.y); qi.z = __fmaf_rn(xk, wi.z, qi.z); qi.w = __fmaf_rn(xk, wi.w, qi.w);
+                qj.x = __fmaf_rn(xk, wj.x, qj.x); qj.y = __fmaf_rn(xk, wj.y, qj.y); qj.z = __fmaf_rn(xk, wj.z, qj.z); qj.w = __fmaf_rn(xk, wj.w, qj.w);
+                qf.x = __fmaf_rn(xk, wf.x, qf.x); qf.y = __fmaf_rn(xk, wf.y, qf.y); qf.z = __fmaf_rn(xk, wf.z, qf.z); qf.w = __fmaf_rn(xk, wf.w, qf.w);
+                qo.x = __fmaf_rn(xk, wo.x, qo.x); qo.y = __fmaf_rn(xk, wo.y, qo.y); qo.z = __fmaf_rn(xk, wo.z, qo.z); qo.w = __fmaf_rn(xk, wo.w, qo.w);
+              }
             }
             float4 si = qi, sj = qj, sf = qf, so = qo;
             if (FMT == 1) {
@@ -687,6 +717,24 @@ __global__ void xfold_tables_kernel(const float* __restrict__ kernel, const floa
   }
 }
 
+// weights of the dense x path: rows (tap, channel) of the TF kernel [3,3,2+256,1024] in the packed column order
+__global__ void xdense_weights_kernel(const float* __restrict__ kernel, float* __restrict__ out) {
+  const int total = 18 * kGates;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % kGates, k = i / kGates, tap = k >> 1, ch = k & 1;
+    const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+    const int col = gate * kHidden + tile * TILE_CH + j;
+    out[i] = kernel[((long long)tap * (2 + kHidden) + ch) * kGates + col];
+  }
+}
+int cell_xdense_weights(const float* kernel, float* out, cudaStream_t stream) {
+  MVB_REQUIRE(kernel && out, "cell_xdense_weights: bad args");
+  xdense_weights_kernel<<<72, 256, 0, stream>>>(kernel, out);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,
                       float* Bt, float* T2, cudaStream_t stream) {
   MVB_REQUIRE(kernel && biases && We && be && Bt && T2 && E > 0, "cell_xfold_tables: bad args");
@@ -769,7 +817,7 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
              float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
-             int fanout, cudaStream_t stream) {
+             int fanout, cudaStream_t stream, const float* xr_in, const float* xr_W) {
   // planes = format of the inputs and weights | (format of hp_out << 8), the latter only when it differs
   const int P_out = (P >> 8) ? (P >> 8) : (P & 0xFF);
   P &= 0xFF;
@@ -832,6 +880,11 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   prm.abl = (abl & 16) ? (abl | 8) : abl;      // "load nothing" without "do not wait for data" would hang the issuer
   if (xf_B) {
     MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
+    prm.skip_x = 1;
+  }
+  prm.xr_in = xr_in; prm.xr_W = xr_W;
+  if (xr_W) {
+    MVB_REQUIRE(xr_in && !xf_B && !row_map && fanout <= 1, "cell_fwd: the dense x path needs its input and excludes x-fold, row maps and fan-out");
     prm.skip_x = 1;
   }
   prm.hp_mixed = P_out == kPlanesF16F8;

@@ -58,6 +58,12 @@ class ScaleWeights(object):
     fp = ops.PLANES_F16F8 if fast else planes
     self.enc_class = ops.PackedCell(f(nm["enc_class"][0]), f(nm["enc_class"][1]), fp)
     self.enc_reg = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), planes, comp=True)
+    # inference: regression encoder with the h block in f16f8 on the tensor cores and the raw 2-channel offsets
+    # (+-1.9e3 pixels) added in fp32 in the epilogue (ops.cell_fwd_xdense) - 2 passes instead of 3 and no x chunk
+    self.enc_reg_fast = self.enc_reg_xd = None
+    if fast and weights[nm["enc_reg"][0]].shape[2] == 2 + ops.HIDDEN:
+      self.enc_reg_fast = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), ops.PLANES_F16F8)
+      self.enc_reg_xd = ops.XDense(f(nm["enc_reg"][0]))
     # class decoder fed by the graph attention: f16f8 operands (2 instead of 3 bf16-pass equivalents per product)
     self.dec_class = ops.PackedCell(f(nm["dec_class"][0]), f(nm["dec_class"][1]),
                                     ops.PLANES_F16F8 if fast_class else planes)
@@ -202,6 +208,26 @@ class ConvRNNEngine(object):
     h, w = self.cfg.scene_grids[i]
     t_len, n = obs_reg_t.shape[0], obs_reg_t.shape[1]
     sw = self.scales[i]
+    if sw.enc_reg_fast is not None and os.environ.get("MVB_REG_XDENSE", "1") != "0":
+      pk = sw.enc_reg_fast
+      xh = self._xh("enc_reg_f", n, h, w, pk.cpad, ops.PLANES_F16F8)
+      c = [self._state("encr_c0", n, h, w), self._state("encr_c1", n, h, w)]
+      h32 = self._state("encr_h32", n, h, w)
+      xh[0][:, :, pk.cxp:].zero_()            # h_0 = 0 (the x blocks are never written nor read)
+      for t in range(t_len):
+        cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+        last = t == t_len - 1
+        if self.cell_events is None:
+          ops.cell_fwd_xdense(cur, pk, sw.enc_reg_xd, obs_reg_t[t], None if t == 0 else c[t % 2], c[(t + 1) % 2],
+                              h32 if last else None, xh_out if last else nxt, h, w, n)
+        else:
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record()
+          ops.cell_fwd_xdense(cur, pk, sw.enc_reg_xd, obs_reg_t[t], None if t == 0 else c[t % 2], c[(t + 1) % 2],
+                              h32 if last else None, xh_out if last else nxt, h, w, n)
+          e1.record()
+          self.cell_events.append(("enc_reg", (h, w, n), e0, e1))
+      return c[t_len % 2], h32
     xh = self._xh("enc_reg", n, h, w, sw.enc_reg.cpad)
     c = [self._state("encr_c0", n, h, w), self._state("encr_c1", n, h, w)]
     h32 = self._state("encr_h32", n, h, w)

@@ -143,6 +143,29 @@ def cell_fwd(xh, packed, c_in, c_out, h32_out, xh_next, h, w, ns, row_map=None,
             packed.cpad, _planes_arg(packed, xh_next), float(forget_bias), _stream())
 
 
+class XDense(object):
+  """fp32 weights [18, 1024] of the dense x path of a regression-encoder cell (mvb_cell_xdense_weights)."""
+
+  def __init__(self, kernel):
+    assert kernel.dim() == 4 and kernel.shape[2] == 2 + HIDDEN, "the dense x path is for 2-channel inputs"
+    self.W = torch.empty((18, 4 * HIDDEN), dtype=torch.float32, device=kernel.device)
+    _lib.call("mvb_cell_xdense_weights", _p(kernel.detach().float().contiguous()), _p(self.W), _stream())
+
+
+def cell_fwd_xdense(xh, packed, xdense, x_in, c_in, c_out, h32_out, xh_next, h, w, ns, forget_bias=1.0):
+  """One ConvLSTM step of the regression encoder: h block of `xh` through the tensor cores, the raw 2-channel input
+  x_in fp32 [ns,h,w,2] added in fp32 in the epilogue (mvb_convlstm_cell_fwd_xdense); the x block of xh is not read."""
+  assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
+  assert x_in.dtype == torch.float32 and x_in.is_contiguous() and x_in.numel() == ns * h * w * 2
+  if xh_next is not None:
+    stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
+  else:
+    stride, cpad_out, off = 0, 0, 0
+  _lib.call("mvb_convlstm_cell_fwd_xdense", _p(xh), _p(packed.w), _p(packed.bias), _p(x_in), _p(xdense.W), _p(c_in),
+            _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w, packed.cpad,
+            _planes_arg(packed, xh_next), float(forget_bias), _stream())
+
+
 class XFold(object):
   """Look-up tables that replace the embedded one-hot input of a class-decoder cell."""
 

@@ -116,6 +116,39 @@ def test_cell_large_input_needs_compensation(dev):
   assert rel(h_comp, g["h"]) < rel(h_plain, g["h"])
 
 
+@pytest.mark.parametrize("zero_c", [False, True])
+def test_cell_xdense_regression_encoder(dev, zero_c):
+  """The regression encoder's cell with its raw 2-channel input (pixel offsets of +-1.9e3) added in fp32 in the gate
+  epilogue and only the h block on the tensor cores, f16f8 (mvb_convlstm_cell_fwd_xdense): against the golden vectors
+  of the compensated-bf16 case, at the tight bar, and better than the plain two-plane path."""
+  from multiverse_b200 import ops
+  d = cases.cell_case("enc_reg_cx2"); g = gold("cell_enc_reg_cx2")
+  ns, h, w, cx = d["x"].shape
+  assert cx == 2 and float(np.abs(d["x"]).max()) > 1e3
+  pk = ops.PackedCell(T(d["kernel"], dev), T(d["biases"], dev), ops.PLANES_F16F8)
+  xd = ops.XDense(T(d["kernel"], dev))
+  xh = ops.alloc_xh(ns, h, w, pk.cpad, ops.PLANES_F16F8, dev)
+  xh2 = ops.alloc_xh(ns, h, w, pk.cpad, ops.PLANES_F16F8, dev)
+  ops.nhwc_to_planes(T(d["h"], dev), xh, pk.cxp, h, w)              # the x block stays zero: it is not read
+  c_in = ops.alloc_state(ns, h, w, dev)
+  ops.nhwc_to_halo(T(d["c"], dev), c_in, h, w)
+  c_out = ops.alloc_state(ns, h, w, dev); h_out = ops.alloc_state(ns, h, w, dev)
+  ops.cell_fwd_xdense(xh, pk, xd, T(d["x"], dev), None if zero_c else c_in, c_out, h_out, xh2, h, w, ns)
+  co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
+  ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
+  gc, gh = (g["c_zero"], g["h_zero"]) if zero_c else (g["c"], g["h"])
+  ec, eh = rel(co.cpu().numpy(), gc), rel(ho.cpu().numpy(), gh)
+  print("xdense regression-encoder cell: rel err c %.2e h %.2e" % (ec, eh))
+  assert ec < TIGHT and eh < TIGHT
+  vals, _ = ops.operand_values(xh2)
+  hp = vals[:, pk.cxp:].reshape(ns, h + 1, w + 1, 256)
+  assert np.abs(hp[:, :h, :w].cpu().numpy() - ho.cpu().numpy()).max() < 1e-5
+  assert float(hp[:, h].abs().max()) == 0.0 and float(hp[:, :, w].abs().max()) == 0.0
+  if not zero_c:
+    _, h_plain, _ = run_cell(d, dev, 2, comp=False)
+    assert eh < rel(h_plain, g["h"])
+
+
 def test_cell_is_deterministic_and_batch_separable(dev):
   d = cases.cell_case("tile_edge")
   c_a, h_a, _ = run_cell(d, dev, 2)
