@@ -346,6 +346,45 @@ def to_dev(feeds, dev):
               grid_obs_regress=[T(a, dev) for a in feeds["grid_obs_regress"]])
 
 
+def test_full_size_batch_is_its_shards(dev):
+  """BASELINE.json's full configuration (K=20 diverse beam, 512 trajectories of 36x18, obs 8 -> pred 12 = 10 240 beam
+  rows per step, the size bench.py times) through a size-independent property: every trajectory's outputs inside the
+  full batch are bit-identical to its outputs inside a 16-trajectory shard (synthetic.shard_feeds, what a rank of a
+  32-way split would hold) - rows never mix, whatever the tile, CTA-pair and launch-order assignment - plus the
+  properties of a rollout that need no oracle: ids inside the grid, log-probabilities non-increasing along the beams,
+  the first beam's logits are the fetched class map."""
+  from multiverse_b200 import synthetic
+  from multiverse_b200.engine import ConvRNNEngine
+  n = 512
+  cfg = synthetic.make_config(batch_size=n, use_grids=[True, False], use_beam_search=True, beam_size=20,
+                              diverse_beam=True, diverse_gamma=0.01, fix_num_timestep=1)
+  w = synthetic.make_weights(cfg, 1)
+  full = synthetic.make_feeds(cfg, n, 1)
+  eng = ConvRNNEngine(cfg, {k: torch.from_numpy(v) for k, v in w.items()}, dev, 2)
+  out = eng.forward(to_dev(full, dev))
+  lg, ids, lp = [t.clone() for t in out["beam_outputs"]]
+  dec, reg = out["grid_pred_decoded"][0].clone(), out["grid_pred_reg_decoded"][0].clone()
+  assert lg.shape == (n, 20, 12, 648) and ids.shape == (n, 20, 12) and lp.shape == (n, 20)
+  assert int(ids.min()) >= 0 and int(ids.max()) < 648
+  assert bool(torch.isfinite(lg).all()) and bool(torch.isfinite(reg).all())
+  assert bool((lp[:, :-1] >= lp[:, 1:]).all())                       # beams come out best first
+  assert torch.equal(dec.reshape(n, 12, 648), lg[:, 0])              # :799-803
+  assert {(16, True)} <= ops_variants()
+  world = 32
+  for rank in (0, 13, 31):
+    shard = synthetic.shard_feeds(full, rank, world)
+    part = eng.forward(to_dev(shard, dev))
+    lo, hi = rank * (n // world), (rank + 1) * (n // world)
+    for a, b in zip(part["beam_outputs"], (lg, ids, lp)):
+      assert torch.equal(a, b[lo:hi])
+    assert torch.equal(part["grid_pred_reg_decoded"][0], reg[lo:hi])
+
+
+def ops_variants():
+  from multiverse_b200 import ops
+  return ops.cell_variants_seen()
+
+
 @pytest.mark.parametrize("name", sorted(cases.ROLLOUTS))
 def test_rollout_golden(dev, name):
   """Whole forward (scene CNN -> encoders -> decoders) against the oracle's fp64 rollouts:
