@@ -112,6 +112,20 @@ int mvb_convlstm_cell_fwd_xdense(const void* xh_planes, const void* w_planes, co
                                  float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
                                  int64_t NS, int H, int W, int cpad, int planes, float forget_bias, void* stream);
 int mvb_cell_xdense_weights(const float* kernel_tf, float* x_weights, void* stream);
+/* The cell of the class encoder (code/pred_models.py:189-195, :210-215), whose 64-channel input scene_conv (.) one_hot
+ * is non-zero at ONE cell per sample row: instead of spending a K chunk of the GEMM on it, mvb_cell_xsparse_table
+ * forms per sample row the nine products  x_table[s][tap][:] = scene_conv[frame_idx[s]][label[s]][:] . W[tap][:64][:]
+ * (fp32; x_weights fp32 [9*64][1024] from mvb_cell_xsparse_weights(kernel_tf, 64, ...), packed column order) and the
+ * gate epilogue adds row `tap = label - p` of it to the <= 9 cells p around the label (labels outside [0,HW) add
+ * nothing, like mvb_enc_class_input).  The x block of xh_planes is not read.  Other arguments as
+ * mvb_convlstm_cell_fwd. */
+int mvb_convlstm_cell_fwd_xsparse(const void* xh_planes, const void* w_planes, const float* bias_packed,
+                                  const float* x_table, const int32_t* label, const float* c_in, float* c_out,
+                                  float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
+                                  int64_t NS, int H, int W, int cpad, int planes, float forget_bias, void* stream);
+int mvb_cell_xsparse_weights(const float* kernel_tf, int cx, float* x_weights, void* stream);
+int mvb_cell_xsparse_table(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                           const float* x_weights, float* x_table, int64_t NS, int H, int W, void* stream);
 
 /* First K-row step of the beam decoder (pred_models.py:611-666 right after the first selection): the K = fanout
  * children of a sample share their parent - the same graph-attended h and the same c - and differ only in the

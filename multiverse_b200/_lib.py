@@ -29,6 +29,10 @@ SIGNATURES = {
     "mvb_convlstm_cell_fwd_xdense": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
                                      _i, _i, _f, _vp],
     "mvb_cell_xdense_weights": [_vp, _vp, _vp],
+    "mvb_convlstm_cell_fwd_xsparse": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i,
+                                      _i, _i, _f, _vp],
+    "mvb_cell_xsparse_weights": [_vp, _i, _vp, _vp],
+    "mvb_cell_xsparse_table": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "mvb_convlstm_cell_fwd_onehot_fanout": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
     "mvb_convlstm_cell_fwd_onehot": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64,
                                      _i, _i, _i, _i, _f, _vp],

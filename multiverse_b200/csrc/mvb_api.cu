@@ -112,7 +112,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 const char* mvb_last_error(void) { return get_error(); }
-int mvb_abi_version(void) { return 10; }
+int mvb_abi_version(void) { return 11; }
 int mvb_cell_last_variant(void) { return cell_last_variant(); }
 long long mvb_cell_variants_seen(int reset) { return (long long)cell_variants_seen(reset); }
 long long mvb_launch_count(void) { return g_launches; }
@@ -158,6 +158,22 @@ int mvb_convlstm_cell_fwd_xdense(const void* xh_planes, const void* w_planes, co
 }
 int mvb_cell_xdense_weights(const float* kernel_tf, float* x_weights, void* stream) {
   return cell_xdense_weights(kernel_tf, x_weights, S(stream));
+}
+int mvb_convlstm_cell_fwd_xsparse(const void* xh_planes, const void* w_planes, const float* bias_packed,
+                                  const float* x_table, const int32_t* label, const float* c_in, float* c_out,
+                                  float* h32_out, void* hp_out, int64_t hp_plane_stride, int cpad_out, int ch_off_out,
+                                  int64_t NS, int H, int W, int cpad, int planes, float forget_bias, void* stream) {
+  MVB_REQUIRE(x_table && label, "mvb_convlstm_cell_fwd_xsparse: null table / labels");
+  return cell_fwd(xh_planes, w_planes, bias_packed, c_in, nullptr, c_out, h32_out, hp_out, hp_plane_stride, cpad_out,
+                  ch_off_out, NS, H, W, cpad, planes, forget_bias, nullptr, nullptr, nullptr, nullptr, 1, S(stream),
+                  nullptr, nullptr, x_table, label);
+}
+int mvb_cell_xsparse_weights(const float* kernel_tf, int cx, float* x_weights, void* stream) {
+  return cell_xsparse_weights(kernel_tf, cx, x_weights, S(stream));
+}
+int mvb_cell_xsparse_table(const float* scene_conv, const int32_t* frame_idx, const int32_t* label,
+                           const float* x_weights, float* x_table, int64_t NS, int H, int W, void* stream) {
+  return cell_xsparse_table(scene_conv, frame_idx, label, x_weights, x_table, NS, H, W, S(stream));
 }
 int mvb_convlstm_cell_fwd_onehot_fanout(const void* xh_planes, const void* w_planes, const float* table_B,
                                         const float* table_T2, const int32_t* ids, const float* c_in,

@@ -84,6 +84,10 @@ struct CellParams {
   int skip_x;               // x-fold: the x chunk of the K loop is skipped
   // dense raw x block of two channels, added in fp32 in the epilogue instead of going through the tensor cores
   // (regression encoder: the +-1.9e3 pixel offsets need all 24 bits, which neither operand format carries in 2 passes):
+  // sparse x block (class encoder: scene features at ONE cell per sample row): per-sample table rows
+  // xs_tab[sample][tap][1024] = features(label cell) . W[tap], added to the <= 9 cells around the label
+  const float* xs_tab;      // [NS, 9, 1024] fp32 packed column order, or nullptr
+  const int* xs_label;      // [NS]
   const float* xr_in;       // [NS, H, W, 2] fp32 NHWC (no halo), or nullptr
   const float* xr_W;        // [9 taps * 2 channels][1024] fp32, packed column order
   int order;                // work order, see work_index()
@@ -440,6 +444,14 @@ cell_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else if (valid) {
           const float* bptr = (xfb ? xfb : prm.bias) + nt * BLOCK_N + j0;
           const float* xft = prm.xf_B ? xft_of(prm.xf_ids[psmp]) : nullptr;
+          if (prm.xs_tab) {          // out[p] += in[p + off(tap)] . W[tap] with the input at the label cell only
+            const int l = prm.xs_label[psmp];
+            if (l >= 0 && l < g.H * g.W) {
+              const int ly = l / g.W, dy = ly - py, dx = (l - ly * g.W) - px;
+              if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1)
+                xft = prm.xs_tab + ((long long)psmp * 9 + (dy + 1) * 3 + (dx + 1)) * kGates;
+            }
+          }
           const float* tptr = xft ? xft + nt * BLOCK_N + j0 : nullptr;
           const float* sptr = FMT == 1 ? prm.col_scale + nt * BLOCK_N + j0 : bptr;
           float cn[16], hn[16];
@@ -735,6 +747,68 @@ int cell_xdense_weights(const float* kernel, float* out, cudaStream_t stream) {
   return MVB_OK;
 }
 
+// weights of the sparse x path: rows (tap, channel) of the x block of the TF kernel [3,3,cx+256,1024], packed columns
+__global__ void xsparse_weights_kernel(const float* __restrict__ kernel, int cx, float* __restrict__ out) {
+  const long long total = 9ll * cx * kGates;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % kGates);
+    const long long k = i / kGates;
+    const int tap = (int)(k / cx), ch = (int)(k % cx);
+    const int tile = n / BLOCK_N, gate = (n % BLOCK_N) / TILE_CH, j = n % TILE_CH;
+    const int col = gate * kHidden + tile * TILE_CH + j;
+    out[i] = kernel[((long long)tap * (cx + kHidden) + ch) * kGates + col];
+  }
+}
+int cell_xsparse_weights(const float* kernel, int cx, float* out, cudaStream_t stream) {
+  MVB_REQUIRE(kernel && out && cx > 0, "cell_xsparse_weights: bad args");
+  xsparse_weights_kernel<<<sm_count() * 4, 256, 0, stream>>>(kernel, cx, out);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
+// xs_tab[s][tap][n] = sum_ch feat[frame[s]][label[s]][ch] * Wx[tap][ch][n]   (64 scene channels).
+// One block per (tap, 256-column tile, sample chunk): the weight tile [64][256] sits in shared memory, thread = column.
+__global__ void __launch_bounds__(256)
+xsparse_table_kernel(const float* __restrict__ scene_conv, const int* __restrict__ frame_idx,
+                     const int* __restrict__ label, const float* __restrict__ Wx, float* __restrict__ tab,
+                     long long NS, int hw, int chunks) {
+  extern __shared__ float wsm[];                      // [64][256]
+  const int tap = blockIdx.x / N_TILES, nt = blockIdx.x % N_TILES;
+  for (int i = threadIdx.x; i < 64 * 256; i += 256)
+    wsm[i] = Wx[((long long)tap * 64 + i / 256) * kGates + nt * 256 + (i % 256)];
+  __syncthreads();
+  const int col = threadIdx.x;
+  for (long long s = blockIdx.y; s < NS; s += chunks) {
+    const int l = label[s];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (l >= 0 && l < hw) {
+      const float4* f4 = reinterpret_cast<const float4*>(scene_conv + ((long long)frame_idx[s] * hw + l) * 64);
+#pragma unroll 4
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 f = __ldg(f4 + c4);              // warp-uniform
+        acc[0] = fmaf(f.x, wsm[(4 * c4 + 0) * 256 + col], acc[0]);
+        acc[1] = fmaf(f.y, wsm[(4 * c4 + 1) * 256 + col], acc[1]);
+        acc[2] = fmaf(f.z, wsm[(4 * c4 + 2) * 256 + col], acc[2]);
+        acc[3] = fmaf(f.w, wsm[(4 * c4 + 3) * 256 + col], acc[3]);
+      }
+    }
+    tab[(s * 9 + tap) * kGates + nt * 256 + col] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+}
+int cell_xsparse_table(const float* scene_conv, const int* frame_idx, const int* label, const float* Wx, float* tab,
+                       long long NS, int H, int W, cudaStream_t stream) {
+  MVB_REQUIRE(scene_conv && frame_idx && label && Wx && tab && NS > 0, "cell_xsparse_table: bad args");
+  static SmemOptIn opt;
+  MVB_CHECK_CUDA(smem_opt_in(opt, xsparse_table_kernel, 64 * 256 * (int)sizeof(float)));
+  const int chunks = (int)(NS < 8 ? NS : 8);
+  xsparse_table_kernel<<<dim3(9 * N_TILES, chunks), 256, 64 * 256 * sizeof(float), stream>>>(
+      scene_conv, frame_idx, label, Wx, tab, NS, H * W, chunks);
+  MVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
+  return MVB_OK;
+}
+
 int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,
                       float* Bt, float* T2, cudaStream_t stream) {
   MVB_REQUIRE(kernel && biases && We && be && Bt && T2 && E > 0, "cell_xfold_tables: bad args");
@@ -817,7 +891,8 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              const int* row_map, float* c_out, float* h32_out, void* hp_out, long long hp_plane_stride,
              int cpad_out, int ch_off_out, long long NS, int H, int W, int cpad, int P,
              float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2, const int* xf_ids,
-             int fanout, cudaStream_t stream, const float* xr_in, const float* xr_W) {
+             int fanout, cudaStream_t stream, const float* xr_in, const float* xr_W, const float* xs_tab,
+             const int* xs_label) {
   // planes = format of the inputs and weights | (format of hp_out << 8), the latter only when it differs
   const int P_out = (P >> 8) ? (P >> 8) : (P & 0xFF);
   P &= 0xFF;
@@ -880,6 +955,11 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
   prm.abl = (abl & 16) ? (abl | 8) : abl;      // "load nothing" without "do not wait for data" would hang the issuer
   if (xf_B) {
     MVB_REQUIRE(xf_T2 && xf_ids && H >= 3 && W >= 3, "cell_fwd: x-fold needs its tables, ids and a grid of at least 3x3");
+    prm.skip_x = 1;
+  }
+  prm.xs_tab = xs_tab; prm.xs_label = xs_label;
+  if (xs_tab) {
+    MVB_REQUIRE(xs_label && !xf_B && !xr_W && !row_map && fanout <= 1, "cell_fwd: the sparse x path needs its labels and excludes x-fold, the dense x path, row maps and fan-out");
     prm.skip_x = 1;
   }
   prm.xr_in = xr_in; prm.xr_W = xr_W;

@@ -13,8 +13,11 @@ int cell_fwd(const void* xh_planes, const void* w_planes, const float* bias, con
              long long hp_plane_stride, int cpad_out, int ch_off_out, long long NS, int H, int W,
              int cpad, int P, float forget_bias, float* gates_out, const float* xf_B, const float* xf_T2,
              const int* xf_ids, int fanout, cudaStream_t stream, const float* xr_in = nullptr,
-             const float* xr_W = nullptr);
+             const float* xr_W = nullptr, const float* xs_tab = nullptr, const int* xs_label = nullptr);
 int cell_xdense_weights(const float* kernel, float* out, cudaStream_t stream);
+int cell_xsparse_weights(const float* kernel, int cx, float* out, cudaStream_t stream);
+int cell_xsparse_table(const float* scene_conv, const int* frame_idx, const int* label, const float* Wx, float* tab,
+                       long long NS, int H, int W, cudaStream_t stream);
 int cell_last_variant();
 unsigned long long cell_variants_seen(int reset);
 int cell_xfold_tables(const float* kernel, const float* biases, const float* We, const float* be, int E,

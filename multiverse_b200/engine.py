@@ -60,6 +60,11 @@ class ScaleWeights(object):
     self.enc_reg = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), planes, comp=True)
     # inference: regression encoder with the h block in f16f8 on the tensor cores and the raw 2-channel offsets
     # (+-1.9e3 pixels) added in fp32 in the epilogue (ops.cell_fwd_xdense) - 2 passes instead of 3 and no x chunk
+    # inference: class encoder with its one-cell scene-feature input added from per-sample table rows in the epilogue
+    # (ops.cell_fwd_xsparse) instead of a K chunk of the GEMM
+    self.enc_class_xs = None
+    if fast and weights[nm["enc_class"][0]].shape[2] == 64 + ops.HIDDEN:
+      self.enc_class_xs = ops.XSparse(f(nm["enc_class"][0]))
     self.enc_reg_fast = self.enc_reg_xd = None
     if fast and weights[nm["enc_reg"][0]].shape[2] == 2 + ops.HIDDEN:
       self.enc_reg_fast = ops.PackedCell(f(nm["enc_reg"][0]), f(nm["enc_reg"][1]), ops.PLANES_F16F8)
@@ -190,6 +195,25 @@ class ConvRNNEngine(object):
     xh = self._xh("enc_class", n, h, w, sw.enc_class.cpad, self.fast_planes)
     c = [self._state("enc_c0", n, h, w), self._state("enc_c1", n, h, w)]
     h32 = self._state("enc_h32", n, h, w)
+    if sw.enc_class_xs is not None and os.environ.get("MVB_ENC_XSPARSE", "1") != "0":
+      # (one table per scale: the chains of different scales run concurrently under forward_graph)
+      table = self._buf(("enc_class_xtab", n, h, w), lambda: torch.empty((n, 9, 4 * ops.HIDDEN), dtype=torch.float32,
+                                                                  device=self.device))
+      xh[0][:, :, sw.enc_class.cxp:].zero_()   # h_0 = 0 (the x blocks are neither written nor read)
+      for t in range(t_len):
+        cur, nxt = xh[t % 2], xh[(t + 1) % 2]
+        last = t == t_len - 1
+        ops.cell_xsparse_table(scene_conv, obs_scene_t[t], labels_t[t], sw.enc_class_xs, table, h, w)
+        ev = None
+        if self.cell_events is not None:
+          ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          ev[0].record()
+        ops.cell_fwd_xsparse(cur, sw.enc_class, table, labels_t[t], None if t == 0 else c[t % 2], c[(t + 1) % 2],
+                             h32 if last else None, xh_out if last else nxt, h, w, n)
+        if ev is not None:
+          ev[1].record()
+          self.cell_events.append(("enc_class", (h, w, n), ev[0], ev[1]))
+      return c[t_len % 2], h32
     # a previous call left the label pixels of its last two steps in the x blocks: clear them
     for j in range(2):
       xh[j][:, :, :sw.enc_class.cxp].zero_()

@@ -166,6 +166,34 @@ def cell_fwd_xdense(xh, packed, xdense, x_in, c_in, c_out, h32_out, xh_next, h, 
             _planes_arg(packed, xh_next), float(forget_bias), _stream())
 
 
+class XSparse(object):
+  """fp32 weights [9 * 64, 1024] of the sparse x path of a class-encoder cell (mvb_cell_xsparse_weights)."""
+
+  def __init__(self, kernel):
+    assert kernel.dim() == 4 and kernel.shape[2] == 64 + HIDDEN, "the sparse x path is for the 64 scene channels"
+    self.W = torch.empty((9 * 64, 4 * HIDDEN), dtype=torch.float32, device=kernel.device)
+    _lib.call("mvb_cell_xsparse_weights", _p(kernel.detach().float().contiguous()), 64, _p(self.W), _stream())
+
+
+def cell_xsparse_table(scene_conv, frame_idx, label, xsparse, table, h, w):
+  """table fp32 [ns, 9, 1024] <- the nine x products of every sample row (features at its label cell)."""
+  _lib.call("mvb_cell_xsparse_table", _p(scene_conv), _p(frame_idx), _p(label), _p(xsparse.W), _p(table),
+            label.shape[0], h, w, _stream())
+
+
+def cell_fwd_xsparse(xh, packed, table, label, c_in, c_out, h32_out, xh_next, h, w, ns, forget_bias=1.0):
+  """One ConvLSTM step of the class encoder: h block of `xh` through the tensor cores, the one-cell scene-feature
+  input added from `table` (cell_xsparse_table) in the epilogue; the x block of xh is not read."""
+  assert xh.shape[2] == packed.cpad and planes_of(xh) == packed.planes
+  if xh_next is not None:
+    stride, cpad_out, off = xh_next.stride(0), xh_next.shape[2], xh_next.shape[2] - HIDDEN
+  else:
+    stride, cpad_out, off = 0, 0, 0
+  _lib.call("mvb_convlstm_cell_fwd_xsparse", _p(xh), _p(packed.w), _p(packed.bias), _p(table), _p(label), _p(c_in),
+            _p(c_out), _p(h32_out), _p(xh_next), stride, cpad_out, off, ns, h, w, packed.cpad,
+            _planes_arg(packed, xh_next), float(forget_bias), _stream())
+
+
 class XFold(object):
   """Look-up tables that replace the embedded one-hot input of a class-decoder cell."""
 

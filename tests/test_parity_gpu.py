@@ -6,6 +6,8 @@ Bars (BASELINE.json north_star): arg-max / beam ids bit-exact, (h,c) and offsets
 (measured as max|diff| / max|ref| per tensor)."""
 import os
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -147,6 +149,52 @@ def test_cell_xdense_regression_encoder(dev, zero_c):
   if not zero_c:
     _, h_plain, _ = run_cell(d, dev, 2, comp=False)
     assert eh < rel(h_plain, g["h"])
+
+
+def test_cell_xsparse_class_encoder(dev):
+  """The class encoder's cell with its one-cell scene-feature input taken out of the GEMM: per-sample table rows
+  (mvb_cell_xsparse_table) added by the epilogue to the cells around the label (mvb_convlstm_cell_fwd_xsparse), against
+  the ordinary path on the same inputs (x block = features at the label cell, through the tensor cores) and against
+  the oracle cell.  Labels on the border, in a corner and out of range included."""
+  from multiverse_b200 import ops
+  rng = np.random.default_rng(12)
+  ns, h, w, cx = 5, 6, 5, 64
+  lim = math.sqrt(6.0 / (9 * (cx + 256) + 9 * 4 * 256))
+  kernel = rng.uniform(-lim, lim, size=(3, 3, cx + 256, 1024)).astype(np.float32)
+  biases = (rng.standard_normal(1024) * 0.1).astype(np.float32)
+  conv = np.tanh(rng.standard_normal((7, h * w, 64))).astype(np.float32)          # 7 frames
+  frames = np.array([3, 0, 6, 3, 1], dtype=np.int32)
+  labels = np.array([0, h * w - 1, 2 * w + 2, w - 1, -1], dtype=np.int32)          # corner, corner, interior, edge, none
+  hh = np.tanh(rng.standard_normal((ns, h, w, 256))).astype(np.float32)
+  cc = rng.standard_normal((ns, h, w, 256)).astype(np.float32)
+  x = np.zeros((ns, h, w, 64), dtype=np.float32)
+  for s_ in range(ns):
+    if labels[s_] >= 0:
+      x[s_].reshape(h * w, 64)[labels[s_]] = conv[frames[s_], labels[s_]]
+  c_ref, h_ref = R.convlstm_cell(x.astype(np.float64), cc.astype(np.float64), hh.astype(np.float64),
+                                 kernel.astype(np.float64), biases.astype(np.float64))
+  pk = ops.PackedCell(T(kernel, dev), T(biases, dev), ops.PLANES_F16F8)
+  xs = ops.XSparse(T(kernel, dev))
+  xh = ops.alloc_xh(ns, h, w, pk.cpad, ops.PLANES_F16F8, dev)
+  ops.nhwc_to_planes(T(hh, dev), xh, pk.cxp, h, w)
+  c_in = ops.alloc_state(ns, h, w, dev); ops.nhwc_to_halo(T(cc, dev), c_in, h, w)
+  c_out = ops.alloc_state(ns, h, w, dev); h_out = ops.alloc_state(ns, h, w, dev)
+  table = torch.empty((ns, 9, 1024), device=dev)
+  ops.cell_xsparse_table(T(conv, dev), T(frames, dev), T(labels, dev), xs, table, h, w)
+  ops.cell_fwd_xsparse(xh, pk, table, T(labels, dev), c_in, c_out, h_out, None, h, w, ns)
+  co = torch.empty((ns, h, w, 256), device=dev); ho = torch.empty((ns, h, w, 256), device=dev)
+  ops.halo_to_nhwc(c_out, co, h, w); ops.halo_to_nhwc(h_out, ho, h, w)
+  ec, eh = rel(co.cpu().numpy(), c_ref), rel(ho.cpu().numpy(), h_ref)
+  print("xsparse class-encoder cell: rel err c %.2e h %.2e" % (ec, eh))
+  assert ec < TIGHT and eh < TIGHT
+  # the table itself against numpy
+  want = np.zeros((ns, 9, 1024))
+  for s_ in range(ns):
+    if labels[s_] >= 0:
+      for tap in range(9):
+        want[s_, tap] = conv[frames[s_], labels[s_]].astype(np.float64) @ kernel[tap // 3, tap % 3, :64].astype(np.float64)
+  perm = np.array([g_ * 256 + t_ * 64 + j_ for t_ in range(4) for g_ in range(4) for j_ in range(64)])   # packed column order
+  assert rel(table.cpu().numpy(), want[:, :, perm]) < 1e-5
 
 
 def test_cell_is_deterministic_and_batch_separable(dev):
