@@ -15,7 +15,6 @@ as opaque activation tokens (pred_utils.py:86-94)."""
 from __future__ import annotations
 
 import contextlib
-import glob
 import os
 import types
 
