@@ -113,6 +113,13 @@ class ConvRNNEngine(object):
     self._graphs = {}         # forward_graph(): feed signature -> (CUDAGraph, static feeds, static outputs)
     self._graph_seen = set()  # signatures seen once (captured at their second occurrence)
 
+  @property
+  def gnn_scene_in_greedy(self):
+    """False = SimAug's model variant: its gnn_edge (SimAug/code/pred_models.py:1213-1226) concatenates the scene
+    features to the node features only under `if tile_to_beam:`, so the greedy class decoder (training, test.py)
+    attends over h alone; the Multiverse file (code/pred_models.py:824-838) always uses them (default)."""
+    return bool(getattr(self.cfg, "gnn_scene_in_greedy", True))
+
   # ------------------------------------------------------------------ weights
   def set_weights(self, weights):
     dev = self.device
@@ -279,7 +286,7 @@ class ConvRNNEngine(object):
     for t in range(pred_len):
       cur, nxt = xh[t % 2], xh[(t + 1) % 2]
       if cfg.use_gnn:
-        ops.gnn_attend_fwd(h_src, scene_mean, cur, h, w, n)
+        ops.gnn_attend_fwd(h_src, scene_mean if self.gnn_scene_in_greedy else None, cur, h, w, n)
       # (no attention: the planes of the previous h already sit in cur's h block)
       # the embedded one_hot(ids_prev) input is folded into table look-ups: nobody writes the x block
       self._cell_onehot("dec_class", cur, sw.dec_class, sw.dec_class_xf, ids_prev, c_src, c[(t + 1) % 2],

@@ -644,6 +644,10 @@ def _engine_config(config):
   for k, default in (("grid_loss_weight", 1.0), ("grid_reg_loss_weight", 0.1), ("wd", 0.0),
                      ("clip_gradient_norm", None), ("is_train", False), ("optimizer", "adadelta")):
     d[k] = getattr(config, k, default)
+  # SimAug's pred_models.py differs from Multiverse's in one line of gnn_edge (scene features only under
+  # tile_to_beam): a config that carries SimAug's flags selects that variant unless it says otherwise
+  simaug = any(hasattr(config, k) for k in ("multiview_train", "adv_train"))
+  d["gnn_scene_in_greedy"] = bool(getattr(config, "gnn_scene_in_greedy", not simaug))
   for flag in ("use_single_decoder", "use_teacher_forcing"):
     if getattr(config, flag, False):
       raise NotImplementedError("--%s is not implemented (no published config uses it)" % flag)

@@ -6,7 +6,11 @@ attributes (``adv_epsilon, adv_step_size, adv_num_iter, adv_start_from_clean_pro
 mixup_alpha, mixup_mix_adv, use_grids, scene_grids``) - with the reference's ``model_func`` + ``tf.gradients(
 classification_loss, adv_input)`` replaced by ``TrainEngine.loss_and_grads(dscene_out=...)``: the ordinary BPTT of
 this library with the scene CNN's input gradient switched on (``mvb_scene_conv_bwd`` ``din`` of the first
-convolution).  The update itself is ``mvb_adv_step`` / ``mvb_mix``.  Random draws (start noise, random target
+convolution).  The update itself is ``mvb_adv_step`` / ``mvb_mix``.  SimAug's model differs from Multiverse's in one place that matters here: its ``gnn_edge`` (:1213-1226) uses the scene
+features only in the beam decoder, so the training tower's graph attention runs over h alone - build the TrainEngine
+with ``cfg.gnn_scene_in_greedy = False`` (the drop-in Model does it for configs that carry SimAug's flags).  Pinned
+on an execution of the reference file (oracle/tf1_eager/run_simaug.py, tests/golden/simaug_multiview.npz).
+Random draws (start noise, random target
 offsets, the Beta mixup weight) come from a numpy Generator - TensorFlow's random streams cannot be reproduced.
 
 ``multiview_augmentation`` (:346-541; second part of row f-4) runs the same one-step attack on the batch tiled

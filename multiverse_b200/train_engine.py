@@ -138,7 +138,7 @@ class TrainEngine(ConvRNNEngine):
       h_prev = h32_last if t == 0 else h32[t - 1]
       c_prev = S["c_ec"][T - 1] if t == 0 else c[t - 1]
       if cfg.use_gnn:
-        ops.gnn_attend_fwd(h_prev, means[i], xh_dc[t], h, w, n)
+        ops.gnn_attend_fwd(h_prev, means[i] if self.gnn_scene_in_greedy else None, xh_dc[t], h, w, n)
       last = t == Tp - 1
       ops.cell_fwd_train(xh_dc[t], sw.dec_class, c_prev, c[t], h32[t],
                          None if (cfg.use_gnn or last) else xh_dc[t + 1], g[t], h, w, n)
@@ -247,7 +247,10 @@ class TrainEngine(ConvRNNEngine):
       gout = dxh[:, sw.dec_class.cxp:].contiguous()
       if cfg.use_gnn:
         h_prev = S["h32_ec"] if t == 0 else S["h32_dc"][t - 1]
-        ops.gnn_bwd(h_prev, means[i], gout, work, dh, False, dsm, h, w, n)
+        if self.gnn_scene_in_greedy:
+          ops.gnn_bwd(h_prev, means[i], gout, work, dh, False, dsm, h, w, n)
+        else:
+          ops.gnn_bwd(h_prev, None, gout, work, dh, False, None, h, w, n)
       else:
         dh.copy_(gout)
     # ---- class encoder
@@ -261,7 +264,8 @@ class TrainEngine(ConvRNNEngine):
                                     dconv[i], h, w)
       if t > 0:
         dh.copy_(dxh[:, sw.enc_class.cxp:])
-    ops.scene_time_mean_bwd(dsm, feeds["obs_scene"].to(torch.int32).contiguous(), dconv[i])
+    if self.gnn_scene_in_greedy:
+      ops.scene_time_mean_bwd(dsm, feeds["obs_scene"].to(torch.int32).contiguous(), dconv[i])
     # ---- regression decoder
     We, be = sw.emb_reg
     dc = None

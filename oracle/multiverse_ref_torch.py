@@ -244,8 +244,12 @@ def _forward(cfg, w, feeds, dtype):
       out["beam_outputs"] = [lg.numpy(), ids.numpy().astype(np.int32), sc.numpy()]   # no_grad only
       dec = lg[:, 0].reshape(n, cfg.pred_len, h, ww, 1)
     else:
+      # SimAug/code/pred_models.py:1213-1226 concatenates the scene features to the node features only under
+      # `if tile_to_beam:` - in SimAug's model the greedy decoder's attention sees h alone (cfg.gnn_scene_in_greedy
+      # False); the Multiverse file (code/pred_models.py:824-838) always uses them
+      sm_greedy = scene_mean if getattr(cfg, "gnn_scene_in_greedy", True) else None
       dec = decoder_greedy(onehot[:, -1], enc, cfg.pred_len, sw.dec_class, sw.emb_class,
-                           sw.head_class, scene_mean, mask, cfg.use_gnn, True)
+                           sw.head_class, sm_greedy, mask, cfg.use_gnn, True)
     reg = decoder_greedy(obs_reg[:, -1], enc_r, cfg.pred_len, sw.dec_reg, sw.emb_reg, sw.head_reg,
                          None, None, False, False)
     out["grid_pred_decoded"].append(dec)

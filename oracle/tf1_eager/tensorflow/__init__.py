@@ -249,6 +249,7 @@ class Tensor(object):
   def __floordiv__(self, o): return self._bin(o, lambda a, b: torch.div(a, b, rounding_mode="floor"))
   def __mod__(self, o): return self._bin(o, torch.remainder)
   def __neg__(self): return Tensor(-self.t)
+  def __pow__(self, o): return self._bin(o, torch.pow)
   def __ge__(self, o): return self._bin(o, torch.ge)
   def __gt__(self, o): return self._bin(o, torch.gt)
   def __le__(self, o): return self._bin(o, torch.le)
@@ -286,6 +287,9 @@ class _State(object):
     self.feed = None             # callable(index, name, dtype, shape) -> array, or None = probe
     self.requires_grad = False
     self.rng = np.random.default_rng(0)
+    # SimAug's random draws are injected by the harness (TF's streams cannot be reproduced):
+    self.beta_sample = None      # value of tf.distributions.Beta(...).sample()
+    self.uniform_hook = None     # callable(shape, minval, maxval, dtype) -> array for tf.random_uniform / tf.random.uniform
 
 
 _S = _State()
@@ -409,8 +413,11 @@ def placeholder(dtype, shape=None, name=None):
     _S.placeholders.append(t)
     return t
   val = _S.feed(idx, name, dtype, shape)
-  t = torch.from_numpy(np.ascontiguousarray(val)) if isinstance(val, np.ndarray) else torch.tensor(val)
-  t = t.to(_torch_dtype(dtype))
+  if isinstance(val, torch.Tensor):      # fed as is: tf.gradients(loss, <tensor computed from this placeholder>)
+    t = val
+  else:
+    t = torch.from_numpy(np.ascontiguousarray(val)) if isinstance(val, np.ndarray) else torch.tensor(val)
+    t = t.to(_torch_dtype(dtype))
   if shape is not None:
     want = [None if s is None else _int(s) for s in shape]
     assert len(want) == t.dim() and all(w is None or w == g for w, g in zip(want, t.shape)), \
@@ -628,6 +635,11 @@ def matmul(a, b, transpose_a=False, transpose_b=False, name=None):
 
 
 def clip_by_value(t, lo, hi, name=None):
+  if isinstance(lo, (Tensor, torch.Tensor)) or isinstance(hi, (Tensor, torch.Tensor)):
+    x = _raw(t)        # tensor bounds (SimAug/code/pred_models.py:404-408): min(max(t, lo), hi)
+    lo_t = _raw(lo) if isinstance(lo, (Tensor, torch.Tensor)) else torch.as_tensor(lo, dtype=x.dtype)
+    hi_t = _raw(hi) if isinstance(hi, (Tensor, torch.Tensor)) else torch.as_tensor(hi, dtype=x.dtype)
+    return Tensor(torch.minimum(torch.maximum(x, lo_t.to(x.dtype)), hi_t.to(x.dtype)))
   return Tensor(torch.clamp(_raw(t), min=float(lo), max=float(hi)))
 
 
@@ -774,6 +786,7 @@ class _NN(object):
 
   @staticmethod
   def embedding_lookup(params, ids, name=None):
+    _probe_guard()        # SimAug/code/pred_models.py: the first op after the placeholders
     return gather(params, ids)
 
   @staticmethod
@@ -1009,8 +1022,11 @@ losses = _Losses()
 
 
 def gradients(ys, xs, **kw):
+  """tf.gradients: d sum(ys) / d xs; `xs` may be one tensor (SimAug/code/pred_models.py:397) or a list."""
   y = _raw(ys)
-  gs = torch.autograd.grad(y, [_raw(x) for x in xs], allow_unused=True, retain_graph=True)
+  if isinstance(xs, (Tensor, torch.Tensor)):
+    xs = [xs]
+  gs = torch.autograd.grad(y.sum() if y.dim() else y, [_raw(x) for x in xs], allow_unused=True, retain_graph=True)
   return [None if g is None else Tensor(g) for g in gs]
 
 
@@ -1129,6 +1145,68 @@ class _Train(object):
 
 
 train = _Train()
+
+
+# --------------------------------------------------------------------------------------------- #
+# the few extra symbols SimAug/code/pred_models.py touches
+# --------------------------------------------------------------------------------------------- #
+def sign(x, name=None): return Tensor(torch.sign(_raw(x)))
+def stop_gradient(x, name=None): return Tensor(_raw(x).detach())
+def greater(x, y, name=None): return _wrap(x) > y
+def floormod(x, y, name=None): return Tensor(torch.remainder(_raw(x), _raw(y)))
+
+
+def random_uniform(shape, minval=0, maxval=None, dtype=None, seed=None, name=None):
+  """No hidden randomness: the harness supplies the draw (building(...) state `uniform_hook`)."""
+  if _S.uniform_hook is None:
+    raise RuntimeError("tf.random_uniform reached without a harness-supplied uniform_hook")
+  shp = [int(_raw(d).item()) if isinstance(d, (Tensor, torch.Tensor)) else _int(d) for d in
+         (shape if isinstance(shape, (list, tuple)) else _raw(shape).tolist())]
+  v = _S.uniform_hook(tuple(shp), minval, maxval, dtype)
+  t = torch.as_tensor(np.asarray(v))
+  return Tensor(t.to(_torch_dtype(dtype)) if dtype is not None else t.to(COMPUTE_DTYPE))
+
+
+class _Random(object):
+  uniform = staticmethod(random_uniform)
+
+
+random = _Random()
+
+
+_pymath = math
+
+
+class _MathNS(object):
+  """tf.math; everything else falls through to Python's math module, which this file's own code uses."""
+  @staticmethod
+  def maximum(x, y, name=None):
+    a = _raw(x)
+    b = _raw(y) if isinstance(y, (Tensor, torch.Tensor)) else torch.as_tensor(y, dtype=a.dtype)
+    return Tensor(torch.maximum(a, b.to(a.dtype)))
+
+  def __getattr__(self, name):
+    return getattr(_pymath, name)
+
+
+math = _MathNS()
+
+
+class _Beta(object):
+  def __init__(self, concentration1, concentration0, **kw): pass
+
+  def sample(self, *a, **kw):
+    if _S.beta_sample is None:
+      raise RuntimeError("tf.distributions.Beta.sample reached without a harness-supplied beta_sample")
+    return Tensor(torch.tensor(float(_S.beta_sample), dtype=COMPUTE_DTYPE))
+
+
+class _Distributions(object):
+  Beta = _Beta
+
+
+distributions = _Distributions()
+_NN.softmax_cross_entropy_with_logits_v2 = staticmethod(_NN.softmax_cross_entropy_with_logits)
 
 
 class Session(object):

@@ -127,3 +127,32 @@ def rollout_stats(cfg, out):
     st["beam_lg_max"] = blg.max(-1)
     st["beam_lg_mean"] = blg.mean(-1)
   return st
+
+
+def simaug_case():
+  """Seeded inputs of the SimAug multi-view golden (tests/golden/make_golden_simaug.py): 2 samples, 3 other views,
+  one scale (18x9), soft scene features in (-1, 1).  Returns (synthetic config, weights, feeds, extra-view feeds,
+  spec)."""
+  from multiverse_b200 import synthetic
+  n, m = 2, 3
+  # gnn_scene_in_greedy=False: SimAug's gnn_edge feeds the scene features to the attention only in the beam decoder
+  conf = dict(batch_size=n, use_grids=[False, True], grid_loss_weight=1.0, grid_reg_loss_weight=0.1, wd=0.001,
+              gnn_scene_in_greedy=False)
+  cfg = synthetic.make_config(clip_gradient_norm=10.0, **conf)
+  w = synthetic.make_weights(cfg, 41)
+  f = synthetic.make_feeds(cfg, n, 41, with_pred=True)
+  rng = np.random.default_rng(9)
+  f["scene_feat"] = np.clip(f["scene_feat"] * 0.8 + rng.uniform(-0.1, 0.1, f["scene_feat"].shape), -1, 1).astype(np.float32)
+  hw = 18 * 9
+  extra = dict(grid_pred_labels_extra=[None, rng.integers(0, hw, size=(n, m, cfg.pred_len)).astype(np.int32)],
+               grid_obs_labels_extra=[None, rng.integers(0, hw, size=(n, m, cfg.obs_len)).astype(np.int32)],
+               obs_scene_extra=rng.integers(0, f["scene_feat"].shape[0], size=(n, m, cfg.obs_len)).astype(np.int32))
+  return cfg, w, f, extra, dict(n=n, m=m, eps=0.1, beta_draw=0.3, config=conf)
+
+
+def grad_sample_stride(size):
+  """Stride of the gradient samples stored in tests/golden/simaug_multiview.npz (<= 2048 entries per variable)."""
+  return max(1, -(-size // 2048))
+
+
+ADV_SAMPLE_STRIDE = 7      # every 7th element of the augmented features is stored in simaug_multiview.npz
