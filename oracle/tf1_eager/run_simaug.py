@@ -79,12 +79,15 @@ def _feed_values(model, config, feeds, extra):
   put(model.is_train, True)
   put(model.obs_scene, np.asarray(feeds["obs_scene"], np.int32))
   put(model.scene_feat, torch.tensor(np.asarray(feeds["scene_feat"], np.float64), requires_grad=True))
-  put(model.obs_scene_extra, np.asarray(extra["obs_scene_extra"], np.int32))
+  if extra is not None:
+    put(model.obs_scene_extra, np.asarray(extra["obs_scene_extra"], np.int32))
   for j, (h, w) in enumerate(config.scene_grids):
     put(model.grid_obs_labels[j], np.asarray(feeds["grid_obs_labels"][j], np.int32))
     put(model.grid_obs_regress[j], np.asarray(feeds["grid_obs_regress"][j], np.float64))
     put(model.grid_pred_labels_T[j], np.asarray(feeds["grid_pred_labels"][j], np.float64))
     put(model.grid_pred_regress[j], np.asarray(feeds["grid_pred_regress"][j], np.float64))
+    if extra is None:
+      continue
     # the other views (:250-267): labels of their own; the regression arrays are tiled from the main view
     obs_l = extra["grid_obs_labels_extra"][j]
     pred_l = extra["grid_pred_labels_extra"][j]
@@ -150,4 +153,51 @@ def multiview(cfg, weights, feeds, extra, m, exp, eps, beta, with_trainer=False,
                         for v, g in zip(names, gs)}
   finally:
     ref.Model.multiview_augmentation = orig
+  return out
+
+
+def adversarial(cfg, weights, feeds, eps, target_offsets, fgsm=True, step_size=None, num_iter=1, mixup_beta=None,
+                **config_kw):
+  """Builds the SimAug Model in training mode with adv_train (white_box_attack, :60-170, called at :289-301) and
+  returns dict(adv_final [N*T,SH,SW,SC], target_label [N,Tp], loss, losses).  The random target offsets
+  (create_random_target's tf.random_uniform ints, :66-72) are injected (`target_offsets` int [N,Tp] in [1, h*w));
+  the start is the clean input (adv_start_from_clean_prob = 1); `mixup_beta` switches use_mixup on with that draw."""
+  tf, ref = load()
+  config = simaug_config(cfg, tf, 1, 1, eps, multiview_train=False, adv_train=True, adv_use_fgsm=bool(fgsm),
+                         adv_step_size=step_size if step_size is not None else eps / 4, adv_num_iter=num_iter,
+                         use_mixup=mixup_beta is not None, **config_kw)
+  rec = {}
+  orig = ref.white_box_attack
+
+  def recording(*a, **kw):
+    out = orig(*a, **kw)
+    rec["adv_final"], rec["target_label"] = out
+    return out
+
+  ref.white_box_attack = recording
+  try:
+    with tf.building(weights, feed=None):
+      probe = ref.Model.__new__(ref.Model)
+      try:
+        probe.__init__(config, config.modelname)
+        raise AssertionError("probe pass was expected to stop at the first op after the placeholders")
+      except tf._StopBuild:
+        pass
+    vals = _feed_values(probe, config, feeds, None)
+    with tf.building(weights, feed=lambda idx, name, dtype, shape: vals[idx], requires_grad=True) as state:
+      state.beta_sample = mixup_beta
+      draws = [np.asarray(target_offsets)]
+
+      def uniform_hook(shape, minval, maxval, dtype):
+        if dtype is not None and "int" in str(dtype):
+          v = draws.pop(0)
+          assert tuple(v.shape) == tuple(shape) and v.min() >= minval and v.max() < maxval
+          return v
+        return np.zeros(shape)            # start noise: drawn (:76-79) but unused with adv_start_from_clean_prob = 1
+      state.uniform_hook = uniform_hook
+      model = ref.get_model(config, 0)
+      out = dict(adv_final=RR._np(rec["adv_final"]), target_label=RR._np(rec["target_label"]),
+                 loss=float(RR._np(model.loss)), losses=[float(RR._np(l)) for l in model.pred_grid_loss])
+  finally:
+    ref.white_box_attack = orig
   return out

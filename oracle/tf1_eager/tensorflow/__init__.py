@@ -663,11 +663,19 @@ def cond(pred, true_fn=None, false_fn=None, name=None, **kw):
   return true_fn() if bool(p.item()) else false_fn()
 
 
-def while_loop(cond, body, loop_vars, back_prop=True, **kw):  # pylint: disable=redefined-outer-name
+def while_loop(cond, body, loop_vars, back_prop=True, maximum_iterations=None, **kw):  # pylint: disable=redefined-outer-name
+  """tf.while_loop, eagerly; `maximum_iterations` bounds the trip count (SimAug's PGD loop has cond = True, :146-155).
+  A body that returns one tensor for a one-element loop_vars list is accepted, and the single result is returned
+  unwrapped for a single loop variable - as TF does."""
   vars_ = list(loop_vars)
-  while bool(_raw(cond(*vars_)).item()):
-    vars_ = list(body(*vars_))
-  return vars_
+  it = 0
+  def truth(v):
+    return bool(v) if isinstance(v, (bool, np.bool_)) else bool(_raw(v).item())
+  while truth(cond(*vars_)) and (maximum_iterations is None or it < int(maximum_iterations)):
+    out = body(*vars_)
+    vars_ = list(out) if isinstance(out, (list, tuple)) else [out]
+    it += 1
+  return vars_ if len(vars_) != 1 or isinstance(loop_vars, tuple) else vars_[0]
 
 
 class TensorArray(object):

@@ -100,3 +100,38 @@ def test_reference_execution_matches_golden_and_oracle_pipeline(exp):
       assert np.abs(samp_g - g["exp3_grad_sample/" + k]).max() <= 1e-6 * scale + 1e-12, k
     print("exp 3: oracle vs reference-exec gradients, worst relative error %.2e over %d variables" % (worst, len(ref["grads"])))
     assert worst < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fgsm", "pgd_mixup"])
+def test_white_box_attack_reference_execution_matches_oracle_pipeline(mode):
+  """white_box_attack (SimAug/code/pred_models.py:60-170) as executed from the reference file - targeted FGSM, and PGD
+  (tf.while_loop, 3 iterations, bounds around the clean input) followed by the mixup with the clean input - against
+  the same update rule driven by the oracle's autograd input gradient: what multiverse_b200/simaug.py::
+  white_box_attack and mvb_adv_step / mvb_mix implement (GPU: test_simaug_scene_input_gradient_and_attack)."""
+  cfg, w, f, extra, spec = cases.simaug_case()
+  rcfg = R.default_config(**spec["config"])
+  n, eps, hw = spec["n"], spec["eps"], 18 * 9
+  rng = np.random.default_rng(3)
+  off = rng.integers(1, hw, size=(n, cfg.pred_len)).astype(np.int32)
+  fgsm = mode == "fgsm"
+  step, iters, beta = (eps, 1, None) if fgsm else (0.03, 3, 0.4)
+  ref = RS.adversarial(rcfg, w, f, eps, off, fgsm=fgsm, step_size=step, num_iter=iters, mixup_beta=beta)
+  target = (f["grid_pred_labels"][1].astype(np.int64) + off) % hw                       # create_random_target
+  assert np.array_equal(ref["target_label"], target) and not (target == f["grid_pred_labels"][1]).any()
+  # the oracle's pipeline: one private frame per (sample, step) row, like the reference's [N*T,SH,SW,SC] input
+  t_obs = cfg.obs_len
+  x = f["scene_feat"].astype(np.float64)[f["obs_scene"]].reshape((n * t_obs,) + f["scene_feat"].shape[1:])
+  rows = dict(f, obs_scene=np.arange(n * t_obs, dtype=np.int32).reshape(n, t_obs))
+  lo, hi = np.clip(x - eps, -1, 1), np.clip(x + eps, -1, 1)
+  adv = x.copy()
+  for _ in range(iters):
+    g = RT.scene_input_grad(rcfg, w, dict(rows, scene_feat=adv), target, 1)
+    adv = np.minimum(np.maximum(adv - step * np.sign(g), lo), hi)
+  if beta is not None:
+    adv = x * beta + adv * (1 - beta)
+  d = np.abs(adv - ref["adv_final"])
+  print("white_box_attack %s: %.6f of the pixels equal, max diff %.3g" % (mode, (d <= 1e-9).mean(), d.max()))
+  assert (d <= 1e-9).mean() > 0.9999 and d.max() <= 2 * eps + 1e-9
+  # and the training tower on the attacked features
+  _, losses, _, _ = RT.loss_and_grads(rcfg, w, dict(rows, scene_feat=ref["adv_final"]))
+  assert np.abs(np.array(losses) - np.array(ref["losses"])).max() < 1e-9 * max(ref["losses"])
