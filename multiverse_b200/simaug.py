@@ -9,7 +9,7 @@ this library with the scene CNN's input gradient switched on (``mvb_scene_conv_b
 convolution).  The update itself is ``mvb_adv_step`` / ``mvb_mix``.  SimAug's model differs from Multiverse's in one place that matters here: its ``gnn_edge`` (:1213-1226) uses the scene
 features only in the beam decoder, so the training tower's graph attention runs over h alone - build the TrainEngine
 with ``cfg.gnn_scene_in_greedy = False`` (the drop-in Model does it for configs that carry SimAug's flags).  Pinned
-on an execution of the reference file (oracle/tf1_eager/run_simaug.py, tests/golden/simaug_multiview.npz).
+on an execution of the reference file (tests/golden/simaug_multiview.npz and its generating script).
 Random draws (start noise, random target
 offsets, the Beta mixup weight) come from a numpy Generator - TensorFlow's random streams cannot be reproduced.
 

@@ -5,7 +5,8 @@ directory.  TEST INFRASTRUCTURE.
 What runs is the reference's own code: ``Model.__init__`` with ``multiview_train`` (placeholders :191-267, the
 augmentation branch :304-310), ``multiview_augmentation`` (:346-541: tiling over the views, ``one_step_attack`` with
 ``build_tower`` + ``tf.gradients`` w.r.t. the input features, per-view losses, ``multiview_exp`` selection, focal
-weights, Beta mixup), ``build_tower`` (:544-, incl. the mixed observed class maps of experiment 3) and ``build_loss``
+weights, Beta mixup), ``white_box_attack`` (:60-170: random targets, FGSM / the PGD ``tf.while_loop``, mixup - see
+``adversarial()`` below), ``build_tower`` (:544-, incl. the mixed observed class maps of experiment 3) and ``build_loss``
 (:1340-, incl. the mixed labels and ``double_weighting``).  Only the TensorFlow ops underneath are emulated (torch
 fp64, autograd for ``tf.gradients``); TensorFlow's random streams cannot be reproduced, so the two draws on this path
 are injected: the Beta sample (``beta``) and - with ``adv_start_from_clean_prob >= 1`` - no uniform start noise.
