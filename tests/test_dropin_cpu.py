@@ -609,3 +609,59 @@ def test_session_run_leaves_no_reference_cycle_on_the_results(monkeypatch):
     assert all(r() is None for r in refs)
   finally:
     gc.enable()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/SimAug/code/pred_models.py"), reason="reference tree not mounted")
+def test_multiview_feed_dict_equals_simaugs(dropin, tmp_path, monkeypatch):
+  """The extra-view feeds of a multiview_train batch (obs_scene_extra, grid_*_extra) against SimAug's own
+  Model.get_feed_dict (SimAug/code/pred_models.py:1457-1560) executed on our Model instance, key for key on every
+  placeholder that method fills."""
+  tf, pm = dropin
+  import types
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "oracle", "tf1_eager"))
+  spec = importlib.util.spec_from_file_location("ref_simaug_pred_models", "/root/reference/SimAug/code/pred_models.py")
+  saved = sys.modules.get("tensorflow")
+  ref = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(ref)                    # binds `tf` to whatever `tensorflow` is importable: only numpy is used below
+  if saved is not None:
+    sys.modules["tensorflow"] = saved
+  tf.reset_default_graph()
+  args, cfg = make_args(tmp_path, use_grids=[False, True])
+  n, m = args.batch_size, 3
+  args.is_train, args.multiview_train, args.multiview_max_num, args.multiview_exp = True, True, m, 1
+  model = pm.get_model(args, gpuid=0)
+  rng = np.random.default_rng(5)
+  ns = len(cfg.scene_grids)
+  t_in, t_pred = cfg.obs_len, cfg.pred_len
+  def views(count):
+    return [np.stack([rng.integers(0, h * w, count) for (h, w) in cfg.scene_grids]) for _ in range(m)]
+  data = dict(obs_grid_class=[np.stack([rng.integers(0, h * w, t_in) for (h, w) in cfg.scene_grids]) for _ in range(n)],
+              pred_grid_class=[np.stack([rng.integers(0, h * w, t_pred) for (h, w) in cfg.scene_grids]) for _ in range(n)],
+              batch_scene_feat=rng.random((7, cfg.scene_h, cfg.scene_w, cfg.scene_class)).astype(np.float32),
+              batch_obs_scene=rng.integers(0, 7, (n, t_in, 1)),
+              batch_extra_obs_scene=rng.integers(0, 7, (n, m, t_in, 1)), extra=[])
+  for j, (h, w) in enumerate(cfg.scene_grids):
+    data["obs_grid_target_all_%d" % j] = [rng.standard_normal((t_in, h, w, 2)).astype(np.float32) for _ in range(n)]
+    data["pred_grid_target_all_%d" % j] = [rng.standard_normal((t_pred, h, w, 2)).astype(np.float32) for _ in range(n)]
+  for i in range(n):
+    ex = dict(obs_grid_class=views(t_in), pred_grid_class=views(t_pred))
+    for j, (h, w) in enumerate(cfg.scene_grids):
+      ex["obs_grid_target_all_%d" % j] = [rng.standard_normal((t_in, h, w, 2)).astype(np.float32) for _ in range(m)]
+      ex["pred_grid_target_all_%d" % j] = [rng.standard_normal((t_pred, h, w, 2)).astype(np.float32) for _ in range(m)]
+    data["extra"].append(ex)
+  batch = types.SimpleNamespace(data=data)
+  theirs = ref.Model.get_feed_dict(model, batch, is_train=True)
+  ours = model.get_feed_dict(batch, is_train=True)
+  assert set(theirs) <= set(ours)
+  extra_keys = [model.obs_scene_extra] + [p for j in range(ns) if cfg_use(args, j) for p in
+                                          (model.grid_obs_labels_extra[j], model.grid_pred_labels_T_extra[j],
+                                           model.grid_pred_regress_extra[j], model.grid_obs_regress_extra[j])]
+  assert all(k in theirs for k in extra_keys)
+  for k in theirs:
+    a, b = np.asarray(ours[k]), np.asarray(theirs[k])
+    assert a.shape == b.shape, k
+    assert np.array_equal(a.astype(np.float64), b.astype(np.float64)), k
+
+
+def cfg_use(args, j):
+  return bool(args.use_grids[j])
